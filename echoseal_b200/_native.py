@@ -1,0 +1,57 @@
+"""ctypes loader for the C-ABI library (include/echoseal_b200.h).
+
+There is NO CPU fallback: if `libechoseal_b200.so` is missing or CUDA is unavailable the product
+path raises.  Build the library with `python -c "import __graft_entry__ as g; g.build()"` (nvcc,
+sm_100a)."""
+from __future__ import annotations
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libechoseal_b200.so")
+_lib = None
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NativeError(
+                f"{LIB_PATH} not built — run __graft_entry__.build(); echoseal_b200 has no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        L.es_last_error.restype = C.c_char_p
+        L.es_scl_scratch_bytes.restype = C.c_size_t
+        _lib = L
+    return _lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = lib().es_last_error().decode("utf-8", "replace")
+        raise NativeError(f"{what} failed rc={rc}: {msg}")
+
+
+def ptr(t):
+    """device (or host) pointer of a torch tensor / None."""
+    if t is None:
+        return C.c_void_p(0)
+    return C.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise NativeError("tensor must live on a CUDA device (no CPU fallback)")
+        if not t.is_contiguous():
+            raise NativeError("tensor must be contiguous")

@@ -1,0 +1,657 @@
+// echoseal_b200/csrc/scl.cu — batched CRC-aided SCL decoder for Polar(1024,K)+CRC-8, list size <= 8,
+// and the matching encoder, hand-written for sm_100a.
+//
+// Replaces rtwm/fastpolar.py:254-359 (PolarCode.decode), :237-252 (encode), :362-389 (CRC-8, transform)
+// behind rtwm/polar_fast.py:26-87.  Arithmetic is IEEE double with the reference's exact formulas:
+//   f = logaddexp(a,b) - logaddexp(0,a+b)          (rtwm/fastpolar.py:18-23; LLR = log P1/P0)
+//   g = b + (1-2u) a                                (rtwm/fastpolar.py:26-29)
+//   penalty(l,bit) = log1p(exp(-|l|)) (+|l| if bit != [l>=0])   (rtwm/fastpolar.py:32-40)
+//   frozen bits are penalised too; candidates are ranked by (metric, path order, bit) = the reference's
+//   stable sort over candidates appended in (path idx, bit 0, bit 1) order (rtwm/fastpolar.py:288-299).
+//
+// Mapping (B200-first):
+//   * one THREAD per list path, 8 lanes per codeword, 4 codewords per warp, 4 warps per CTA,
+//     persistent grid sized to the SM count x resident CTAs;  warps never wait on each other.
+//   * LLR tree: level l (1..10) keeps only its CURRENT node (2^(10-l) doubles) per path slot.
+//     levels >= S live in shared memory, levels < S in an L2-resident global scratch, both laid out
+//     [element][codeword(4)][slot(8)] so a warp access is one 256-byte row (conflict-free / coalesced).
+//   * lazy copy without reference counts: every path rewrites a level at the same bit index, so a path
+//     always writes its OWN slot and a clone only copies a 30-bit word of per-level slot pointers.
+//   * partial sums are bit-packed: levels 6..10 in one register, levels 1..5 as pointer-indirected
+//     32-bit words; the root (codeword estimate) is transformed back to u-hat at the end.
+//   * list pruning: 16 candidates ranked with 8-wide warp shuffles; survivors/clones matched by ballots.
+#include "common.cuh"
+#include <math_constants.h>
+#include "phi_tables.h"
+#include "phi_impl.h"
+#include <string.h>
+
+namespace es {
+
+__constant__ uint32_t c_frozen[32];      // bit (i&31) of word (i>>5): 1 = frozen
+__constant__ uint16_t c_datapos[1024];   // ascending un-frozen positions (K entries used)
+__constant__ int c_K;                    // info + CRC bits
+
+static int g_code_ready = 0;
+static int g_K = 0;
+
+constexpr double LOGE2 = 0.693147180559945309417232121458176568;
+
+// ---------------------------------------------------------------------------------------------
+// arithmetic
+// ---------------------------------------------------------------------------------------------
+// phi(d) = log1p(exp(-d)), d >= 0: branch-free table-driven double routine (phi_impl.h), < 1.4 ulp —
+// the same accuracy class as the reference's libm composition, a quarter of the instructions.
+// numpy's npy_logaddexp: x==y -> x+ln2 ; else max + log1p(exp(-|x-y|))
+__device__ __forceinline__ double np_logaddexp(double x, double y, uint32_t tab)
+{
+    const double d = x - y;
+    const double mx = (d > 0.0) ? x : y;
+    const double r = mx + phi_fast(fabs(d), tab);
+    return (x == y) ? (x + LOGE2) : r;
+}
+
+__device__ __forceinline__ double fcomb(double a, double b, uint32_t tab)
+{
+    return np_logaddexp(a, b, tab) - np_logaddexp(0.0, a + b, tab);
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-lane state
+// ---------------------------------------------------------------------------------------------
+struct SclParams {
+    const float* llr;        // [nrows][1024] float32 channel LLRs
+    const int32_t* index;    // optional list of codeword ids to decode (nullptr = 0..ncw-1)
+    int ncw;                 // number of codewords to decode (length of index if given)
+    int neg_mode;            // 0: codeword w = +row w ; 1: codeword w = (w&1 ? - : +) row (w>>1)
+    int list_size;           // 1..8
+    double* scratch;         // global alpha scratch, per warp
+    size_t scratch_stride;   // doubles per warp
+    const double* phi_tab;   // 896 doubles (phi_impl.h layout)
+    uint8_t* path_payload;   // [ncw_total][list_size][ (K-8)/8 ]
+    uint8_t* path_crc;       // [ncw_total][list_size]
+    double* path_metric;     // [ncw_total][list_size]
+    int32_t* npaths;         // [ncw_total]
+};
+
+struct Lane {
+    double* sa;          // shared alpha rows (+gbase)
+    uint32_t* sb;        // shared beta words (row stride 32 words)
+    double* ga;          // global alpha rows, levels 1..S-1 (+gbase)
+    double* g0;          // global level-0 copy of this warp's 4 codewords, [k][4] (+codeword)
+    uint32_t tab;        // shared-window address of the phi tables
+    int lane, p, gbase;
+    double m, leaf;
+    uint32_t ptr, bptr, bs;
+    int ord;
+    bool active;
+};
+
+struct LvlRef { double* base; int stride; };
+
+// element k of level lv in `slot` lives at ref.base[k * ref.stride]
+template <int S> __device__ __forceinline__ LvlRef lvl_ref(const Lane& L, int lv, int slot)
+{
+    LvlRef r;
+    if (lv == 0) { r.base = L.g0; r.stride = 4; }
+    else if (lv >= S) { r.base = L.sa + (((1 << (11 - S)) - (1 << (11 - lv))) * 32) + slot; r.stride = 32; }
+    else { r.base = L.ga + ((1024 - (1 << (11 - lv))) * 32) + slot; r.stride = 32; }
+    return r;
+}
+
+// the one place the f-combine is evaluated: dst[k*ds] = f(a[k*ss], b[k*ss]), k < count
+__device__ __noinline__ void f_loop(const double* a, const double* b, int ss, double* dst, int ds, int count,
+                                    uint32_t tab)
+{
+#pragma unroll 1
+    for (int k = 0; k < count; ++k) {
+        const double r = fcomb(a[k * ss], b[k * ss], tab);
+        dst[k * ds] = r;
+    }
+}
+
+template <int S>
+__device__ __forceinline__ void f_level(Lane& L, int lv)   // 2 <= lv <= 10, parent in own slot
+{
+    const int s = 1 << (10 - lv);
+    const LvlRef src = lvl_ref<S>(L, lv - 1, L.p);
+    const LvlRef dst = lvl_ref<S>(L, lv, L.p);
+    f_loop(src.base, src.base + s * src.stride, src.stride, dst.base, dst.stride, s, L.tab);
+    L.ptr = (L.ptr & ~(7u << (3 * (lv - 1)))) | ((uint32_t)L.p << (3 * (lv - 1)));
+}
+
+// g over one level l0 (1..10): dst[k] = par[k+s] +- par[k], sign from the left-child partial sums
+template <int S>
+__device__ __forceinline__ void g_level(Lane& L, int l0)
+{
+    const int s = 1 << (10 - l0);
+    const int ps = (l0 >= 2) ? ((L.ptr >> (3 * (l0 - 2))) & 7) : 0;
+    const LvlRef src = lvl_ref<S>(L, l0 - 1, ps);
+    const LvlRef dst = lvl_ref<S>(L, l0, L.p);
+    const double* pa = src.base;
+    const double* pb = src.base + s * src.stride;
+    if (s <= 16) {   // levels 6..10: bits in the bs register
+        const uint32_t bits = L.bs >> s;
+#pragma unroll 1
+        for (int k = 0; k < s; ++k) {
+            const double a = pa[k * src.stride], b = pb[k * src.stride];
+            dst.base[k * dst.stride] = ((bits >> k) & 1u) ? (b - a) : (b + a);
+        }
+    } else {         // levels 1..5: bits in pointer-indirected words
+        const int bsl = (L.bptr >> (3 * (l0 - 1))) & 7;
+        const uint32_t* bw = L.sb + ((1 << (5 - l0)) - 1) * 32 + L.gbase + bsl;
+#pragma unroll 1
+        for (int kw = 0; kw < (s >> 5); ++kw) {
+            const uint32_t word = bw[kw * 32];
+#pragma unroll 8
+            for (int kk = 0; kk < 32; ++kk) {
+                const int k = kw * 32 + kk;
+                const double a = pa[k * src.stride], b = pb[k * src.stride];
+                dst.base[k * dst.stride] = ((word >> kk) & 1u) ? (b - a) : (b + a);
+            }
+        }
+    }
+    L.ptr = (L.ptr & ~(7u << (3 * (l0 - 1)))) | ((uint32_t)L.p << (3 * (l0 - 1)));
+}
+
+// bit 0: only one path exists; the 8 lanes of the codeword share the work, everything goes to slot 0
+template <int S>
+__device__ __forceinline__ void spine(Lane& L)
+{
+#pragma unroll 1
+    for (int lv = 1; lv <= 10; ++lv) {
+        const int s = 1 << (10 - lv);
+        const LvlRef src = lvl_ref<S>(L, lv - 1, 0);
+        const LvlRef dst = lvl_ref<S>(L, lv, 0);
+        const int count = (s > L.p) ? ((s - L.p + 7) >> 3) : 0;
+        const double* pa = src.base + L.p * src.stride;
+        f_loop(pa, pa + s * src.stride, 8 * src.stride, dst.base + L.p * dst.stride, 8 * dst.stride, count, L.tab);
+        __syncwarp();
+    }
+    L.ptr = 0;
+}
+
+template <int S>
+__device__ __forceinline__ void llr_update(Lane& L, int i)
+{
+    const int l0 = 11 - __ffs(i);    // i > 0: level of the g node
+    g_level<S>(L, l0);
+#pragma unroll 1
+    for (int lv = l0 + 1; lv <= 10; ++lv) f_level<S>(L, lv);
+}
+
+__device__ __forceinline__ int nth_set8(uint32_t mask, int n)
+{
+    int r = 0;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+        const bool set = (mask >> b) & 1u;
+        if (set && n == 0) r = b;
+        n -= set ? 1 : 0;
+    }
+    return r;
+}
+
+// information-bit step: rank the 2*np candidates, keep list_size, clone into free lanes.
+// pen0/pen1 = penalties of deciding 0 / 1 (rtwm/fastpolar.py:32-40).
+__device__ __forceinline__ int info_step(Lane& L, int list_size, double pen0, double pen1)
+{
+    const unsigned full = 0xffffffffu;
+    const double m0 = L.m + pen0, m1 = L.m + pen1;
+    int r0 = 0, r1 = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int aj = __shfl_sync(full, (int)L.active, j, 8);
+        const double m0j = __shfl_sync(full, m0, j, 8);
+        const double m1j = __shfl_sync(full, m1, j, 8);
+        const int oj = __shfl_sync(full, L.ord, j, 8);
+        if (aj) {
+            const bool lt = oj < L.ord, le = oj <= L.ord;
+            r0 += (m0j < m0) + (m1j < m0) + ((m0j == m0) && lt) + ((m1j == m0) && lt);
+            r1 += (m0j < m1) + (m1j < m1) + ((m0j == m1) && le) + ((m1j == m1) && lt);
+        }
+    }
+    const bool s0 = L.active && (r0 < list_size);
+    const bool s1 = L.active && (r1 < list_size);
+    const uint32_t cm = (__ballot_sync(full, s0 && s1) >> L.gbase) & 0xffu;
+    const uint32_t fm = (__ballot_sync(full, !(s0 || s1)) >> L.gbase) & 0xffu;
+    // clone source for free lanes (j-th free lane takes the j-th clone)
+    const int jfree = __popc(fm & ((1u << L.p) - 1u));
+    const bool take = !(s0 || s1) && (jfree < __popc(cm));
+    const int src = take ? nth_set8(cm, jfree) : L.p;
+    const double cm1 = __shfl_sync(full, m1, src, 8);
+    const int cr1 = __shfl_sync(full, r1, src, 8);
+    const uint32_t cptr = __shfl_sync(full, L.ptr, src, 8);
+    const uint32_t cbptr = __shfl_sync(full, L.bptr, src, 8);
+    const uint32_t cbs = __shfl_sync(full, L.bs, src, 8);
+    int bit = 0;
+    if (s0) { L.m = m0; L.ord = r0; bit = 0; }
+    else if (s1) { L.m = m1; L.ord = r1; bit = 1; }
+    else if (take) { L.m = cm1; L.ord = cr1; L.ptr = cptr; L.bptr = cbptr; L.bs = cbs; bit = 1; L.active = true; }
+    else { L.active = false; }
+    return bit;
+}
+
+// partial-sum update after deciding `bit` at index i (see tests/model_scl_lanes.py for the model)
+__device__ __forceinline__ void beta_update(Lane& L, int i, int bit, uint32_t* xroot)
+{
+    if ((i & 1) == 0) { L.bs = (L.bs & ~2u) | ((uint32_t)bit << 1); return; }
+    const int t1 = __ffs(~i) - 1;            // trailing ones, 1..10
+    uint32_t X = (uint32_t)bit;
+    const int tr = t1 < 5 ? t1 : 5;
+    for (int j = 0; j < tr; ++j) {
+        const int s = 1 << j;
+        const uint32_t Lb = (L.bs >> s) & ((1u << s) - 1u);
+        X = (Lb ^ X) | (X << s);
+    }
+    if (t1 <= 4) {
+        const int s = 1 << t1;
+        L.bs = (L.bs & ~(((1u << s) - 1u) << s)) | (X << s);
+    } else if (t1 == 5) {
+        L.sb[L.lane] = X;                       // level 5, word offset 0
+        L.bptr = (L.bptr & ~(7u << 12)) | ((uint32_t)L.p << 12);
+    } else {
+        const int lstar = 10 - t1;              // 4..0
+        uint32_t* D = (lstar == 0) ? (xroot + L.lane) : (L.sb + ((1 << (5 - lstar)) - 1) * 32 + L.lane);
+        D[0] = X;
+        int n = 1;
+        for (int l = 5; l > lstar; --l) {
+            const int bsl = (L.bptr >> (3 * (l - 1))) & 7;
+            const uint32_t* Lp = L.sb + ((1 << (5 - l)) - 1) * 32 + L.gbase + bsl;
+            for (int w = 0; w < n; ++w) {
+                const uint32_t x = D[w * 32];
+                D[(n + w) * 32] = x;
+                D[w * 32] = x ^ Lp[w * 32];
+            }
+            n <<= 1;
+        }
+        if (lstar > 0) L.bptr = (L.bptr & ~(7u << (3 * (lstar - 1)))) | ((uint32_t)L.p << (3 * (lstar - 1)));
+    }
+}
+
+__device__ __forceinline__ uint32_t xform_word(uint32_t x)
+{
+    x ^= (x >> 1) & 0x55555555u;
+    x ^= (x >> 2) & 0x33333333u;
+    x ^= (x >> 4) & 0x0f0f0f0fu;
+    x ^= (x >> 8) & 0x00ff00ffu;
+    x ^= (x >> 16) & 0x0000ffffu;
+    return x;
+}
+
+__device__ __forceinline__ uint8_t crc8_step_bit(uint8_t reg, uint32_t bit)
+{
+    reg ^= (uint8_t)(bit << 7);
+    return (reg & 0x80) ? (uint8_t)((reg << 1) ^ 0x07) : (uint8_t)(reg << 1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// list decoder kernel: W warps per CTA share the phi tables; each warp decodes 4 codewords at a time
+// ---------------------------------------------------------------------------------------------
+template <int S> struct SclLayout {
+    static constexpr int AROWS = (1 << (11 - S)) - 2 + 1;            // levels S..9 + one row for the leaves
+    static constexpr int WARP_BYTES = AROWS * 256 + 31 * 128;
+    static constexpr int TAB_BYTES = PHI_TAB_DOUBLES * 8;
+    static constexpr size_t G_ROWS = 1024 - (1 << (11 - S));           // global rows, levels 1..S-1
+    static constexpr size_t G_DOUBLES = G_ROWS * 32 + 1024 * 4;        // + level-0 copy [1024][4]
+    static_assert(AROWS * 256 >= 32 * 128, "alpha region must hold the root partial sums");
+};
+
+template <int S, int W>
+__global__ void __launch_bounds__(W * 32) scl_list_kernel(SclParams P)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    using LY = SclLayout<S>;
+    const unsigned full = 0xffffffffu;
+    // phi tables -> shared
+    {
+        double* st = reinterpret_cast<double*>(smem_raw);
+        for (int q = threadIdx.x; q < PHI_TAB_DOUBLES; q += W * 32) st[q] = P.phi_tab[q];
+        __syncthreads();
+    }
+    const int warp = threadIdx.x >> 5;
+    unsigned char* wbase = smem_raw + LY::TAB_BYTES + (size_t)warp * LY::WARP_BYTES;
+    uint32_t* xroot = reinterpret_cast<uint32_t*>(wbase);               // aliases alpha (dead by then)
+
+    Lane L;
+    L.lane = threadIdx.x & 31;
+    L.p = L.lane & 7;
+    L.gbase = L.lane & ~7;
+    L.tab = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    L.sa = reinterpret_cast<double*>(wbase) + L.gbase;
+    L.sb = reinterpret_cast<uint32_t*>(wbase + (size_t)LY::AROWS * 256);
+    const int gwarp = blockIdx.x * W + warp;
+    double* gscr = P.scratch + (size_t)gwarp * P.scratch_stride;
+    L.ga = gscr + L.gbase;
+    L.g0 = gscr + LY::G_ROWS * 32 + (L.lane >> 3);
+    const int K = c_K;
+    const int nbytes = (K - 8) >> 3;
+    const int ngroups = (P.ncw + 3) >> 2;
+    const int nwarps = gridDim.x * W;
+
+    for (int grp = gwarp; grp < ngroups; grp += nwarps) {
+        const int j = grp * 4 + (L.lane >> 3);
+        const bool valid = j < P.ncw;
+        const int jj = valid ? j : (P.ncw - 1);
+        const int w = P.index ? P.index[jj] : jj;
+        {   // level 0: widen this warp's 4 codewords to double, [k][4]
+            const int row = P.neg_mode ? (w >> 1) : w;
+            const float sgn = (P.neg_mode && (w & 1)) ? -1.0f : 1.0f;
+            const float* src = P.llr + (size_t)row * 1024;
+            double* dst = gscr + LY::G_ROWS * 32 + (L.lane >> 3);
+#pragma unroll 4
+            for (int k = L.p; k < 1024; k += 8) dst[k * 4] = (double)(sgn * __ldg(src + k));
+        }
+        L.m = 0.0; L.leaf = 0.0; L.ptr = 0; L.bptr = 0; L.bs = 0; L.ord = 0;
+        L.active = (L.p == 0);
+        __syncwarp();
+
+#pragma unroll 1
+        for (int i = 0; i < 1024; ++i) {
+            if (i == 0) spine<S>(L);
+            else llr_update<S>(L, i);
+            __syncwarp();
+            // leaf LLR of this lane's path: level-10 row, slot from the pointer word (own slot unless i == 0)
+            {
+                const int ls = (i == 0) ? 0 : L.p;
+                L.leaf = lvl_ref<S>(L, 10, ls).base[0];
+            }
+            const double al = fabs(L.leaf);
+            const double ph = phi_fast(al, L.tab);
+            const bool pref1 = (L.leaf >= 0.0);
+            const double pen0 = pref1 ? (ph + al) : ph;    // deciding 0 against a non-negative LLR costs |l| more
+            const double pen1 = pref1 ? ph : (ph + al);
+            int bit = 0;
+            const bool frozen = (c_frozen[i >> 5] >> (i & 31)) & 1u;
+            if (frozen) {
+                if (L.active) L.m += pen0;
+            } else {
+                bit = info_step(L, P.list_size, pen0, pen1);
+            }
+            beta_update(L, i, bit, xroot);
+            __syncwarp();
+        }
+
+        // ---- output: rank by (metric, order) = sorted(paths, key=metric) (rtwm/fastpolar.py:335)
+        int rank = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int aj = __shfl_sync(full, (int)L.active, q, 8);
+            const double mj = __shfl_sync(full, L.m, q, 8);
+            const int oj = __shfl_sync(full, L.ord, q, 8);
+            if (aj && (mj < L.m || (mj == L.m && oj < L.ord))) ++rank;
+        }
+        const uint32_t am = (__ballot_sync(full, L.active) >> L.gbase) & 0xffu;
+        const int np = __popc(am);
+        if (!L.active) rank = np + __popc((~am & 0xffu) & ((1u << L.p) - 1u));
+
+        // u-hat = transform(x-hat), in registers
+        uint32_t x[32];
+#pragma unroll
+        for (int q = 0; q < 32; ++q) x[q] = xform_word(xroot[q * 32 + L.lane]);
+#pragma unroll
+        for (int h = 1; h < 32; h <<= 1)
+#pragma unroll
+            for (int q = 0; q < 32; ++q)
+                if (!(q & h)) x[q] ^= x[q + h];
+#pragma unroll
+        for (int q = 0; q < 32; ++q) xroot[q * 32 + L.lane] = x[q];
+
+        const bool wr = valid && (rank < P.list_size);
+        const size_t orow = (size_t)w * P.list_size + (size_t)(wr ? rank : 0);
+        uint8_t* out = P.path_payload + orow * nbytes;
+        uint8_t crcreg = 0, crcbits = 0;
+        uint32_t acc = 0;
+#pragma unroll 1
+        for (int q = 0; q < K; ++q) {
+            const int pos = c_datapos[q];
+            const uint32_t b = (xroot[(pos >> 5) * 32 + L.lane] >> (pos & 31)) & 1u;
+            if (q < K - 8) {
+                acc = (acc << 1) | b;
+                crcreg = crc8_step_bit(crcreg, b);
+                if ((q & 7) == 7 && wr && L.active) out[q >> 3] = (uint8_t)(acc & 0xffu);
+            } else {
+                crcbits = (uint8_t)((crcbits << 1) | b);
+            }
+        }
+        if (wr) {
+            P.path_crc[orow] = (L.active && crcreg == crcbits) ? 1 : 0;
+            P.path_metric[orow] = L.active ? L.m : CUDART_INF;
+        }
+        if (valid && L.p == 0) P.npaths[w] = np;
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// hard-decision fast path (rtwm/fastpolar.py:261-276): one warp per codeword
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t warp_transform(uint32_t x, int lane)
+{
+    x = xform_word(x);
+#pragma unroll
+    for (int h = 1; h < 32; h <<= 1) {
+        const uint32_t v = __shfl_down_sync(0xffffffffu, x, h);
+        if (!(lane & h)) x ^= v;
+    }
+    return x;
+}
+
+__global__ void __launch_bounds__(128) scl_hard_kernel(const float* __restrict__ llr, int ncw, int neg_mode,
+                                                       uint8_t* __restrict__ hard_payload,
+                                                       uint8_t* __restrict__ hard_crc)
+{
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= ncw) return;
+    const int row = neg_mode ? (w >> 1) : w;
+    const float sgn = (neg_mode && (w & 1)) ? -1.0f : 1.0f;
+    const float* src = llr + (size_t)row * 1024;
+    const int K = c_K;
+    const int nbytes = (K - 8) >> 3;
+    uint32_t x = 0;
+#pragma unroll 4
+    for (int it = 0; it < 32; ++it) {
+        const uint32_t bal = __ballot_sync(full, sgn * __ldg(src + it * 32 + lane) > 0.0f);
+        if (lane == it) x = bal;
+    }
+    x = warp_transform(x, lane);
+    uint8_t* out = hard_payload + (size_t)w * nbytes;
+    uint8_t crcreg = 0, crcbits = 0;
+    const int nchunk = (K + 31) >> 5;
+    for (int c = 0; c < nchunk; ++c) {
+        const int q = c * 32 + lane;
+        const int pos = (q < K) ? c_datapos[q] : 0;
+        const uint32_t wv = __shfl_sync(full, x, pos >> 5);
+        const uint32_t b = (q < K) ? ((wv >> (pos & 31)) & 1u) : 0u;
+        const uint32_t word = __brev(__ballot_sync(full, b));   // bit q -> MSB-first
+#pragma unroll
+        for (int bb = 0; bb < 4; ++bb) {
+            const int byte_idx = c * 4 + bb;
+            const uint8_t byte = (uint8_t)(word >> (24 - 8 * bb));
+            if (byte_idx < nbytes) {
+                if (lane == bb) out[byte_idx] = byte;
+#pragma unroll
+                for (int t = 7; t >= 0; --t) crcreg = crc8_step_bit(crcreg, (byte >> t) & 1u);
+            } else if (byte_idx == nbytes) {
+                crcbits = byte;
+            }
+        }
+    }
+    if (lane == 0) hard_crc[w] = (crcreg == crcbits) ? 1 : 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// encoder (rtwm/fastpolar.py:237-252): one warp per payload, output one byte per code bit
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) polar_encode_kernel(const uint8_t* __restrict__ payload, int n,
+                                                           uint8_t* __restrict__ cw_bits,
+                                                           uint32_t* __restrict__ cw_words)
+{
+    __shared__ uint32_t su[4][32];
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+    const int w = blockIdx.x * (blockDim.x >> 5) + wl;
+    if (w >= n) return;
+    const int K = c_K;
+    const int nbytes = (K - 8) >> 3;
+    const uint8_t* src = payload + (size_t)w * nbytes;
+    // CRC-8 over the payload bits, MSB first (every lane computes it; 55 bytes)
+    uint8_t crc = 0;
+    for (int b = 0; b < nbytes; ++b) {
+        const uint8_t byte = __ldg(src + b);
+#pragma unroll
+        for (int t = 7; t >= 0; --t) crc = crc8_step_bit(crc, (byte >> t) & 1u);
+    }
+    su[wl][lane] = 0;
+    __syncwarp();
+    for (int q = lane; q < K; q += 32) {
+        const int byte_idx = q >> 3;
+        const uint8_t byte = (byte_idx < nbytes) ? __ldg(src + byte_idx) : crc;
+        const uint32_t b = (byte >> (7 - (q & 7))) & 1u;
+        const int pos = c_datapos[q];
+        if (b) atomicOr(&su[wl][pos >> 5], 1u << (pos & 31));
+    }
+    __syncwarp();
+    const uint32_t x = warp_transform(su[wl][lane], lane);
+    if (cw_words) cw_words[(size_t)w * 32 + lane] = x;
+    if (cw_bits) {
+        uint8_t* out = cw_bits + (size_t)w * 1024;
+        for (int it = 0; it < 32; ++it) {
+            const uint32_t wv = __shfl_sync(full, x, it);
+            out[it * 32 + lane] = (uint8_t)((wv >> lane) & 1u);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+constexpr int SCL_S = 6;   // first LLR-tree level kept in shared memory
+constexpr int SCL_W = 4;   // warps per CTA (share the phi tables)
+using SclLY = SclLayout<SCL_S>;
+
+static size_t scl_smem_bytes() { return (size_t)SclLY::TAB_BYTES + (size_t)SCL_W * SclLY::WARP_BYTES; }
+static size_t scl_scratch_doubles_per_warp() { return SclLY::G_DOUBLES; }
+
+static int g_scl_ctas_per_sm = 0;
+static double* g_phi_tab_dev = nullptr;
+
+static int scl_configure()
+{
+    if (g_scl_ctas_per_sm) return ES_OK;
+    auto kern = scl_list_kernel<SCL_S, SCL_W>;
+    ES_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scl_smem_bytes()));
+    ES_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                    cudaSharedmemCarveoutMaxShared));
+    int nb = 0;
+    ES_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, SCL_W * 32, scl_smem_bytes()));
+    if (nb < 1) { set_error("scl_list_kernel does not fit on an SM"); return ES_EINVAL; }
+    // phi tables (phi_impl.h layout)
+    static double tab[PHI_TAB_DOUBLES];
+    for (int j = 0; j < PHI_NE; ++j) {
+        memcpy(&tab[PHI_OFF_EXP_HI + j], &PHI_EXP_HI[j], 8);
+        memcpy(&tab[PHI_OFF_EXP_LO + j], &PHI_EXP_LO[j], 8);
+    }
+    for (int i = 0; i < PHI_NL; ++i) {
+        memcpy(&tab[PHI_OFF_INVC + i], &PHI_INVC[i], 8);
+        memcpy(&tab[PHI_OFF_LOGC_HI + i], &PHI_LOGC_HI[i], 8);
+        memcpy(&tab[PHI_OFF_LOGC_LO + i], &PHI_LOGC_LO[i], 8);
+    }
+    ES_CUDA_OK(cudaMalloc(&g_phi_tab_dev, sizeof(tab)));
+    ES_CUDA_OK(cudaMemcpy(g_phi_tab_dev, tab, sizeof(tab), cudaMemcpyHostToDevice));
+    g_scl_ctas_per_sm = nb;
+    return ES_OK;
+}
+
+}  // namespace es
+
+using namespace es;
+
+extern "C" {
+
+int es_polar_set_code(const uint8_t* frozen_host, int K)
+{
+    if (!frozen_host || K < 16 || K > 1024 || (K & 7)) { set_error("es_polar_set_code: bad K=%d", K); return ES_EINVAL; }
+    uint32_t words[32] = {0};
+    uint16_t pos[1024] = {0};
+    int n = 0;
+    for (int i = 0; i < 1024; ++i) {
+        if (frozen_host[i]) words[i >> 5] |= 1u << (i & 31);
+        else { if (n < 1024) pos[n] = (uint16_t)i; ++n; }
+    }
+    if (n != K) { set_error("es_polar_set_code: %d unfrozen positions != K=%d", n, K); return ES_EINVAL; }
+    ES_CUDA_OK(cudaMemcpyToSymbol(c_frozen, words, sizeof(words)));
+    ES_CUDA_OK(cudaMemcpyToSymbol(c_datapos, pos, sizeof(pos)));
+    ES_CUDA_OK(cudaMemcpyToSymbol(c_K, &K, sizeof(int)));
+    g_code_ready = 1;
+    g_K = K;
+    return ES_OK;
+}
+
+int es_scl_grid_ctas(void)
+{
+    if (scl_configure() != ES_OK) return -1;
+    return sm_count() * g_scl_ctas_per_sm;
+}
+
+int es_scl_ctas_per_sm(void)
+{
+    if (scl_configure() != ES_OK) return -1;
+    return g_scl_ctas_per_sm;
+}
+
+size_t es_scl_scratch_bytes(void)
+{
+    const int ctas = es_scl_grid_ctas();
+    if (ctas < 0) return 0;
+    return (size_t)ctas * SCL_W * scl_scratch_doubles_per_warp() * sizeof(double);
+}
+
+int es_scl_hard(const float* llr, int ncw, int neg_mode, uint8_t* hard_payload, uint8_t* hard_crc, void* stream)
+{
+    if (!g_code_ready) { set_error("es_scl_hard: call es_polar_set_code first"); return ES_ENOTREADY; }
+    if (ncw <= 0) return ES_OK;
+    const int wpb = 4;
+    scl_hard_kernel<<<(ncw + wpb - 1) / wpb, wpb * 32, 0, (cudaStream_t)stream>>>(llr, ncw, neg_mode, hard_payload, hard_crc);
+    ES_CUDA_OK(cudaGetLastError());
+    return ES_OK;
+}
+
+int es_scl_list(const float* llr, const int32_t* index, int ncw, int neg_mode, int list_size,
+                void* scratch, size_t scratch_bytes,
+                uint8_t* path_payload, uint8_t* path_crc, double* path_metric, int32_t* npaths, void* stream)
+{
+    if (!g_code_ready) { set_error("es_scl_list: call es_polar_set_code first"); return ES_ENOTREADY; }
+    if (list_size < 1 || list_size > 8) { set_error("es_scl_list: list_size %d not in 1..8", list_size); return ES_EINVAL; }
+    if (ncw <= 0) return ES_OK;
+    int rc = scl_configure();
+    if (rc != ES_OK) return rc;
+    const int ngroups = (ncw + 3) / 4;
+    int ctas = sm_count() * g_scl_ctas_per_sm;
+    const int need_ctas = (ngroups + SCL_W - 1) / SCL_W;
+    if (ctas > need_ctas) ctas = need_ctas;
+    const size_t need = (size_t)ctas * SCL_W * scl_scratch_doubles_per_warp() * sizeof(double);
+    if (!scratch || scratch_bytes < need) { set_error("es_scl_list: scratch %zu < %zu bytes", scratch_bytes, need); return ES_EINVAL; }
+    SclParams P;
+    P.llr = llr; P.index = index; P.ncw = ncw; P.neg_mode = neg_mode; P.list_size = list_size;
+    P.scratch = (double*)scratch; P.scratch_stride = scl_scratch_doubles_per_warp();
+    P.phi_tab = g_phi_tab_dev;
+    P.path_payload = path_payload; P.path_crc = path_crc; P.path_metric = path_metric; P.npaths = npaths;
+    scl_list_kernel<SCL_S, SCL_W><<<ctas, SCL_W * 32, scl_smem_bytes(), (cudaStream_t)stream>>>(P);
+    ES_CUDA_OK(cudaGetLastError());
+    return ES_OK;
+}
+
+int es_polar_encode(const uint8_t* payload, int n, uint8_t* cw_bits, uint32_t* cw_words, void* stream)
+{
+    if (!g_code_ready) { set_error("es_polar_encode: call es_polar_set_code first"); return ES_ENOTREADY; }
+    if (n <= 0) return ES_OK;
+    const int wpb = 4;
+    polar_encode_kernel<<<(n + wpb - 1) / wpb, wpb * 32, 0, (cudaStream_t)stream>>>(payload, n, cw_bits, cw_words);
+    ES_CUDA_OK(cudaGetLastError());
+    return ES_OK;
+}
+
+}  // extern "C"

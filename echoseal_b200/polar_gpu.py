@@ -1,0 +1,101 @@
+"""Batched device-side polar codec: thin tensor-level wrappers over the C-ABI
+(es_polar_set_code / es_scl_hard / es_scl_list / es_polar_encode).  Used by
+echoseal_b200.polar_fast (reference-shaped API) and by the detector / embedder."""
+from __future__ import annotations
+import ctypes as C
+import numpy as np
+import torch
+
+from . import _native as N
+from .polar_tables import frozen_mask
+
+_code_key = None
+_scratch = {}
+
+
+def set_code(N_: int = 1024, K: int = 448):
+    """Upload the frozen mask for Polar(N_,K) (rtwm/fastpolar.py:219-229)."""
+    global _code_key
+    dev = torch.cuda.current_device()
+    if _code_key == (N_, K, dev):
+        return
+    fr = np.ascontiguousarray(frozen_mask(N_, K).astype(np.uint8))
+    N.check(N.lib().es_polar_set_code(fr.ctypes.data_as(C.c_void_p), C.c_int(K)), "es_polar_set_code")
+    _code_key = (N_, K, dev)
+
+
+def _get_scratch(device):
+    key = (device.index if device.index is not None else torch.cuda.current_device())
+    s = _scratch.get(key)
+    if s is None:
+        nbytes = int(N.lib().es_scl_scratch_bytes())
+        if nbytes <= 0:
+            N.check(-1, "es_scl_scratch_bytes")
+        s = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        _scratch[key] = s
+    return s
+
+
+def hard_decide(llr: torch.Tensor, neg_mode: int = 0, K: int = 448):
+    """Hard-decision fast path for every codeword.  llr float32[rows,1024] on the GPU.
+    Returns (payload uint8[ncw,(K-8)/8], crc_ok uint8[ncw]); ncw = rows*(2 if neg_mode else 1)."""
+    N.require_cuda(llr)
+    if llr.dtype != torch.float32 or llr.dim() != 2 or llr.shape[1] != 1024:
+        raise ValueError("llr must be float32 [rows,1024]")
+    set_code(1024, K)
+    ncw = llr.shape[0] * (2 if neg_mode else 1)
+    pay = torch.empty((ncw, (K - 8) // 8), dtype=torch.uint8, device=llr.device)
+    crc = torch.empty((ncw,), dtype=torch.uint8, device=llr.device)
+    N.check(N.lib().es_scl_hard(N.ptr(llr), C.c_int(ncw), C.c_int(neg_mode), N.ptr(pay), N.ptr(crc),
+                                N.stream_ptr()), "es_scl_hard")
+    return pay, crc
+
+
+def list_decode(llr: torch.Tensor, list_size: int = 8, neg_mode: int = 0, index: torch.Tensor | None = None,
+                K: int = 448):
+    """CA-SCL list stage.  Returns dict(payload uint8[ncw,L,55], crc uint8[ncw,L], metric f64[ncw,L],
+    npaths i32[ncw]) — paths in ascending-metric order; rows not listed in `index` are left zero/inf."""
+    N.require_cuda(llr, index)
+    if llr.dtype != torch.float32 or llr.dim() != 2 or llr.shape[1] != 1024:
+        raise ValueError("llr must be float32 [rows,1024]")
+    if not (1 <= list_size <= 8):
+        raise ValueError("list_size must be in 1..8 on the B200 path")
+    set_code(1024, K)
+    dev = llr.device
+    ncw_total = llr.shape[0] * (2 if neg_mode else 1)
+    nb = (K - 8) // 8
+    out = dict(
+        payload=torch.zeros((ncw_total, list_size, nb), dtype=torch.uint8, device=dev),
+        crc=torch.zeros((ncw_total, list_size), dtype=torch.uint8, device=dev),
+        metric=torch.full((ncw_total, list_size), float("inf"), dtype=torch.float64, device=dev),
+        npaths=torch.zeros((ncw_total,), dtype=torch.int32, device=dev),
+    )
+    if index is not None:
+        if index.dtype != torch.int32:
+            raise ValueError("index must be int32")
+        n = int(index.numel())
+    else:
+        n = ncw_total
+    if n == 0:
+        return out
+    scratch = _get_scratch(dev)
+    N.check(N.lib().es_scl_list(N.ptr(llr), N.ptr(index), C.c_int(n), C.c_int(neg_mode), C.c_int(list_size),
+                                N.ptr(scratch), C.c_size_t(scratch.numel()),
+                                N.ptr(out["payload"]), N.ptr(out["crc"]), N.ptr(out["metric"]),
+                                N.ptr(out["npaths"]), N.stream_ptr()), "es_scl_list")
+    return out
+
+
+def encode(payload: torch.Tensor, K: int = 448, want_bits: bool = True, want_words: bool = False):
+    """payload uint8[n,(K-8)/8] on the GPU -> code bits uint8[n,1024] (and/or packed uint32[n,32],
+    bit (i&31) of word (i>>5) = code bit i)."""
+    N.require_cuda(payload)
+    if payload.dtype != torch.uint8 or payload.dim() != 2 or payload.shape[1] != (K - 8) // 8:
+        raise ValueError(f"payload must be uint8 [n,{(K - 8) // 8}]")
+    set_code(1024, K)
+    n = payload.shape[0]
+    bits = torch.empty((n, 1024), dtype=torch.uint8, device=payload.device) if want_bits else None
+    words = torch.empty((n, 32), dtype=torch.int32, device=payload.device) if want_words else None
+    N.check(N.lib().es_polar_encode(N.ptr(payload), C.c_int(n), N.ptr(bits), N.ptr(words), N.stream_ptr()),
+            "es_polar_encode")
+    return bits, words

@@ -39,12 +39,42 @@
 
 static const double LOGE2 = 0.693147180559945309417232121458176568;
 
+/*
+ * phi(d) = log1p(exp(-d)), d >= 0.  Default build: glibc, i.e. the reference's arithmetic.
+ * -DORACLE_PHI_FAST builds the "device arithmetic model" instead (liboracle_fastphi.so): the
+ * very same IEEE operation sequence the CUDA kernel runs (echoseal_b200/csrc/phi_impl.h), so
+ * that library predicts the GPU's path lists bit-for-bit, ties included; the difference between
+ * the two libraries isolates the effect of <1.4-ulp libm differences (hard part 1).
+ */
+#ifdef ORACLE_PHI_FAST
+#include "../echoseal_b200/csrc/phi_tables.h"
+#include "../echoseal_b200/csrc/phi_impl.h"
+static double g_phi_tab[PHI_TAB_DOUBLES];
+static int g_phi_init = 0;
+static void phi_init(void)
+{
+    for (int j = 0; j < PHI_NE; j++) {
+        g_phi_tab[PHI_OFF_EXP_HI + j] = PHI_U2D(PHI_EXP_HI[j]);
+        g_phi_tab[PHI_OFF_EXP_LO + j] = PHI_U2D(PHI_EXP_LO[j]);
+    }
+    for (int i = 0; i < PHI_NL; i++) {
+        g_phi_tab[PHI_OFF_INVC + i] = PHI_U2D(PHI_INVC[i]);
+        g_phi_tab[PHI_OFF_LOGC_HI + i] = PHI_U2D(PHI_LOGC_HI[i]);
+        g_phi_tab[PHI_OFF_LOGC_LO + i] = PHI_U2D(PHI_LOGC_LO[i]);
+    }
+    g_phi_init = 1;
+}
+static inline double phi(double d) { return phi_fast(d, g_phi_tab); }
+#else
+static inline double phi(double d) { return log1p(exp(-d)); }
+#endif
+
 static inline double np_logaddexp(double x, double y)
 {
     if (x == y) return x + LOGE2;
     double d = x - y;
-    if (d > 0) return x + log1p(exp(-d));
-    if (d <= 0) return y + log1p(exp(d));
+    if (d > 0) return x + phi(d);
+    if (d <= 0) return y + phi(-d);
     return d; /* NaN */
 }
 
@@ -56,7 +86,7 @@ static inline double f_comb(double a, double b)
 static inline double penalty(double l, int bit)
 {
     double al = fabs(l);
-    double p = log1p(exp(-al));
+    double p = phi(al);
     int pref = (l >= 0.0) ? 1 : 0;
     if (bit != pref) p += al;
     return p;
@@ -181,6 +211,9 @@ int es_oracle_scl_decode(const double *llr, const uint8_t *frozen, int K, int L,
                          double *stats)
 {
     if (L < 1 || L > LMAX) return -1;
+#ifdef ORACLE_PHI_FAST
+    if (!g_phi_init) phi_init();
+#endif
     int ninfo = K - 8;
     /* fast path candidate */
     {
@@ -311,6 +344,9 @@ int es_oracle_scl_decode_batch(const float *llr, int ncw, const uint8_t *frozen,
 {
     batch_t b = { llr, ncw, frozen, K, L, flags, hard_info, hard_crc, path_info, path_metric, path_crc,
                   npaths, stats, 0, 0 };
+#ifdef ORACLE_PHI_FAST
+    if (!g_phi_init) phi_init();
+#endif
     if (nthreads < 1) nthreads = 1;
     if (nthreads > 256) nthreads = 256;
     if (nthreads == 1) { batch_worker(&b); return b.rc; }

@@ -14,12 +14,16 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
+_LIB_FAST = None
 
 
 def build(force: bool = False) -> str:
     so = os.path.join(_HERE, "_build", "liboracle.so")
+    so2 = os.path.join(_HERE, "_build", "liboracle_fastphi.so")
     srcs = [os.path.join(_HERE, f) for f in ("polar_oracle.c", "dsp_oracle.c")]
-    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+    srcs += [os.path.join(_HERE, "..", "echoseal_b200", "csrc", f) for f in ("phi_impl.h", "phi_tables.h")]
+    if force or not os.path.exists(so) or not os.path.exists(so2) or \
+            any(os.path.getmtime(s) > min(os.path.getmtime(so), os.path.getmtime(so2)) for s in srcs):
         subprocess.check_call(["make", "-s", "-C", _HERE])
     return so
 
@@ -31,6 +35,16 @@ def lib():
         _LIB.es_oracle_scl_decode_batch.restype = C.c_int
         _LIB.es_oracle_crc8.restype = C.c_uint8
     return _LIB
+
+
+def lib_fastphi():
+    """Device-arithmetic model: the oracle decoder built with the CUDA kernel's phi() routine."""
+    global _LIB_FAST
+    if _LIB_FAST is None:
+        build()
+        _LIB_FAST = C.CDLL(os.path.join(_HERE, "_build", "liboracle_fastphi.so"))
+        _LIB_FAST.es_oracle_scl_decode_batch.restype = C.c_int
+    return _LIB_FAST
 
 
 def _p(a):
@@ -45,7 +59,7 @@ def frozen_default(K: int = 448) -> np.ndarray:
 
 
 def scl_batch(llr: np.ndarray, L: int = 8, K: int = 448, frozen=None, skip_on_hard_crc: bool = False,
-              threads: int | None = None):
+              threads: int | None = None, device_arith: bool = False):
     """llr float32[ncw,1024] -> dict(hard_info, hard_crc, path_info, path_metric, path_crc, npaths, stats)."""
     llr = np.ascontiguousarray(llr, dtype=np.float32).reshape(-1, 1024)
     ncw = llr.shape[0]
@@ -57,7 +71,7 @@ def scl_batch(llr: np.ndarray, L: int = 8, K: int = 448, frozen=None, skip_on_ha
         path_crc=np.zeros((ncw, L), np.int32), npaths=np.zeros(ncw, np.int32),
         stats=np.zeros((ncw, 4), np.float64),
     )
-    rc = lib().es_oracle_scl_decode_batch(_p(llr), C.c_int(ncw), _p(fr), C.c_int(K), C.c_int(L),
+    rc = (lib_fastphi() if device_arith else lib()).es_oracle_scl_decode_batch(_p(llr), C.c_int(ncw), _p(fr), C.c_int(K), C.c_int(L),
                                           C.c_int(1 if skip_on_hard_crc else 0), C.c_int(threads or (os.cpu_count() or 1)),
                                           _p(out["hard_info"]), _p(out["hard_crc"]), _p(out["path_info"]),
                                           _p(out["path_metric"]), _p(out["path_crc"]), _p(out["npaths"]),
