@@ -47,13 +47,14 @@ static inline uint64_t PHI_D2U(double x) { uint64_t u; memcpy(&u, &x, 8); return
 static inline double PHI_U2D(uint64_t u) { double x; memcpy(&x, &u, 8); return x; }
 #endif
 
-// tables: [0,64) exp hi, [64,128) exp lo, [128,384) invc, [384,640) logc hi, [640,896) logc lo
-#define PHI_TAB_DOUBLES 896
+// tables: [0,64) exp hi, [64,128) exp lo, then 257-entry log tables (entry 256 serves u == 2.0)
+#define PHI_NLT 257
 #define PHI_OFF_EXP_HI 0
 #define PHI_OFF_EXP_LO 64
 #define PHI_OFF_INVC 128
-#define PHI_OFF_LOGC_HI 384
-#define PHI_OFF_LOGC_LO 640
+#define PHI_OFF_LOGC_HI (128 + PHI_NLT)
+#define PHI_OFF_LOGC_LO (128 + 2 * PHI_NLT)
+#define PHI_TAB_DOUBLES (128 + 3 * PHI_NLT + 1)   /* 900, even */
 
 PHI_FN double phi_fast(double d, phi_tab_t tab)
 {
@@ -61,15 +62,18 @@ PHI_FN double phi_fast(double d, phi_tab_t tab)
     const double LN2HIN = PHI_U2D(0x3f862e42fef00000ULL);    // ln2/64, 33 significant bits
     const double LN2LON = PHI_U2D(0x3d7473de6af278edULL);
     const double SHIFT = 6755399441055744.0;                 // 1.5 * 2^52
-    // ---- t = exp(-d)
-    const double dd = d < 1500.0 ? d : 1500.0;               // exp(-1500) == 0 either way
+    // ---- t = exp(-|d|); |d| clamped to < 1401 on the high word (exp(-1400) == 0 either way)
+    const uint64_t db = PHI_D2U(d);
+    uint32_t dhi = (uint32_t)(db >> 32) & 0x7fffffffu;
+    dhi = dhi < 0x4095e000u ? dhi : 0x4095e000u;             // 0x4095e000_00000000 = 1400.0
+    const double dd = PHI_U2D(((uint64_t)dhi << 32) | (db & 0xffffffffu));
     double kd = PHI_FMA(-dd, INVLN2N, SHIFT);
     const int32_t ki = (int32_t)(uint32_t)PHI_D2U(kd);
     kd -= SHIFT;
     double r = PHI_FMA(kd, -LN2HIN, -dd);
     r = PHI_FMA(kd, -LN2LON, r);
     const int j = ki & 63;
-    const int e = ki >> 6;                                    // <= 0
+    const int e = ki >> 6;                                    // -2020 .. 0
     const double r2 = r * r;
     double q = PHI_FMA(r, 1.0 / 720.0, 1.0 / 120.0);
     q = PHI_FMA(r, q, 1.0 / 24.0);
@@ -78,14 +82,15 @@ PHI_FN double phi_fast(double d, phi_tab_t tab)
     const double p = PHI_FMA(r2, q, r);                       // exp(r) - 1
     const double th = PHI_LD(tab, PHI_OFF_EXP_HI + j), tl = PHI_LD(tab, PHI_OFF_EXP_LO + j);
     const double tm = th + PHI_FMA(th, p, tl);                // 2^(j/64) * exp(r), in [1,2)
-    const int e1 = e > -1000 ? e : -1000;
-    double t = PHI_U2D(PHI_D2U(tm) + ((uint64_t)(int64_t)e1 << 52));
-    const int e2 = e - e1;                                    // 0 unless the result is < 2^-1000
-    t *= PHI_U2D((uint64_t)(1023 + (e2 > -1022 ? e2 : -1022)) << 52);
+    // t = tm * 2^e in two exact steps (2^e1 on the exponent field, 2^e2 as a factor): the product with
+    // 2^e2 is folded into the two fmas below, so a subnormal t is rounded exactly once
+    const int e1 = e >> 1, e2 = e - e1;                       // both >= -1010
+    const double t1 = PHI_U2D(PHI_D2U(tm) + ((uint64_t)(int64_t)e1 << 52));
+    const double s2 = PHI_U2D((uint64_t)(1023 + e2) << 52);
     // ---- log1p(t), 0 <= t <= 1
-    const double u = 1.0 + t;
-    const double c = t - (u - 1.0);
-    const int i = (int)((PHI_D2U(u) >> 44) & 255u);
+    const double u = PHI_FMA(t1, s2, 1.0);
+    const double c = PHI_FMA(t1, s2, -(u - 1.0));
+    const int i = (int)(uint32_t)(PHI_D2U(u) >> 44) - 0x3ff00;  // 0..255, 256 iff u == 2.0
     const double ic = PHI_LD(tab, PHI_OFF_INVC + i);
     const double rr = PHI_FMA(u, ic, -1.0);
     double w = PHI_FMA(rr, 1.0 / 7.0, -1.0 / 6.0);
@@ -94,8 +99,25 @@ PHI_FN double phi_fast(double d, phi_tab_t tab)
     w = PHI_FMA(rr, w, 1.0 / 3.0);
     w = PHI_FMA(rr, w, -0.5);
     const double ci = c * ic;                                 // c/u to first order ...
-    double tail = PHI_FMA(-ci, rr, ci) + PHI_LD(tab, PHI_OFF_LOGC_LO + i);   // ... times (1 - rr): second order matters for tiny t
+    double tail = PHI_FMA(-ci, rr, ci) + PHI_LD(tab, PHI_OFF_LOGC_LO + i);   // ... times (1 - rr)
     tail = PHI_FMA(rr * rr, w, tail);
-    const double res = PHI_LD(tab, PHI_OFF_LOGC_HI + i) + (rr + tail);
-    return (u >= 2.0) ? 0.693147180559945309417232121458176568 : res;
+    return PHI_LD(tab, PHI_OFF_LOGC_HI + i) + (rr + tail);
 }
+
+// fill `tab` (PHI_TAB_DOUBLES doubles) from the generated bit patterns in phi_tables.h
+#ifdef PHI_WANT_FILL
+static void phi_fill_table(double* tab)
+{
+    for (int j = 0; j < 64; ++j) { tab[PHI_OFF_EXP_HI + j] = 0; tab[PHI_OFF_EXP_LO + j] = 0; }
+    for (int j = 0; j < 64; ++j) {
+        memcpy(&tab[PHI_OFF_EXP_HI + j], &PHI_EXP_HI[j], 8);
+        memcpy(&tab[PHI_OFF_EXP_LO + j], &PHI_EXP_LO[j], 8);
+    }
+    for (int i = 0; i < PHI_NLT; ++i) {
+        memcpy(&tab[PHI_OFF_INVC + i], &PHI_INVC[i], 8);
+        memcpy(&tab[PHI_OFF_LOGC_HI + i], &PHI_LOGC_HI[i], 8);
+        memcpy(&tab[PHI_OFF_LOGC_LO + i], &PHI_LOGC_LO[i], 8);
+    }
+    tab[PHI_TAB_DOUBLES - 1] = 0.0;
+}
+#endif

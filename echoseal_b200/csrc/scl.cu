@@ -22,9 +22,10 @@
 //   * list pruning: 16 candidates ranked with 8-wide warp shuffles; survivors/clones matched by ballots.
 #include "common.cuh"
 #include <math_constants.h>
-#include "phi_tables.h"
-#include "phi_impl.h"
 #include <string.h>
+#include "phi_tables.h"
+#define PHI_WANT_FILL
+#include "phi_impl.h"
 
 namespace es {
 
@@ -45,10 +46,10 @@ constexpr double LOGE2 = 0.693147180559945309417232121458176568;
 // numpy's npy_logaddexp: x==y -> x+ln2 ; else max + log1p(exp(-|x-y|))
 __device__ __forceinline__ double np_logaddexp(double x, double y, uint32_t tab)
 {
+    // x == y needs no special case here: phi_fast(0) == ln2 exactly (table entry 256)
     const double d = x - y;
     const double mx = (d > 0.0) ? x : y;
-    const double r = mx + phi_fast(fabs(d), tab);
-    return (x == y) ? (x + LOGE2) : r;
+    return mx + phi_fast(d, tab);          // phi_fast takes |d| itself
 }
 
 __device__ __forceinline__ double fcomb(double a, double b, uint32_t tab)
@@ -99,15 +100,26 @@ template <int S> __device__ __forceinline__ LvlRef lvl_ref(const Lane& L, int lv
     return r;
 }
 
-// the one place the f-combine is evaluated: dst[k*ds] = f(a[k*ss], b[k*ss]), k < count
+// the one place the f-combine is evaluated: dst[k*ds] = f(a[k*ss], b[k*ss]), k < count.
+// Two elements per trip (4 independent phi chains) with the next pair's operands prefetched.
 __device__ __noinline__ void f_loop(const double* a, const double* b, int ss, double* dst, int ds, int count,
                                     uint32_t tab)
 {
+    int k = 0;
+    if (count >= 2) {
+        double a0 = a[0], b0 = b[0], a1 = a[ss], b1 = b[ss];
 #pragma unroll 1
-    for (int k = 0; k < count; ++k) {
-        const double r = fcomb(a[k * ss], b[k * ss], tab);
-        dst[k * ds] = r;
+        for (; k + 2 <= count; k += 2) {
+            const int kn = (k + 4 <= count) ? (k + 2) : k;      // prefetch (re-reads the last pair at the end)
+            const double na0 = a[kn * ss], nb0 = b[kn * ss], na1 = a[(kn + 1) * ss], nb1 = b[(kn + 1) * ss];
+            const double r0 = fcomb(a0, b0, tab);
+            const double r1 = fcomb(a1, b1, tab);
+            dst[k * ds] = r0;
+            dst[(k + 1) * ds] = r1;
+            a0 = na0; b0 = nb0; a1 = na1; b1 = nb1;
+        }
     }
+    if (k < count) dst[k * ds] = fcomb(a[k * ss], b[k * ss], tab);
 }
 
 template <int S>
@@ -137,18 +149,21 @@ __device__ __forceinline__ void g_level(Lane& L, int l0)
             const double a = pa[k * src.stride], b = pb[k * src.stride];
             dst.base[k * dst.stride] = ((bits >> k) & 1u) ? (b - a) : (b + a);
         }
-    } else {         // levels 1..5: bits in pointer-indirected words
+    } else {         // levels 1..5: bits in pointer-indirected words; 16 elements (32 loads) in flight
         const int bsl = (L.bptr >> (3 * (l0 - 1))) & 7;
         const uint32_t* bw = L.sb + ((1 << (5 - l0)) - 1) * 32 + L.gbase + bsl;
 #pragma unroll 1
-        for (int kw = 0; kw < (s >> 5); ++kw) {
-            const uint32_t word = bw[kw * 32];
-#pragma unroll 8
-            for (int kk = 0; kk < 32; ++kk) {
-                const int k = kw * 32 + kk;
-                const double a = pa[k * src.stride], b = pb[k * src.stride];
-                dst.base[k * dst.stride] = ((word >> kk) & 1u) ? (b - a) : (b + a);
+        for (int k0 = 0; k0 < s; k0 += 16) {
+            const uint32_t word = bw[(k0 >> 5) * 32] >> (k0 & 31);
+            double va[16], vb[16];
+#pragma unroll
+            for (int kk = 0; kk < 16; ++kk) {
+                va[kk] = pa[(k0 + kk) * src.stride];
+                vb[kk] = pb[(k0 + kk) * src.stride];
             }
+#pragma unroll
+            for (int kk = 0; kk < 16; ++kk)
+                dst.base[(k0 + kk) * dst.stride] = ((word >> kk) & 1u) ? (vb[kk] - va[kk]) : (vb[kk] + va[kk]);
         }
     }
     L.ptr = (L.ptr & ~(7u << (3 * (l0 - 1)))) | ((uint32_t)L.p << (3 * (l0 - 1)));
@@ -298,7 +313,7 @@ template <int S> struct SclLayout {
 };
 
 template <int S, int W>
-__global__ void __launch_bounds__(W * 32) scl_list_kernel(SclParams P)
+__global__ void __launch_bounds__(W * 32, 4) scl_list_kernel(SclParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using LY = SclLayout<S>;
@@ -357,7 +372,7 @@ __global__ void __launch_bounds__(W * 32) scl_list_kernel(SclParams P)
                 L.leaf = lvl_ref<S>(L, 10, ls).base[0];
             }
             const double al = fabs(L.leaf);
-            const double ph = phi_fast(al, L.tab);
+            const double ph = phi_fast(L.leaf, L.tab);
             const bool pref1 = (L.leaf >= 0.0);
             const double pen0 = pref1 ? (ph + al) : ph;    // deciding 0 against a non-negative LLR costs |l| more
             const double pen1 = pref1 ? ph : (ph + al);
@@ -550,15 +565,7 @@ static int scl_configure()
     if (nb < 1) { set_error("scl_list_kernel does not fit on an SM"); return ES_EINVAL; }
     // phi tables (phi_impl.h layout)
     static double tab[PHI_TAB_DOUBLES];
-    for (int j = 0; j < PHI_NE; ++j) {
-        memcpy(&tab[PHI_OFF_EXP_HI + j], &PHI_EXP_HI[j], 8);
-        memcpy(&tab[PHI_OFF_EXP_LO + j], &PHI_EXP_LO[j], 8);
-    }
-    for (int i = 0; i < PHI_NL; ++i) {
-        memcpy(&tab[PHI_OFF_INVC + i], &PHI_INVC[i], 8);
-        memcpy(&tab[PHI_OFF_LOGC_HI + i], &PHI_LOGC_HI[i], 8);
-        memcpy(&tab[PHI_OFF_LOGC_LO + i], &PHI_LOGC_LO[i], 8);
-    }
+    phi_fill_table(tab);
     ES_CUDA_OK(cudaMalloc(&g_phi_tab_dev, sizeof(tab)));
     ES_CUDA_OK(cudaMemcpy(g_phi_tab_dev, tab, sizeof(tab), cudaMemcpyHostToDevice));
     g_scl_ctas_per_sm = nb;

@@ -48,22 +48,11 @@ static const double LOGE2 = 0.693147180559945309417232121458176568;
  */
 #ifdef ORACLE_PHI_FAST
 #include "../echoseal_b200/csrc/phi_tables.h"
+#define PHI_WANT_FILL
 #include "../echoseal_b200/csrc/phi_impl.h"
 static double g_phi_tab[PHI_TAB_DOUBLES];
 static int g_phi_init = 0;
-static void phi_init(void)
-{
-    for (int j = 0; j < PHI_NE; j++) {
-        g_phi_tab[PHI_OFF_EXP_HI + j] = PHI_U2D(PHI_EXP_HI[j]);
-        g_phi_tab[PHI_OFF_EXP_LO + j] = PHI_U2D(PHI_EXP_LO[j]);
-    }
-    for (int i = 0; i < PHI_NL; i++) {
-        g_phi_tab[PHI_OFF_INVC + i] = PHI_U2D(PHI_INVC[i]);
-        g_phi_tab[PHI_OFF_LOGC_HI + i] = PHI_U2D(PHI_LOGC_HI[i]);
-        g_phi_tab[PHI_OFF_LOGC_LO + i] = PHI_U2D(PHI_LOGC_LO[i]);
-    }
-    g_phi_init = 1;
-}
+static void phi_init(void) { phi_fill_table(g_phi_tab); g_phi_init = 1; }
 static inline double phi(double d) { return phi_fast(d, g_phi_tab); }
 #else
 static inline double phi(double d) { return log1p(exp(-d)); }
