@@ -38,3 +38,71 @@ def detector_like_llr_set(n: int, seed: int = 11):
         else:
             out[i] = np.clip(rng.normal(0.0, 2.0, N), -12.0, 12.0).astype(np.float32)
     return out
+
+
+# ----------------------------------------------------------------------------------------------
+# RX / TX clips.  Built with oracle/tx_oracle.py, whose equality
+# with the reference embedder is asserted when the golden files are generated.
+# ----------------------------------------------------------------------------------------------
+FS = 48_000
+CLIP_SPECS = {
+    # name: (kind, key, seed, secs, start_ctr, slice)   slice = (embed_secs, offset) or None
+    "chirp_aa": ("chirp", bytes([0xAA]) * 32, 52, 3.0, 0, None),
+    "noise_44": ("noise", bytes([0x44]) * 32, 1, 3.0, 0, None),
+    "silence_ee": ("silence", bytes([0xEE]) * 32, 2, 3.0, 0, None),
+    "bench_17": ("noise", None, 17, 3.0, None, "bench"),
+    "bench_19": ("chirpmix", None, 19, 3.0, None, "bench"),
+    "plain_noise": ("noise", bytes([0x11]) * 32, 5, 3.0, None, "nowm"),
+    "short_1s": ("noise", bytes([0x22]) * 32, 6, 1.0, 0, None),
+}
+
+
+def bench_key(i: int) -> bytes:
+    import hashlib
+    return hashlib.sha256(b"echoseal-bench" + int(i).to_bytes(4, "big")).digest()
+
+
+def host_signal(kind: str, n: int, rng) -> np.ndarray:
+    t = np.arange(n, dtype=np.float64) / FS
+    T = n / FS
+    if kind == "chirp":
+        return (0.3 * np.cos(2 * np.pi * (300.0 * t + (3500.0 - 300.0) / (2 * T) * t * t))).astype(np.float32)
+    if kind == "noise":
+        return (0.05 * rng.standard_normal(n)).astype(np.float32)
+    if kind == "chirpmix":
+        c = 0.3 * np.cos(2 * np.pi * (300.0 * t + (3500.0 - 300.0) / (2 * T) * t * t))
+        return (c + 0.02 * rng.standard_normal(n)).astype(np.float32)
+    if kind == "silence":
+        return np.zeros(n, np.float32)
+    raise ValueError(kind)
+
+
+def make_clip(name: str, embedder_factory=None):
+    """Returns (audio float32[n], key32).  embedder_factory(key, seed) -> object with .frame_ctr and
+    .process(x); defaults to the TX oracle with seeded randomness."""
+    kind, key, seed, secs, start_ctr, mode = CLIP_SPECS[name]
+    return make_clip_spec(kind, key, seed, secs, start_ctr, mode, embedder_factory)
+
+
+def make_clip_spec(kind, key, seed, secs, start_ctr, mode, embedder_factory=None):
+    if embedder_factory is None:
+        from oracle import tx_oracle as txo
+        embedder_factory = lambda k, s: txo.Embedder(k, txo.seeded_rand(s))
+    rng = np.random.default_rng(seed)
+    n = int(round(secs * FS))
+    if mode == "bench":
+        key = bench_key(seed)
+        r = int(rng.integers(0, 2000))
+        n5 = 5 * FS
+        host = host_signal(kind, n5, rng)
+        tx = embedder_factory(key, seed)
+        tx.frame_ctr = r
+        wm = tx.process(host)
+        off = int(rng.integers(0, n5 - n))
+        return np.ascontiguousarray(wm[off:off + n], dtype=np.float32), key
+    host = host_signal(kind, n, rng)
+    if mode == "nowm":
+        return host, key
+    tx = embedder_factory(key, seed)
+    tx.frame_ctr = start_ctr
+    return np.ascontiguousarray(tx.process(host), dtype=np.float32), key

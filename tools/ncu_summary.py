@@ -1,0 +1,50 @@
+#!/usr/bin/env python3
+"""Summarise an .ncu-rep (raw + source pages) into text: headline metrics and hot SASS regions."""
+import csv, subprocess, sys, io
+
+def page(rep, name):
+    out = subprocess.run(["ncu", "-i", rep, "--page", name, "--csv"], capture_output=True, text=True).stdout
+    return list(csv.reader(io.StringIO(out)))
+
+KEYS = ['gpu__time_duration.sum', 'sm__cycles_elapsed.avg.per_second', 'smsp__inst_executed.sum',
+        'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active',
+        'smsp__issue_active.avg.pct_of_peak_sustained_active', 'sm__warps_active.avg.pct_of_peak_sustained_active',
+        'launch__registers_per_thread', 'launch__occupancy_limit_registers', 'launch__occupancy_limit_shared_mem',
+        'dram__bytes_read.sum', 'dram__bytes_write.sum', 'dram__bytes_read.sum.per_second', 'dram__bytes_write.sum.per_second',
+        'lts__t_sector_hit_rate.pct', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum',
+        'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'smsp__thread_inst_executed_per_inst_executed.ratio']
+
+def main():
+    rep = sys.argv[1]
+    rows = page(rep, "raw")
+    hdr, units, vals = rows[0], rows[1], rows[2]
+    for h, u, v in zip(hdr, units, vals):
+        if h in KEYS or ('issue_stalled' in h and 'per_issue_active' in h and float(v or 0) > 0.1):
+            print(f"{h:88s} {u:14s} {v}")
+    rows = page(rep, "source")
+    hdr, data = rows[1], rows[2:]
+    ci = {h: i for i, h in enumerate(hdr)}
+    ex = [int(r[ci['Instructions Executed']]) for r in data]
+    sm = [int(r[ci['# Samples']]) for r in data]
+    tot, totS = sum(ex), sum(sm)
+    print(f"\nSASS instructions: {len(data)}  executed: {tot}  samples: {totS}")
+    runs, cur = [], None
+    for k, r in enumerate(data):
+        if cur and abs(ex[k] - cur['ex']) <= 0.02 * max(cur['ex'], 1):
+            cur['n'] += 1; cur['s'] += sm[k]; cur['end'] = k
+            for key in ('stall_long_sb', 'stall_wait', 'stall_short_sb', 'stall_math'):
+                cur[key] += int(r[ci[key]])
+        else:
+            cur = dict(start=k, end=k, ex=ex[k], n=1, s=sm[k], stall_long_sb=int(r[ci['stall_long_sb']]),
+                       stall_wait=int(r[ci['stall_wait']]), stall_short_sb=int(r[ci['stall_short_sb']]),
+                       stall_math=int(r[ci['stall_math']]))
+            runs.append(cur)
+    for r in runs:
+        if r['ex'] * r['n'] > 0.005 * tot or r['s'] > 0.01 * totS:
+            print(f"{r['start']:5d}-{r['end']:5d} n={r['n']:4d} exec={r['ex']:>11d} inst%={r['ex']*r['n']/tot*100:5.1f} "
+                  f"samp%={r['s']/totS*100:5.1f} long_sb={r['stall_long_sb']} wait={r['stall_wait']} "
+                  f"short_sb={r['stall_short_sb']} math={r['stall_math']} | {data[r['start']][ci['Source']].strip()[:40]}")
+
+if __name__ == "__main__":
+    main()
