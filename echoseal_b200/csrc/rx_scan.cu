@@ -1,0 +1,678 @@
+// echoseal_b200/csrc/rx_scan.cu — RX scan stages of the detector, hand-written for sm_100a:
+//   K1  es_rx_bandpass : 4 x order-8 Butterworth band-pass, fp64, chunked with zero-state warm-up
+//                        (rtwm/detector.py:59-60  scipy.signal.lfilter(b, a, x.astype(float32)))
+//   K2  es_rx_ncc      : cosine-normalised 63-tap preamble correlation, fp64
+//                        (rtwm/detector.py:76-79)
+//   K3  es_rx_peaks    : exact median / MAD threshold, +-607 non-max suppression, first 25 peaks,
+//                        top-5 fallback (rtwm/detector.py:83-99, 107-110)
+//   K4  es_rx_frames   : per peak: header decode (rtwm/detector.py:452-515) and the PN-independent
+//                        part of _llr: matched filter + shift search (rtwm/detector.py:322-383)
+//   K5  es_rx_llr      : per (peak, counter, PN variant): despread + robust LLR scaling
+//                        (rtwm/detector.py:384-414)
+// Everything else of the detector (hop schedule, PN generation, AEAD validation, candidate budget)
+// stays on the host by design and feeds / consumes these kernels (echoseal_b200/detector.py).
+//
+// Layouts (all contiguous):  x f32 [clips][n] ; y f64 [clips][4][n] ; corr f64 [clips][4][n-62] ;
+// peaks i32 [clips][4][25] ; mf_aligned f32 [clips][4][25][1024].
+#include "common.cuh"
+#include <math_constants.h>
+
+namespace es {
+
+constexpr int PRE_L = 63, HDR_L = 128, NPAY = 1024, FRAME_LEN = 1215;
+constexpr int NBANDS = 4, PEAK_LIMIT = 25, NMS_HALF = FRAME_LEN / 2;   // 607
+constexpr int MAXH = 192;            // matched-filter taps per band (131/116/123/93 at 48 kHz)
+constexpr int BP_CHUNK = 2048;       // outputs per thread in K1
+constexpr int BP_WARM = 768;         // zero-state warm-up samples (error < 4e-13 of peak)
+
+__constant__ double c_bp_b[NBANDS][9];
+__constant__ double c_bp_a[NBANDS][9];
+__constant__ double c_tpl[NBANDS][PRE_L];
+__constant__ float c_mf[NBANDS][MAXH];
+__constant__ int c_mf_len[NBANDS];
+static int g_rx_ready = 0;
+
+// ---------------------------------------------------------------------------------------------
+// K1: band-pass.  One thread per (chunk, band, clip): direct-form II transposed, the operation
+// order of scipy's lfilter, states in registers; chunks other than the first start from zero state
+// BP_WARM samples early (the filter's impulse response has decayed below 1e-12 by then).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) bandpass_kernel(const float* __restrict__ x, int nclips, int n,
+                                                       long long x_stride, double* __restrict__ y)
+{
+    const int nchunks = (n + BP_CHUNK - 1) / BP_CHUNK;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)nclips * NBANDS * nchunks;
+    if (tid >= total) return;
+    const int chunk = (int)(tid % nchunks);
+    const int band = (int)((tid / nchunks) % NBANDS);
+    const int clip = (int)(tid / ((long long)nchunks * NBANDS));
+    const float* xs = x + (long long)clip * x_stride;
+    double* ys = y + ((long long)clip * NBANDS + band) * n;
+    double b[9], a[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { b[i] = c_bp_b[band][i]; a[i] = c_bp_a[band][i]; }
+    double z[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) z[i] = 0.0;
+    const int out0 = chunk * BP_CHUNK;
+    const int out1 = min(n, out0 + BP_CHUNK);
+    const int j0 = max(0, out0 - BP_WARM);
+#pragma unroll 1
+    for (int j = j0; j < out1; ++j) {
+        const double xn = (double)__ldg(xs + j);
+        const double yn = fma(b[0], xn, z[0]);
+#pragma unroll
+        for (int i = 0; i < 7; ++i) z[i] = fma(-a[i + 1], yn, fma(b[i + 1], xn, z[i + 1]));
+        z[7] = fma(-a[8], yn, b[8] * xn);
+        if (j >= out0) ys[j] = yn;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2: normalised cross-correlation, 1024 outputs per CTA from a shared y tile
+// ---------------------------------------------------------------------------------------------
+constexpr int NCC_TILE = 1024;
+__global__ void __launch_bounds__(256) ncc_kernel(const double* __restrict__ y, int n, int nc,
+                                                  double* __restrict__ corr)
+{
+    __shared__ double sy[NCC_TILE + PRE_L - 1];
+    const int cb = blockIdx.y;                  // clip*4 + band
+    const int band = cb & 3;
+    const int i0 = blockIdx.x * NCC_TILE;
+    const double* ys = y + (long long)cb * n;
+    for (int t = threadIdx.x; t < NCC_TILE + PRE_L - 1; t += 256) {
+        const int j = i0 + t;
+        sy[t] = (j < n) ? ys[j] : 0.0;
+    }
+    __syncthreads();
+    double* cs = corr + (long long)cb * nc;
+    for (int t = threadIdx.x; t < NCC_TILE; t += 256) {
+        const int i = i0 + t;
+        if (i >= nc) break;
+        double e = 0.0, d = 0.0;
+#pragma unroll 9
+        for (int k = 0; k < PRE_L; ++k) {
+            const double v = sy[t + k];
+            e = fma(v, v, e);
+            d = fma(v, c_tpl[band][k], d);
+        }
+        cs[i] = d / (sqrt(e) + 1e-12);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3: exact order statistics + NMS.  One CTA of 1024 threads per (clip, band).
+// ---------------------------------------------------------------------------------------------
+constexpr int PK_THREADS = 1024;
+constexpr int SEL_BINS = 2048;
+constexpr int SEL_CAP = 4096;       // values gathered from the selected bin (shared memory)
+constexpr int NMS_BLOCK = 4096;
+
+__device__ __forceinline__ uint64_t f64_key(double v)   // order-preserving map to uint64
+{
+    const uint64_t u = (uint64_t)__double_as_longlong(v);
+    return (u & 0x8000000000000000ull) ? ~u : (u | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double key_f64(uint64_t k)
+{
+    const uint64_t u = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
+    return __longlong_as_double((long long)u);
+}
+
+struct SelShared {
+    unsigned int hist[SEL_BINS];
+    double buf[SEL_CAP];
+    unsigned int count;
+    int bin;
+    unsigned int below;
+    unsigned long long prefix;
+    double result;
+};
+
+// value(v) = MODE ? |v - center| : v
+template <int MODE> __device__ __forceinline__ double sel_value(double v, double center)
+{
+    return MODE ? fabs(v - center) : v;
+}
+template <int MODE> __device__ __forceinline__ int sel_bin(double val)
+{
+    // MODE 0: corr in [-1,1] -> (val+1)*1024 ; MODE 1: |corr-med| in [0,2] -> val*1024.  Monotone in val.
+    const double s = MODE ? val * 1024.0 : (val + 1.0) * 1024.0;
+    int b = (s >= 2047.0) ? 2047 : ((s <= 0.0) ? 0 : (int)s);
+    return b;
+}
+
+// k-th smallest (0-based) of value(c[i]), i < nc.  All threads of the CTA call it; result broadcast.
+template <int MODE>
+__device__ double select_kth(const double* __restrict__ c, int nc, int k, double center, SelShared& S)
+{
+    const int tid = threadIdx.x;
+    for (int b = tid; b < SEL_BINS; b += PK_THREADS) S.hist[b] = 0;
+    if (tid == 0) S.count = 0;
+    __syncthreads();
+    for (int i = tid; i < nc; i += PK_THREADS) atomicAdd(&S.hist[sel_bin<MODE>(sel_value<MODE>(c[i], center))], 1u);
+    __syncthreads();
+    if (tid == 0) {
+        unsigned int acc = 0;
+        int b = 0;
+        for (; b < SEL_BINS; ++b) {
+            if (acc + S.hist[b] > (unsigned)k) break;
+            acc += S.hist[b];
+        }
+        S.bin = b; S.below = acc;
+    }
+    __syncthreads();
+    const int bin = S.bin;
+    const unsigned int m = S.hist[bin];
+    const int kk = k - (int)S.below;               // rank inside the bin
+    if (m <= (unsigned)SEL_CAP) {
+        for (int i = tid; i < nc; i += PK_THREADS) {
+            const double v = sel_value<MODE>(c[i], center);
+            if (sel_bin<MODE>(v) == bin) S.buf[atomicAdd(&S.count, 1u)] = v;
+        }
+        __syncthreads();
+        // rank counting: the kk-th smallest is the value v with  #less <= kk < #less + #equal
+        for (int i = tid; i < (int)m; i += PK_THREADS) {
+            const double v = S.buf[i];
+            int less = 0, eq = 0;
+            for (int j = 0; j < (int)m; ++j) {
+                const double w = S.buf[j];
+                less += (w < v); eq += (w == v);
+            }
+            if (less <= kk && kk < less + eq) S.result = v;    // all writers write the same value
+        }
+        __syncthreads();
+        return S.result;
+    }
+    // degenerate distribution (e.g. silence: every value equal): MSB radix select on the raw bits,
+    // restricted to the selected bin, 8 bits per pass
+    unsigned long long prefix = 0, mask = 0;
+    int kr = kk;
+    for (int shift = 56; shift >= 0; shift -= 8) {
+        for (int b = tid; b < 256; b += PK_THREADS) S.hist[SEL_BINS - 256 + b] = 0;
+        __syncthreads();
+        for (int i = tid; i < nc; i += PK_THREADS) {
+            const double v = sel_value<MODE>(c[i], center);
+            if (sel_bin<MODE>(v) != bin) continue;
+            const uint64_t key = f64_key(v);
+            if ((key & mask) == prefix) atomicAdd(&S.hist[SEL_BINS - 256 + (int)((key >> shift) & 255ull)], 1u);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            unsigned int acc = 0;
+            int d = 0;
+            for (; d < 256; ++d) {
+                const unsigned int h = S.hist[SEL_BINS - 256 + d];
+                if (acc + h > (unsigned)kr) break;
+                acc += h;
+            }
+            S.below = acc; S.prefix = prefix | ((unsigned long long)d << shift);
+        }
+        __syncthreads();
+        kr -= (int)S.below;
+        prefix = S.prefix;
+        mask |= 255ull << shift;
+        __syncthreads();
+    }
+    return key_f64(prefix);
+}
+
+struct PeakShared {
+    SelShared sel;
+    int cand[NMS_BLOCK];
+    unsigned int ncand;
+    int found[NMS_BLOCK];
+    unsigned int nfound;
+    int npeaks;
+    double top_v[32];
+    int top_i[32];
+};
+
+__global__ void __launch_bounds__(PK_THREADS) peaks_kernel(const double* __restrict__ corr, int nc,
+                                                           int32_t* __restrict__ peaks, int32_t* __restrict__ npeaks,
+                                                           double* __restrict__ stats)
+{
+    extern __shared__ __align__(16) unsigned char pk_raw[];
+    PeakShared& S = *reinterpret_cast<PeakShared*>(pk_raw);
+    const int cb = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const double* c = corr + (long long)cb * nc;
+    int32_t* pk = peaks + (long long)cb * PEAK_LIMIT;
+    for (int t = tid; t < PEAK_LIMIT; t += PK_THREADS) pk[t] = -1;
+    if (nc <= 0) {
+        if (tid == 0) { npeaks[cb] = 0; stats[cb * 4 + 0] = 0; stats[cb * 4 + 1] = 0; stats[cb * 4 + 2] = 0; stats[cb * 4 + 3] = 0; }
+        return;
+    }
+    // ---- median, MAD, threshold (rtwm/detector.py:83-86)
+    const int k2 = nc >> 1, k1 = (nc - 1) >> 1;
+    const double v2 = select_kth<0>(c, nc, k2, 0.0, S.sel);
+    __syncthreads();
+    const double v1 = (k1 == k2) ? v2 : select_kth<0>(c, nc, k1, 0.0, S.sel);
+    __syncthreads();
+    const double med = (v1 + v2) * 0.5;
+    const double w2 = select_kth<1>(c, nc, k2, med, S.sel);
+    __syncthreads();
+    const double w1 = (k1 == k2) ? w2 : select_kth<1>(c, nc, k1, med, S.sel);
+    __syncthreads();
+    const double mad = (w1 + w2) * 0.5 + 1e-12;
+    double thr = med + (4.5 * 1.4826) * mad;
+    thr = thr < 0.95 ? thr : 0.95;
+    // ---- NMS in ascending index blocks until 25 peaks are found (rtwm/detector.py:87-97, 108-110)
+    if (tid == 0) S.npeaks = 0;
+    __syncthreads();
+    for (int blk0 = 0; blk0 < nc; blk0 += NMS_BLOCK) {
+        if (tid == 0) { S.ncand = 0; S.nfound = 0; }
+        __syncthreads();
+        for (int i = blk0 + tid; i < min(nc, blk0 + NMS_BLOCK); i += PK_THREADS)
+            if (c[i] >= thr) S.cand[atomicAdd(&S.ncand, 1u)] = i;
+        __syncthreads();
+        const int ncand = (int)S.ncand;
+        for (int q = warp; q < ncand; q += PK_THREADS / 32) {
+            const int i = S.cand[q];
+            const double v = c[i];
+            const int lo = max(0, i - NMS_HALF), hi = min(nc, i + NMS_HALF + 1);
+            bool bigger = false;
+            for (int j = lo + lane; j < hi; j += 32) bigger |= (c[j] > v);
+            if (!__any_sync(0xffffffffu, bigger) && lane == 0) S.found[atomicAdd(&S.nfound, 1u)] = i;
+        }
+        __syncthreads();
+        const int nf = (int)S.nfound;
+        // append in ascending index order (rank by counting)
+        for (int q = tid; q < nf; q += PK_THREADS) {
+            const int i = S.found[q];
+            int r = 0;
+            for (int j = 0; j < nf; ++j) r += (S.found[j] < i);
+            const int slot = S.npeaks + r;
+            if (slot < PEAK_LIMIT) pk[slot] = i;
+        }
+        __syncthreads();
+        if (tid == 0) S.npeaks += nf;
+        __syncthreads();
+        if (S.npeaks >= PEAK_LIMIT) break;
+    }
+    int np = S.npeaks;
+    int fallback = 0;
+    if (np == 0) {
+        // ---- top-k fallback, k = min(5, nc): descending value (ties: larger index first)
+        fallback = 1;
+        const int kf = nc < 5 ? nc : 5;
+        for (int r = 0; r < kf; ++r) {
+            double bv = -CUDART_INF; int bi = -1;
+            for (int i = tid; i < nc; i += PK_THREADS) {
+                bool taken = false;
+                for (int q = 0; q < r; ++q) taken |= (pk[q] == i);
+                const double v = c[i];
+                if (!taken && (v > bv || (v == bv && i > bi))) { bv = v; bi = i; }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, bv, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ov > bv || (ov == bv && oi > bi)) { bv = ov; bi = oi; }
+            }
+            if (lane == 0) { S.top_v[warp] = bv; S.top_i[warp] = bi; }
+            __syncthreads();
+            if (tid == 0) {
+                for (int q = 1; q < PK_THREADS / 32; ++q)
+                    if (S.top_v[q] > bv || (S.top_v[q] == bv && S.top_i[q] > bi)) { bv = S.top_v[q]; bi = S.top_i[q]; }
+                pk[r] = bi;
+            }
+            __syncthreads();
+        }
+        np = kf;
+    }
+    if (tid == 0) {
+        npeaks[cb] = np < PEAK_LIMIT ? np : PEAK_LIMIT;
+        stats[cb * 4 + 0] = med; stats[cb * 4 + 1] = mad; stats[cb * 4 + 2] = thr; stats[cb * 4 + 3] = (double)fallback;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K4: per-peak front end: header decode + matched filter / shift search of the payload
+// ---------------------------------------------------------------------------------------------
+constexpr int FR_THREADS = 256;
+constexpr int MF_MAX = NPAY + 2 * MAXH;      // upper bound of conv length we keep
+
+struct FrameShared {
+    float hs[MAXH];
+    float frame[FRAME_LEN];
+    float mf[MF_MAX];
+    double pre[MF_MAX + 1];
+    float score[2 * MAXH + 64];
+    float d[HDR_L];
+    float sums[16];
+    int best;
+};
+
+__device__ __forceinline__ float conv_at(const float* __restrict__ sig, int nsig, const float* __restrict__ h, int nh, int t)
+{
+    // np.convolve(sig, h, 'full')[t] = sum_k sig[k] * h[t-k]
+    const int k0 = max(0, t - (nh - 1)), k1 = min(nsig - 1, t);
+    double acc = 0.0;
+    for (int k = k0; k <= k1; ++k) acc = fma((double)sig[k], (double)h[t - k], acc);
+    return (float)acc;
+}
+
+__global__ void __launch_bounds__(FR_THREADS) frames_kernel(const double* __restrict__ y, int n,
+                                                            const int32_t* __restrict__ peaks,
+                                                            const int32_t* __restrict__ npeaks,
+                                                            const uint8_t* __restrict__ hdr_pn /*[clips][16]*/,
+                                                            float* __restrict__ mf_aligned, int32_t* __restrict__ llr_best_s,
+                                                            float* __restrict__ hdr_out, int32_t* __restrict__ hdr_best_s)
+{
+    __shared__ FrameShared S;
+    const int slot = blockIdx.x, cb = blockIdx.y;
+    const int band = cb & 3, clip = cb >> 2;
+    const int tid = threadIdx.x;
+    const long long pidx = (long long)cb * PEAK_LIMIT + slot;
+    const int start = (slot < npeaks[cb]) ? peaks[pidx] : -1;
+    if (start < 0 || start + FRAME_LEN > n) {       // rtwm/detector.py:112-113
+        if (tid == 0) { hdr_out[pidx * 4 + 0] = -1.0f; hdr_out[pidx * 4 + 1] = 0; hdr_out[pidx * 4 + 2] = 0; hdr_out[pidx * 4 + 3] = 0;
+                        llr_best_s[pidx] = 0; hdr_best_s[pidx] = 0; }
+        return;
+    }
+    const double* ys = y + (long long)cb * n + start;
+    for (int t = tid; t < FRAME_LEN; t += FR_THREADS) S.frame[t] = (float)ys[t];
+    __syncthreads();
+    const int nh = c_mf_len[band];
+    const int mem = nh - 1;
+    for (int t = tid; t < nh; t += FR_THREADS) S.hs[t] = c_mf[band][t];   // divergent indices below: keep taps in smem
+    __syncthreads();
+    const float* h = S.hs;
+    // ======== header (rtwm/detector.py:452-515) ========
+    {
+        const int prefix = min(mem, PRE_L);
+        const float* sig = S.frame + PRE_L - prefix;
+        const int nsig = prefix + HDR_L;
+        const int nmf = nsig + nh - 1;
+        for (int t = tid; t < nmf; t += FR_THREADS) S.mf[t] = conv_at(sig, nsig, h, nh, t);
+        __syncthreads();
+        const int offset = mem + prefix;
+        int maxs = min(HDR_L / 2 + prefix, 4 * nh);
+        if (maxs < mem) maxs = mem;
+        const int wstart = max(0, offset - maxs), wstop = min(nmf, offset + HDR_L + maxs);
+        const int base = offset - wstart;
+        const int wlen = wstop - wstart;
+        const int guard = max(8, min(32, nh / 8));
+        const float* win = S.mf + wstart;
+        for (int si = tid; si <= 2 * maxs; si += FR_THREADS) {
+            const int s = si - maxs;
+            const int i0 = base + s;
+            float sc = -2.0f;                           // skipped shifts never win (score >= 0 > -1)
+            if (i0 >= 0 && i0 + HDR_L <= wlen) {
+                double acc = 0.0;
+                for (int k = guard; k < HDR_L; ++k) {
+                    const float pn = ((hdr_pn[clip * 16 + (k >> 3)] >> (7 - (k & 7))) & 1) ? 1.0f : -1.0f;
+                    acc += (double)(win[i0 + k] * pn);
+                }
+                sc = fabsf((float)acc);
+            }
+            S.score[si] = sc;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int bs = 0; float bsc = -1.0f;
+            for (int si = 0; si <= 2 * maxs; ++si) if (S.score[si] > bsc) { bsc = S.score[si]; bs = si - maxs; }
+            S.best = bs;
+        }
+        __syncthreads();
+        const int i0 = base + S.best;
+        if (tid < HDR_L) {
+            const float pn = ((hdr_pn[clip * 16 + (tid >> 3)] >> (7 - (tid & 7))) & 1) ? 1.0f : -1.0f;
+            S.d[tid] = win[i0 + tid] * pn;
+        }
+        __syncthreads();
+        if (tid < 16) {
+            float s8 = 0.0f;
+            for (int k = 0; k < 8; ++k) s8 += S.d[tid * 8 + k];
+            S.sums[tid] = s8;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int val = 0, npos = 0;
+            double mabs = 0.0, msq = 0.0, mean = 0.0;
+            for (int q = 0; q < 16; ++q) {
+                val = (val << 1) | (S.sums[q] < 0.0f ? 1 : 0);     // inverted bit sense, as the reference (quirk 2)
+                npos += (S.sums[q] > 0.0f);
+                mabs += fabs((double)S.sums[q]);
+            }
+            mabs /= 16.0;
+            for (int k = 0; k < HDR_L; ++k) { msq += (double)S.d[k] * (double)S.d[k]; mean += (double)S.d[k]; }
+            msq /= HDR_L; mean /= HDR_L;
+            double var = 0.0;
+            for (int k = 0; k < HDR_L; ++k) { const double e = (double)S.d[k] - mean; var += e * e; }
+            var /= HDR_L;
+            const float margin = (float)mabs / ((float)sqrt(msq) + 1e-12f);
+            const float score = (float)(mabs / (sqrt(var) + 1e-12));
+            const bool ok = (npos >= 10) && (margin > 0.5f);
+            hdr_out[pidx * 4 + 0] = ok ? 1.0f : 0.0f;
+            hdr_out[pidx * 4 + 1] = (float)val;
+            hdr_out[pidx * 4 + 2] = score;
+            hdr_out[pidx * 4 + 3] = margin;
+            hdr_best_s[pidx] = S.best;
+        }
+        __syncthreads();
+    }
+    // ======== payload matched filter + shift search (rtwm/detector.py:322-383) ========
+    {
+        const int pstart = PRE_L + HDR_L;
+        const int prefix = min(mem, pstart);
+        const float* sig = S.frame + pstart - prefix;
+        const int nsig = prefix + NPAY;
+        const int nmf = nsig + nh - 1;
+        const int offset = prefix + mem;
+        const int raw = min(min(NPAY / 2, 4 * nh), HDR_L);
+        const int maxs = max(mem, raw);
+        const int wstart = max(0, offset - maxs), wstop = min(nmf, offset + NPAY + maxs);
+        const int wlen = wstop - wstart;
+        const int base = offset - wstart;
+        int guard = min(NPAY / 4, max(nh / 2, 24));
+        for (int t = tid; t < wlen; t += FR_THREADS) S.mf[t] = conv_at(sig, nsig, h, nh, wstart + t);
+        __syncthreads();
+        // prefix sums of |mf| (fp64) -> score(s) = mean |mf_win[i0+guard : i0+n]|  (PN cancels under |.|, quirk 3)
+        if (tid < 32) {
+            // warp 0: blocked scan
+            const int per = (wlen + 31) / 32;
+            const int a0 = tid * per, a1 = min(wlen, a0 + per);
+            double s = 0.0;
+            for (int t = a0; t < a1; ++t) s += (double)fabsf(S.mf[t]);
+            double incl = s;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const double v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (tid >= o) incl += v;
+            }
+            double run = incl - s;
+            if (tid == 0) S.pre[0] = 0.0;
+            for (int t = a0; t < a1; ++t) { run += (double)fabsf(S.mf[t]); S.pre[t + 1] = run; }
+        }
+        __syncthreads();
+        for (int si = tid; si <= 2 * maxs; si += FR_THREADS) {
+            const int i0 = base + si - maxs;
+            float sc = -2.0f;
+            if (i0 >= 0 && i0 + NPAY <= wlen)
+                sc = (float)((S.pre[i0 + NPAY] - S.pre[i0 + guard]) / (double)(NPAY - guard));
+            S.score[si] = sc;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int bs = 0; float bsc = -1.0f;
+            for (int si = 0; si <= 2 * maxs; ++si) if (S.score[si] > bsc) { bsc = S.score[si]; bs = si - maxs; }
+            S.best = bs;
+            llr_best_s[pidx] = bs;
+        }
+        __syncthreads();
+        const int i0 = base + S.best;
+        float* out = mf_aligned + pidx * NPAY;
+        for (int t = tid; t < NPAY; t += FR_THREADS) out[t] = S.mf[i0 + t];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K5: despread + LLR scaling, one CTA per (item, variant)
+// ---------------------------------------------------------------------------------------------
+constexpr int LLR_THREADS = 256;
+
+__device__ void bitonic_sort_1024(float* s, int tid)
+{
+    for (int k = 2; k <= 1024; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < 1024; i += LLR_THREADS) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const float a = s[i], b = s[l];
+                    const bool up = ((i & k) == 0);
+                    if ((a > b) == up) { s[i] = b; s[l] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+__device__ double block_sum(double v, double* red, int tid)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((tid & 31) == 0) red[tid >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int q = 0; q < LLR_THREADS / 32; ++q) t += red[q];
+    return t;
+}
+
+__global__ void __launch_bounds__(LLR_THREADS) llr_kernel(const float* __restrict__ mf_aligned,
+                                                          const int32_t* __restrict__ item_peak,
+                                                          const uint8_t* __restrict__ pn_packed /*[items][152]*/,
+                                                          float* __restrict__ llr)
+{
+    __shared__ float desp[NPAY];
+    __shared__ float srt[NPAY];
+    __shared__ double red[LLR_THREADS / 32];
+    const int item = blockIdx.x >> 1, variant = blockIdx.x & 1;
+    const int tid = threadIdx.x;
+    const int pidx = item_peak[item];
+    const int band = (pidx / PEAK_LIMIT) & 3;
+    const int nh = c_mf_len[band];
+    const int guard = min(NPAY / 4, max(nh / 2, 24));
+    const float* mf = mf_aligned + (long long)pidx * NPAY;
+    const uint8_t* pn = pn_packed + (long long)item * 152;
+    const int pn_off = variant ? 0 : (PRE_L + HDR_L);      // variant 0: bits [191,1215) ; variant 1: bits [0,1024)
+    for (int t = tid; t < NPAY; t += LLR_THREADS) {
+        const int q = pn_off + t;
+        const float s = ((pn[q >> 3] >> (7 - (q & 7))) & 1) ? 1.0f : -1.0f;
+        desp[t] = mf[t] * s;
+    }
+    __syncthreads();
+    const int nt = NPAY - guard;
+    // mean of the tail
+    double acc = 0.0;
+    for (int t = guard + tid; t < NPAY; t += LLR_THREADS) acc += (double)desp[t];
+    const float mu = (float)(block_sum(acc, red, tid) / nt);
+    // median of the tail (float32; even count -> mean of the two middle values in float32)
+    for (int t = tid; t < NPAY; t += LLR_THREADS) srt[t] = (t < nt) ? desp[guard + t] : CUDART_INF_F;
+    __syncthreads();
+    bitonic_sort_1024(srt, tid);
+    const float medv = (nt & 1) ? srt[nt >> 1] : (srt[(nt >> 1) - 1] + srt[nt >> 1]) * 0.5f;
+    __syncthreads();
+    for (int t = tid; t < NPAY; t += LLR_THREADS) srt[t] = (t < nt) ? fabsf(desp[guard + t] - medv) : CUDART_INF_F;
+    __syncthreads();
+    bitonic_sort_1024(srt, tid);
+    const float madv = (nt & 1) ? srt[nt >> 1] : (srt[(nt >> 1) - 1] + srt[nt >> 1]) * 0.5f;
+    // std of the tail (population, float32 semantics approximated in fp64)
+    double a2 = 0.0;
+    for (int t = guard + tid; t < NPAY; t += LLR_THREADS) { const double e = (double)desp[t] - (double)mu; a2 += e * e; }
+    const float sd = (float)sqrt(block_sum(a2, red, tid) / nt);
+    const double sigma_mad = 1.4826 * ((double)madv + 1e-12);
+    const double sigma_std = (double)sd + 1e-12;
+    const double sigma = fmax(fmax(sigma_mad, sigma_std), 0.1);
+    double scale = 2.0 / (sigma * sigma);
+    scale = fmin(fmax(scale, 0.5), 30.0);
+    const float fscale = (float)scale;
+    float* out = llr + ((long long)item * 2 + variant) * NPAY;
+    for (int t = tid; t < NPAY; t += LLR_THREADS) {
+        const float v = (desp[t] - mu) * fscale;
+        out[t] = fminf(fmaxf(v, -12.0f), 12.0f);
+    }
+}
+
+}  // namespace es
+
+using namespace es;
+
+extern "C" {
+
+int es_rx_set_filters(const double* bp_b /*[4][9]*/, const double* bp_a /*[4][9]*/, const double* tpl /*[4][63]*/,
+                      const float* mf /*[4][192]*/, const int* mf_len /*[4]*/)
+{
+    for (int b = 0; b < NBANDS; ++b)
+        if (mf_len[b] < 1 || mf_len[b] > MAXH) { set_error("es_rx_set_filters: mf_len[%d]=%d out of range", b, mf_len[b]); return ES_EINVAL; }
+    ES_CUDA_OK(cudaMemcpyToSymbol(c_bp_b, bp_b, sizeof(double) * NBANDS * 9));
+    ES_CUDA_OK(cudaMemcpyToSymbol(c_bp_a, bp_a, sizeof(double) * NBANDS * 9));
+    ES_CUDA_OK(cudaMemcpyToSymbol(c_tpl, tpl, sizeof(double) * NBANDS * PRE_L));
+    ES_CUDA_OK(cudaMemcpyToSymbol(c_mf, mf, sizeof(float) * NBANDS * MAXH));
+    ES_CUDA_OK(cudaMemcpyToSymbol(c_mf_len, mf_len, sizeof(int) * NBANDS));
+    g_rx_ready = 1;
+    return ES_OK;
+}
+
+int es_rx_bandpass(const float* x, int nclips, int n, long long x_stride, double* y, void* stream)
+{
+    if (!g_rx_ready) { set_error("es_rx_bandpass: call es_rx_set_filters first"); return ES_ENOTREADY; }
+    if (nclips <= 0 || n <= 0) return ES_OK;
+    const long long nchunks = (n + BP_CHUNK - 1) / BP_CHUNK;
+    const long long total = (long long)nclips * NBANDS * nchunks;
+    const int threads = 128;
+    bandpass_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(x, nclips, n, x_stride, y);
+    ES_CUDA_OK(cudaGetLastError());
+    return ES_OK;
+}
+
+int es_rx_ncc(const double* y, int nclips, int n, double* corr, void* stream)
+{
+    if (!g_rx_ready) { set_error("es_rx_ncc: call es_rx_set_filters first"); return ES_ENOTREADY; }
+    const int nc = n - (PRE_L - 1);
+    if (nclips <= 0 || nc <= 0) return ES_OK;
+    dim3 grid((nc + NCC_TILE - 1) / NCC_TILE, nclips * NBANDS);
+    ncc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(y, n, nc, corr);
+    ES_CUDA_OK(cudaGetLastError());
+    return ES_OK;
+}
+
+int es_rx_peaks(const double* corr, int nclips, int nc, int32_t* peaks, int32_t* npeaks, double* stats, void* stream)
+{
+    if (nclips <= 0) return ES_OK;
+    static int configured = 0;
+    if (!configured) {
+        ES_CUDA_OK(cudaFuncSetAttribute(peaks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PeakShared)));
+        configured = 1;
+    }
+    peaks_kernel<<<nclips * NBANDS, PK_THREADS, sizeof(PeakShared), (cudaStream_t)stream>>>(corr, nc, peaks, npeaks, stats);
+    ES_CUDA_OK(cudaGetLastError());
+    return ES_OK;
+}
+
+int es_rx_frames(const double* y, int nclips, int n, const int32_t* peaks, const int32_t* npeaks, const uint8_t* hdr_pn,
+                 float* mf_aligned, int32_t* llr_best_s, float* hdr_out, int32_t* hdr_best_s, void* stream)
+{
+    if (!g_rx_ready) { set_error("es_rx_frames: call es_rx_set_filters first"); return ES_ENOTREADY; }
+    if (nclips <= 0) return ES_OK;
+    dim3 grid(PEAK_LIMIT, nclips * NBANDS);
+    frames_kernel<<<grid, FR_THREADS, 0, (cudaStream_t)stream>>>(y, n, peaks, npeaks, hdr_pn, mf_aligned, llr_best_s, hdr_out, hdr_best_s);
+    ES_CUDA_OK(cudaGetLastError());
+    return ES_OK;
+}
+
+int es_rx_llr(const float* mf_aligned, const int32_t* item_peak, const uint8_t* pn_packed, int nitems, float* llr, void* stream)
+{
+    if (!g_rx_ready) { set_error("es_rx_llr: call es_rx_set_filters first"); return ES_ENOTREADY; }
+    if (nitems <= 0) return ES_OK;
+    llr_kernel<<<nitems * 2, LLR_THREADS, 0, (cudaStream_t)stream>>>(mf_aligned, item_peak, pn_packed, llr);
+    ES_CUDA_OK(cudaGetLastError());
+    return ES_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,132 @@
+"""Tensor-level wrappers over the RX scan kernels of the C-ABI (include/echoseal_b200.h:
+es_rx_set_filters / es_rx_bandpass / es_rx_ncc / es_rx_peaks / es_rx_frames / es_rx_llr).
+Used by echoseal_b200.detector; no CPU fallback."""
+from __future__ import annotations
+import ctypes as C
+import numpy as np
+import torch
+from scipy.signal import lfilter as _host_lfilter   # host constants only (taps/templates), never signal data
+
+from . import _native as N
+from .utils import BAND_PLAN, butter_bandpass, mseq_63
+
+PRE_L, HDR_L, NPAY, FRAME_LEN, PEAK_LIMIT, MAXH = 63, 128, 1024, 1215, 25, 192
+
+
+def preamble_template(band, fs: int) -> np.ndarray:
+    """float64[63] doubly band-passed, unit-norm MLS preamble (rtwm/detector.py:67-69). Host constant."""
+    b, a = butter_bandpass(*band, fs, order=4)
+    pre = 2.0 * mseq_63().astype(np.float32) - 1.0
+    tpl = _host_lfilter(b, a, _host_lfilter(b, a, pre))
+    return tpl / float(np.sqrt(np.sum(tpl * tpl)) + 1e-12)
+
+
+def matched_filter_taps(band, fs: int) -> np.ndarray:
+    """float32 taps of the time-reversed TX*RX cascade truncated at 99.9 % energy
+    (rtwm/detector.py:260-294). Host constant, input of the K4 kernel."""
+    b, a = butter_bandpass(*band, fs, order=4)
+    M = max(256, max(len(a), len(b)) * 64)
+    imp = np.zeros(M, dtype=np.float32)
+    imp[0] = 1.0
+    g_tx = _host_lfilter(b, a, imp).astype(np.float32)
+    g_eff = np.convolve(g_tx, g_tx).astype(np.float32)
+    e = g_eff * g_eff
+    c = np.cumsum(e)
+    total = float(c[-1]) + 1e-20
+    idx = int(np.searchsorted(c, 0.999 * total))
+    g_eff = g_eff[:idx + 1] if idx + 1 < g_eff.size else g_eff
+    h = g_eff[::-1].copy()
+    h /= (np.sqrt(float(np.sum(h * h))) + 1e-12)
+    return h
+
+
+_filter_sig = None
+
+
+def set_filters(fs: int, mf_taps: list[np.ndarray]):
+    """Upload the per-band constants (filter coefficients, preamble templates, matched-filter taps)."""
+    global _filter_sig
+    sig = (fs, torch.cuda.current_device(), tuple(t.tobytes() for t in mf_taps))
+    if sig == _filter_sig:
+        return
+    bb = np.zeros((4, 9)); aa = np.zeros((4, 9)); tpl = np.zeros((4, PRE_L))
+    mf = np.zeros((4, MAXH), np.float32); ml = np.zeros(4, np.int32)
+    for i, band in enumerate(BAND_PLAN):
+        b, a = butter_bandpass(*band, fs, order=4)
+        bb[i] = b / a[0]; aa[i] = a / a[0]
+        tpl[i] = preamble_template(band, fs)
+        h = np.asarray(mf_taps[i], np.float32)
+        if h.size > MAXH:
+            raise ValueError(f"matched filter of band {band} has {h.size} taps > {MAXH}")
+        mf[i, :h.size] = h; ml[i] = h.size
+    p = lambda a_: a_.ctypes.data_as(C.c_void_p)
+    N.check(N.lib().es_rx_set_filters(p(bb), p(aa), p(tpl), p(mf), p(ml)), "es_rx_set_filters")
+    _filter_sig = sig
+
+
+def bandpass(x: torch.Tensor) -> torch.Tensor:
+    """x float32[B,n] -> y float64[B,4,n] (K1)."""
+    N.require_cuda(x)
+    B, n = x.shape
+    y = torch.empty((B, 4, n), dtype=torch.float64, device=x.device)
+    N.check(N.lib().es_rx_bandpass(N.ptr(x), C.c_int(B), C.c_int(n), C.c_longlong(x.stride(0)), N.ptr(y),
+                                   N.stream_ptr()), "es_rx_bandpass")
+    return y
+
+
+def ncc(y: torch.Tensor) -> torch.Tensor:
+    """y float64[B,4,n] -> corr float64[B,4,n-62] (K2)."""
+    N.require_cuda(y)
+    B, _, n = y.shape
+    nc = max(0, n - (PRE_L - 1))
+    corr = torch.empty((B, 4, nc), dtype=torch.float64, device=y.device)
+    if nc > 0:
+        N.check(N.lib().es_rx_ncc(N.ptr(y), C.c_int(B), C.c_int(n), N.ptr(corr), N.stream_ptr()), "es_rx_ncc")
+    return corr
+
+
+def peaks(corr: torch.Tensor):
+    """corr float64[B,4,nc] -> (peaks i32[B,4,25] (-1 padded), npeaks i32[B,4], stats f64[B,4,4] =
+    med, mad, thr, used_fallback) (K3)."""
+    N.require_cuda(corr)
+    B, _, nc = corr.shape
+    pk = torch.full((B, 4, PEAK_LIMIT), -1, dtype=torch.int32, device=corr.device)
+    npk = torch.zeros((B, 4), dtype=torch.int32, device=corr.device)
+    st = torch.zeros((B, 4, 4), dtype=torch.float64, device=corr.device)
+    if nc > 0:
+        N.check(N.lib().es_rx_peaks(N.ptr(corr), C.c_int(B), C.c_int(nc), N.ptr(pk), N.ptr(npk), N.ptr(st),
+                                    N.stream_ptr()), "es_rx_peaks")
+    return pk, npk, st
+
+
+def frames(y: torch.Tensor, pk: torch.Tensor, npk: torch.Tensor, hdr_pn: torch.Tensor):
+    """Per-peak front end (K4).  hdr_pn uint8[B,16] = packed 128 header-PN bits of each clip's key.
+    Returns dict(mf_aligned f32[B,4,25,1024], llr_best_s i32[B,4,25], hdr f32[B,4,25,4] = ok(-1 = no
+    frame), val, score, margin, hdr_best_s i32[B,4,25])."""
+    N.require_cuda(y, pk, npk, hdr_pn)
+    B, _, n = y.shape
+    dev = y.device
+    out = dict(
+        mf_aligned=torch.empty((B, 4, PEAK_LIMIT, NPAY), dtype=torch.float32, device=dev),
+        llr_best_s=torch.zeros((B, 4, PEAK_LIMIT), dtype=torch.int32, device=dev),
+        hdr=torch.zeros((B, 4, PEAK_LIMIT, 4), dtype=torch.float32, device=dev),
+        hdr_best_s=torch.zeros((B, 4, PEAK_LIMIT), dtype=torch.int32, device=dev),
+    )
+    N.check(N.lib().es_rx_frames(N.ptr(y), C.c_int(B), C.c_int(n), N.ptr(pk), N.ptr(npk), N.ptr(hdr_pn),
+                                 N.ptr(out["mf_aligned"]), N.ptr(out["llr_best_s"]), N.ptr(out["hdr"]),
+                                 N.ptr(out["hdr_best_s"]), N.stream_ptr()), "es_rx_frames")
+    return out
+
+
+def llr(mf_aligned: torch.Tensor, item_peak: torch.Tensor, pn_packed: torch.Tensor) -> torch.Tensor:
+    """K5: item_peak i32[I] = flat (clip*4+band)*25+slot index, pn_packed uint8[I,152] (1215 PN bits,
+    MSB-first) -> llr f32[2*I,1024], row 2i = PN variant 0, row 2i+1 = variant 1 (rtwm/detector.py:306-314)."""
+    N.require_cuda(mf_aligned, item_peak, pn_packed)
+    I = int(item_peak.numel())
+    out = torch.empty((2 * I, NPAY), dtype=torch.float32, device=mf_aligned.device)
+    if I:
+        if pn_packed.shape != (I, 152) or pn_packed.dtype != torch.uint8:
+            raise ValueError("pn_packed must be uint8 [items,152]")
+        N.check(N.lib().es_rx_llr(N.ptr(mf_aligned), N.ptr(item_peak), N.ptr(pn_packed), C.c_int(I), N.ptr(out),
+                                  N.stream_ptr()), "es_rx_llr")
+    return out

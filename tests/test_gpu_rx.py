@@ -1,0 +1,128 @@
+"""GPU parity of the RX scan path (K1-K5 + host orchestration) through the C-ABI against the
+oracle (oracle/detector_oracle.py) and the reference-generated golden vectors."""
+import os
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from _inputs import CLIP_SPECS, make_clip
+
+G = np.load(os.path.join(os.path.dirname(__file__), "golden", "rx_golden.npz"))
+NAMES = list(CLIP_SPECS)
+
+
+@pytest.fixture(scope="module")
+def env():
+    import torch
+    from echoseal_b200 import rx_gpu, detector
+    from echoseal_b200.utils import BAND_PLAN
+    clips = {n: make_clip(n) for n in NAMES}
+    taps = [rx_gpu.matched_filter_taps(b, 48000) for b in BAND_PLAN]
+    rx_gpu.set_filters(48000, taps)
+    return torch, rx_gpu, detector, clips, taps
+
+
+def test_host_constants_match_reference(env):
+    torch, rx_gpu, detector, clips, taps = env
+    from echoseal_b200.utils import BAND_PLAN
+    for bi, band in enumerate(BAND_PLAN):
+        np.testing.assert_array_equal(taps[bi], G[f"chirp_aa/b{bi}/mf_taps"])
+        np.testing.assert_array_equal(rx_gpu.preamble_template(band, 48000), G[f"chirp_aa/b{bi}/tpl"])
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_scan_stages_vs_oracle_and_golden(env, name):
+    torch, rx_gpu, detector, clips, taps = env
+    from oracle import detector_oracle as do
+    audio, key = clips[name]
+    x = torch.from_numpy(audio[None]).cuda()
+    y = rx_gpu.bandpass(x)
+    corr = rx_gpu.ncc(y)
+    pk, npk, st = rx_gpu.peaks(corr)
+    y_h, c_h = y.cpu().numpy()[0], corr.cpu().numpy()[0]
+    pk_h, npk_h, st_h = pk.cpu().numpy()[0], npk.cpu().numpy()[0], st.cpu().numpy()[0]
+    for bi, band in enumerate(do.BAND_PLAN):
+        ref = do.scan_band(audio, band)
+        scale = np.abs(ref["y"]).max() + 1e-300
+        assert np.abs(y_h[bi] - ref["y"]).max() / scale < 1e-9          # filtered signal: 1e-4 required
+        assert np.abs(c_h[bi] - ref["corr"]).max() < 1e-7                # correlation: 1e-4 required
+        med, mad, thr, npk_ref, fb = G[f"{name}/b{bi}/stats"]
+        np.testing.assert_allclose(st_h[bi, :3], [med, mad, thr], rtol=1e-7, atol=1e-12)
+        assert int(st_h[bi, 3]) == int(fb)
+        want = list(G[f"{name}/b{bi}/peaks"])[:25]
+        got = [int(v) for v in pk_h[bi, :npk_h[bi]]]
+        assert got == want, (name, bi)                                   # sync offsets: bit-exact
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_verify_details_vs_golden(env, name):
+    """Header tuples, attempted (start, ctr) lists incl. the 400-try budget, LLRs and the verdict."""
+    torch, rx_gpu, detector, clips, taps = env
+    from oracle import detector_oracle as do
+    from oracle import tx_oracle as txo
+    audio, key = clips[name]
+    v, res = detector.verify_batch([key], audio[None], details=True)
+    r = res[0]
+    assert v[0] == False
+    k = txo.Keys(key)
+    for bi, band in enumerate(do.BAND_PLAN):
+        pre = f"{name}/b{bi}/"
+        hdr_ref = G[pre + "hdr"]
+        valid = [s for s in range(int(r.npeaks[bi])) if 0 <= r.peaks[bi, s] and r.peaks[bi, s] + 1215 <= audio.size]
+        # the reference decodes headers peak by peak until the budget stops it
+        got = np.array([[r.hdr[bi, s, 0], r.hdr[bi, s, 1], r.hdr[bi, s, 2]] for s in valid]).reshape(-1, 3)[: hdr_ref.shape[0]]
+        assert got.shape == hdr_ref.shape
+        assert (got[:, :2] == hdr_ref[:, :2]).all(), (name, bi)
+        np.testing.assert_allclose(got[:, 2], hdr_ref[:, 2], rtol=2e-3)
+        assert [c for _, c in r.attempts[bi]] == list(G[pre + "att_ctr"]), (name, bi)
+
+
+def test_llr_vs_oracle(env):
+    torch, rx_gpu, detector, clips, taps = env
+    from oracle import detector_oracle as do
+    from oracle import tx_oracle as txo
+    for name in ("chirp_aa", "silence_ee", "bench_17"):
+        audio, key = clips[name]
+        k = txo.Keys(key)
+        x = torch.from_numpy(audio[None]).cuda()
+        y = rx_gpu.bandpass(x)
+        pk, npk, st = rx_gpu.peaks(rx_gpu.ncc(y))
+        hdr_pn = torch.from_numpy(np.packbits(k.pn_bits(0, 128))[None]).cuda()
+        fr = rx_gpu.frames(y, pk, npk, hdr_pn)
+        pk_h, npk_h = pk.cpu().numpy()[0], npk.cpu().numpy()[0]
+        bs_h = fr["llr_best_s"].cpu().numpy()[0]
+        items, ctrs, refs = [], [], []
+        for bi, band in enumerate(do.BAND_PLAN):
+            ref = do.scan_band(audio, band)
+            h = do.matched_filter_taps(band)
+            for slot in range(min(3, int(npk_h[bi]))):
+                start = int(pk_h[bi, slot])
+                if start + 1215 > audio.size:
+                    continue
+                frame = ref["y"][start:start + 1215]
+                for ctr in (0, 7, 123456):
+                    pn_full = k.pn_bits(ctr, 1215)
+                    l0, s0 = do.llr(frame, h, pn_full[191:])
+                    l1, s1 = do.llr(frame, h, pn_full[:1024])
+                    assert s0 == s1 == int(bs_h[bi, slot])
+                    items.append(bi * 25 + slot); ctrs.append(ctr); refs.append((l0, l1))
+        pn = np.stack([np.packbits(k.pn_bits(c, 1215)) for c in ctrs])
+        out = rx_gpu.llr(fr["mf_aligned"], torch.tensor(items, dtype=torch.int32).cuda(),
+                         torch.from_numpy(pn).cuda()).cpu().numpy()
+        for i, (l0, l1) in enumerate(refs):
+            # LLR parity: 1e-4 relative (to the +-12 clip range)
+            assert np.abs(out[2 * i] - l0).max() <= 1e-4 * 12.0
+            assert np.abs(out[2 * i + 1] - l1).max() <= 1e-4 * 12.0
+
+
+def test_edge_cases(env):
+    torch, rx_gpu, detector, clips, taps = env
+    key = bytes([0x33]) * 32
+    rx = detector.WatermarkDetector(key)
+    assert rx.verify(np.zeros(0, np.float32), 48000) is False          # empty audio (rtwm/detector.py:72-73)
+    assert rx.verify(np.zeros(40, np.float32), 48000) is False         # shorter than the template
+    assert rx.verify(np.zeros(2000, np.float32), 48000) is False       # silence: degenerate order statistics
+    assert rx.verify(np.ones(70, np.float32), 48000) is False          # corr shorter than a frame
+    with pytest.raises(ValueError):
+        detector.WatermarkDetector(b"short")
