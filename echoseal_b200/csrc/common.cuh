@@ -28,4 +28,7 @@ constexpr int POLAR_NLOG = 10;
 // device info cache
 int sm_count();
 
+// tx.cu keeps its own constant-memory copy of the polar code layout
+int tx_set_code(const uint16_t* pos, int K);
+
 }  // namespace es

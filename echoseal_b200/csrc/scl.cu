@@ -592,6 +592,7 @@ int es_polar_set_code(const uint8_t* frozen_host, int K)
     ES_CUDA_OK(cudaMemcpyToSymbol(c_frozen, words, sizeof(words)));
     ES_CUDA_OK(cudaMemcpyToSymbol(c_datapos, pos, sizeof(pos)));
     ES_CUDA_OK(cudaMemcpyToSymbol(c_K, &K, sizeof(int)));
+    { const int rc = tx_set_code(pos, K); if (rc != ES_OK) return rc; }
     g_code_ready = 1;
     g_K = K;
     return ES_OK;

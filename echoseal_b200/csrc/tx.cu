@@ -1,0 +1,253 @@
+// echoseal_b200/csrc/tx.cu — embed-side kernels, hand-written for sm_100a:
+//   K7  es_tx_frames : CRC-8 + polar encode + header/PN spreading + zero-state hop-band band-pass
+//                      of one 1215-chip frame per lane (rtwm/embedder.py:78-151, rtwm/fastpolar.py:237-252)
+//   K8  es_tx_mix    : level-controlled mix  out = x + chips*scale  per stream block
+//                      (rtwm/embedder.py:50-75)
+// Host inputs (stay on the host by design): sealed payload (ChaCha20-Poly1305), PN bits (AES-ECB),
+// hop band (HMAC), header PN of the key.
+#include "common.cuh"
+
+namespace es {
+
+constexpr int TX_FRAME = 1215, TX_PRE = 63, TX_HDR = 128, TX_PAY = 1024;
+constexpr int TX_SYM_WORDS = 38;          // 1216 sign bits per frame
+
+// this translation unit's copy of the polar code layout (filled by es_polar_set_code via tx_set_code)
+__constant__ uint16_t c_datapos[1024];
+__constant__ int c_K;
+static int g_tx_code_ready = 0;
+
+int tx_set_code(const uint16_t* pos, int K)
+{
+    ES_CUDA_OK(cudaMemcpyToSymbol(c_datapos, pos, sizeof(uint16_t) * 1024));
+    ES_CUDA_OK(cudaMemcpyToSymbol(c_K, &K, sizeof(int)));
+    g_tx_code_ready = 1;
+    return ES_OK;
+}
+
+__constant__ double c_tx_b[4][9];
+__constant__ double c_tx_a[4][9];
+__constant__ uint32_t c_pre_words[2];     // 63 preamble sign bits (bit i = chip i is +1)
+static int g_tx_ready = 0;
+
+__device__ __forceinline__ uint32_t tx_xform_word(uint32_t x)
+{
+    x ^= (x >> 1) & 0x55555555u;
+    x ^= (x >> 2) & 0x33333333u;
+    x ^= (x >> 4) & 0x0f0f0f0fu;
+    x ^= (x >> 8) & 0x00ff00ffu;
+    x ^= (x >> 16) & 0x0000ffffu;
+    return x;
+}
+__device__ __forceinline__ uint8_t tx_crc8_bit(uint8_t reg, uint32_t bit)
+{
+    reg ^= (uint8_t)(bit << 7);
+    return (reg & 0x80) ? (uint8_t)((reg << 1) ^ 0x07) : (uint8_t)(reg << 1);
+}
+__device__ __forceinline__ uint32_t msb_bit(const uint8_t* p, int q) { return (p[q >> 3] >> (7 - (q & 7))) & 1u; }
+
+// One warp = 32 frames.  Phase 1 (cooperative, frame by frame): sign bits of the 1215 symbols into shared
+// memory.  Phase 2: lane f runs the order-8 IIR over frame f from zero state (fp64, scipy's DF-II-transposed
+// operation order); outputs are staged 32x32 in shared memory so global writes are 128-byte rows.
+struct TxWarpShared {
+    uint32_t sym[32][TX_SYM_WORDS + 1];   // +1: conflict-free column reads
+    float tile[32][33];
+    uint32_t u[32];
+};
+
+__global__ void __launch_bounds__(128) tx_frames_kernel(const uint8_t* __restrict__ payload /*[F][nbytes]*/,
+                                                        const uint8_t* __restrict__ pn /*[F][152]*/,
+                                                        const uint8_t* __restrict__ hdr_pn /*[F][16]*/,
+                                                        const int32_t* __restrict__ band /*[F]*/,
+                                                        const int32_t* __restrict__ ctr_lo16 /*[F]*/,
+                                                        int nframes, float* __restrict__ chips /*[F][1215]*/)
+{
+    __shared__ TxWarpShared SH[4];
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+    TxWarpShared& S = SH[wl];
+    const int f0 = (blockIdx.x * 4 + wl) * 32;
+    if (f0 >= nframes) return;
+    const int K = c_K, nbytes = (K - 8) >> 3;
+    // ---------------- phase 1: symbols
+    for (int r = 0; r < 32; ++r) {
+        const int f = f0 + r;
+        if (f >= nframes) break;
+        const uint8_t* pay = payload + (size_t)f * nbytes;
+        const uint8_t* pnf = pn + (size_t)f * 152;
+        const uint8_t* hp = hdr_pn + (size_t)f * 16;
+        uint8_t crc = 0;
+        for (int b = 0; b < nbytes; ++b) {
+            const uint8_t byte = __ldg(pay + b);
+#pragma unroll
+            for (int t = 7; t >= 0; --t) crc = tx_crc8_bit(crc, (byte >> t) & 1u);
+        }
+        S.u[lane] = 0;
+        __syncwarp();
+        for (int q = lane; q < K; q += 32) {
+            const int bi = q >> 3;
+            const uint8_t byte = (bi < nbytes) ? __ldg(pay + bi) : crc;
+            if ((byte >> (7 - (q & 7))) & 1u) { const int pos = c_datapos[q]; atomicOr(&S.u[pos >> 5], 1u << (pos & 31)); }
+        }
+        __syncwarp();
+        uint32_t x = tx_xform_word(S.u[lane]);
+#pragma unroll
+        for (int h = 1; h < 32; h <<= 1) {
+            const uint32_t v = __shfl_down_sync(full, x, h);
+            if (!(lane & h)) x ^= v;
+        }
+        // x = code bits 32*lane .. 32*lane+31.  symbol sign bit = 1 for +1.
+        // payload chip j (frame index 191+j): data ^ pn == 0 -> (+1)(+1) or (-1)(-1) = +1  => sign = ~(data ^ pn)
+        uint32_t pw = 0;
+#pragma unroll 4
+        for (int t = 0; t < 32; ++t) pw |= msb_bit(pnf, TX_PRE + TX_HDR + lane * 32 + t) << t;
+        const uint32_t sw = ~(x ^ pw);
+        // scatter into the frame's sign words at bit offset 191 + 32*lane
+        __syncwarp();
+        for (int wq = lane; wq < TX_SYM_WORDS; wq += 32) S.sym[r][wq] = 0;
+        __syncwarp();
+        {
+            const int bitpos = TX_PRE + TX_HDR + lane * 32;
+            const int w0 = bitpos >> 5, sh = bitpos & 31;       // sh = 31
+            atomicOr(&S.sym[r][w0], sw << sh);
+            atomicOr(&S.sym[r][w0 + 1], sw >> (32 - sh));
+        }
+        // preamble (63) + header (128): header chip k = (2*bit-1) * hdrpn  => sign = ~(bit ^ hdrpn_bit)
+        if (lane < 2) atomicOr(&S.sym[r][lane], c_pre_words[lane]);
+        const int lo16 = ctr_lo16[f] & 0xffff;
+        for (int k = lane; k < TX_HDR; k += 32) {
+            const uint32_t hb = (lo16 >> (15 - (k >> 3))) & 1u;          // MSB-first, each bit repeated 8x
+            const uint32_t s = (~(hb ^ msb_bit(hp, k))) & 1u;
+            const int bitpos = TX_PRE + k;
+            if (s) atomicOr(&S.sym[r][bitpos >> 5], 1u << (bitpos & 31));
+        }
+        __syncwarp();
+    }
+    // ---------------- phase 2: IIR per lane
+    const int f = f0 + lane;
+    const bool live = f < nframes;
+    const int bd = live ? (band[f] & 3) : 0;
+    double b[9], a[9], z[8];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { b[i] = c_tx_b[bd][i]; a[i] = c_tx_a[bd][i]; }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) z[i] = 0.0;
+    double peak = 0.0;
+    for (int pass = 0; pass < 2; ++pass) {
+        const double gain = (pass == 0) ? 1.0 : 1.0 / (peak + 1e-12);
+        const bool need = (pass == 0) || (peak + 1e-12 > 3.0);         // rtwm/embedder.py:147-149
+        if (pass == 1 && !__any_sync(full, need && live)) break;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) z[i] = 0.0;
+        for (int j0 = 0; j0 < TX_FRAME; j0 += 32) {
+            uint32_t sw = 0;
+            {   // 32 sign bits starting at j0 (word aligned)
+                sw = S.sym[lane][j0 >> 5];
+            }
+            const int jn = min(32, TX_FRAME - j0);
+            for (int t = 0; t < jn; ++t) {
+                const double xn = ((sw >> t) & 1u) ? 1.0 : -1.0;
+                const double yn = fma(b[0], xn, z[0]);
+#pragma unroll
+                for (int i = 0; i < 7; ++i) z[i] = fma(-a[i + 1], yn, fma(b[i + 1], xn, z[i + 1]));
+                z[7] = fma(-a[8], yn, b[8] * xn);
+                if (pass == 0) peak = fmax(peak, fabs(yn));
+                S.tile[lane][t] = (float)(yn * gain);
+            }
+            __syncwarp();
+            for (int r = 0; r < 32; ++r) {
+                const int fr = f0 + r;
+                const bool wr = (fr < nframes) && (lane < jn);
+                // on the rescale pass only frames whose peak exceeded 3.0 are rewritten
+                const bool needr = __shfl_sync(full, (int)need, r);
+                if (wr && needr) chips[(size_t)fr * TX_FRAME + j0 + lane] = S.tile[r][lane];
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K8: mix.  One CTA per stream block: block RMS / peaks (fp64 accumulation), scale, axpy.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) tx_mix_kernel(const float* __restrict__ x, const float* __restrict__ chips,
+                                                     int nstreams, int blk, double alpha, double floor_scale,
+                                                     float* __restrict__ out, float* __restrict__ scale_out)
+{
+    __shared__ double red[3][8];
+    __shared__ float s_scale;
+    const int s = blockIdx.x;
+    const int tid = threadIdx.x;
+    const float* xs = x + (size_t)s * blk;
+    const float* cs = chips + (size_t)s * blk;
+    double e = 0.0; float px = 0.0f, pc = 0.0f;
+    for (int i = tid; i < blk; i += 256) {
+        const float v = xs[i];
+        e += (double)(v * v);
+        px = fmaxf(px, fabsf(v));
+        pc = fmaxf(pc, fabsf(cs[i]));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        e += __shfl_xor_sync(0xffffffffu, e, o);
+        px = fmaxf(px, __shfl_xor_sync(0xffffffffu, px, o));
+        pc = fmaxf(pc, __shfl_xor_sync(0xffffffffu, pc, o));
+    }
+    if ((tid & 31) == 0) { red[0][tid >> 5] = e; red[1][tid >> 5] = px; red[2][tid >> 5] = pc; }
+    __syncthreads();
+    if (tid == 0) {
+        double et = 0.0; float pxt = 0.0f, pct = 0.0f;
+        for (int q = 0; q < 8; ++q) { et += red[0][q]; pxt = fmaxf(pxt, (float)red[1][q]); pct = fmaxf(pct, (float)red[2][q]); }
+        const double in_rms = (double)sqrtf((float)(et / blk)) + 1e-12;       // float(np.sqrt(np.mean(x*x)) + EPS)
+        double sc = fmax(alpha * in_rms, floor_scale);
+        double headroom = 0.98 - (double)pxt;
+        if (headroom < 0.0) headroom = 0.0;
+        const double peak = (double)pct + 1e-12;
+        sc = fmin(sc, headroom / peak);
+        s_scale = (float)sc;
+        if (scale_out) scale_out[s] = (float)sc;
+    }
+    __syncthreads();
+    const float sc = s_scale;
+    float* os = out + (size_t)s * blk;
+    for (int i = tid; i < blk; i += 256) os[i] = __fadd_rn(xs[i], __fmul_rn(cs[i], sc));   // two roundings, as numpy
+}
+
+}  // namespace es
+
+using namespace es;
+
+extern "C" {
+
+int es_tx_set_filters(const double* bp_b /*[4][9]*/, const double* bp_a /*[4][9]*/, const uint8_t* preamble_bits /*[63]*/)
+{
+    uint32_t w[2] = {0, 0};
+    for (int i = 0; i < TX_PRE; ++i) if (preamble_bits[i]) w[i >> 5] |= 1u << (i & 31);
+    ES_CUDA_OK(cudaMemcpyToSymbol(c_tx_b, bp_b, sizeof(double) * 36));
+    ES_CUDA_OK(cudaMemcpyToSymbol(c_tx_a, bp_a, sizeof(double) * 36));
+    ES_CUDA_OK(cudaMemcpyToSymbol(c_pre_words, w, sizeof(w)));
+    g_tx_ready = 1;
+    return ES_OK;
+}
+
+int es_tx_frames(const uint8_t* payload, const uint8_t* pn, const uint8_t* hdr_pn, const int32_t* band,
+                 const int32_t* ctr_lo16, int nframes, float* chips, void* stream)
+{
+    if (!g_tx_ready || !g_tx_code_ready) { set_error("es_tx_frames: call es_tx_set_filters and es_polar_set_code first"); return ES_ENOTREADY; }
+    if (nframes <= 0) return ES_OK;
+    const int per_cta = 128;
+    tx_frames_kernel<<<(nframes + per_cta - 1) / per_cta, 128, 0, (cudaStream_t)stream>>>(payload, pn, hdr_pn, band, ctr_lo16, nframes, chips);
+    ES_CUDA_OK(cudaGetLastError());
+    return ES_OK;
+}
+
+int es_tx_mix(const float* x, const float* chips, int nstreams, int blk, double alpha, double floor_scale,
+              float* out, float* scale_out, void* stream)
+{
+    if (nstreams <= 0 || blk <= 0) return ES_OK;
+    tx_mix_kernel<<<nstreams, 256, 0, (cudaStream_t)stream>>>(x, chips, nstreams, blk, alpha, floor_scale, out, scale_out);
+    ES_CUDA_OK(cudaGetLastError());
+    return ES_OK;
+}
+
+}  // extern "C"

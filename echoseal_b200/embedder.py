@@ -1,0 +1,120 @@
+"""B200-native drop-in for rtwm/embedder.py (WatermarkEmbedder, TxParams): embed-side spreading.
+
+Same class names, constructor arguments, methods and state attributes as the reference
+(rtwm/embedder.py:20-168).  Frame synthesis (CRC-8 + polar encode + PN spread + header + zero-state
+hop-band band-pass) and the level-controlled mix run in the sm_100a kernels behind the C-ABI; the
+payload sealing (ChaCha20-Poly1305), the PN bits (AES-ECB) and the hop band (HMAC) are produced on
+the host and fed to the kernels (BASELINE.json north_star).  `EmbedderBank` is the additive batched
+form: many concurrent streams per launch.  No CPU fallback."""
+from __future__ import annotations
+from dataclasses import dataclass, field
+import secrets
+import numpy as np
+import torch
+
+from . import tx_gpu
+from .crypto import SecureChannel
+from .utils import choose_band_index, db_to_lin, mseq_63
+
+N_DEFAULT = 1024
+K_DEFAULT = 448
+EPS = 1e-12
+MIN_RMS_SILENCE = 1e-4
+MIX_HEADROOM = 0.98
+HDR_BITS = 16
+HDR_REPEAT = 8
+HDR_L = 128
+FRAME_LEN = 63 + HDR_L + N_DEFAULT
+
+
+@dataclass(slots=True)
+class TxParams:
+    """rtwm/embedder.py:20-27"""
+    fs: int = 48_000
+    target_rel_db: float = -10.0
+    floor_rel_dbfs: float = -35.0
+    N: int = N_DEFAULT
+    K: int = K_DEFAULT
+    preamble: np.ndarray = field(default_factory=lambda: mseq_63())
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        raise RuntimeError("echoseal_b200 needs a CUDA device (no CPU fallback)")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+class WatermarkEmbedder:
+    def __init__(self, key32: bytes, params: TxParams | None = None) -> None:
+        self.p = params or TxParams()
+        if self.p.N != N_DEFAULT:
+            raise ValueError("the B200 path implements Polar(1024, K) only")
+        self.sec = SecureChannel(key32)
+        self._band_key = getattr(self.sec, "band_key", key32)
+        self.frame_ctr = 0
+        self._chip_buf: np.ndarray | None = None
+        self._session_nonce = secrets.token_bytes(8)
+        self._preamble_sy = 2.0 * self.p.preamble.astype(np.float32) - 1.0
+        self._hdr_pn_bits = self.sec.pn_bits(0, HDR_L)
+        self._hdr_pn_sy = 2.0 * self._hdr_pn_bits.astype(np.float32) - 1.0
+        self._hdr_pn_packed = np.packbits(self._hdr_pn_bits)
+
+    # ------------------------------------------------------------------ API
+    def process(self, samples: np.ndarray) -> np.ndarray:
+        """rtwm/embedder.py:44-75 — one call = one block: block RMS, floor, headroom limiter."""
+        if self._chip_buf is None:
+            self._chip_buf = np.empty(0, dtype=np.float32)
+        x = np.ascontiguousarray(samples, dtype=np.float32).reshape(-1)
+        needed = x.size
+        if needed == 0:
+            return x.copy()
+        missing = needed - self._chip_buf.size
+        if missing > 0:
+            nfr = (missing + FRAME_LEN - 1) // FRAME_LEN
+            chips = self._make_frames(nfr)
+            self._chip_buf = np.concatenate((self._chip_buf, chips.reshape(-1)))
+        chips = self._chip_buf[:needed]
+        self._chip_buf = self._chip_buf[needed:]
+        dev = _dev()
+        xd = torch.from_numpy(x[None]).to(dev)
+        cd = torch.from_numpy(np.ascontiguousarray(chips)[None]).to(dev)
+        out, _ = tx_gpu.mix(xd, cd, db_to_lin(self.p.target_rel_db), db_to_lin(self.p.floor_rel_dbfs))
+        return out[0].cpu().numpy()
+
+    # ------------------------------------------------------------------ internals
+    def _frame_inputs(self, ctr: int, payload: bytes):
+        band = choose_band_index(self._band_key, ctr)
+        pn = self.sec.pn_bytes_batch(np.array([ctr], np.uint64), FRAME_LEN)[0]
+        return payload, pn, band, ctr & 0xFFFF
+
+    def _synth(self, items) -> np.ndarray:
+        """items: list of (payload55, pn152, band, ctr_lo16) -> float32[F,1215] via K7."""
+        dev = _dev()
+        tx_gpu.set_filters(self.p.fs, self.p.preamble)
+        F = len(items)
+        pay = torch.from_numpy(np.frombuffer(b"".join(i[0] for i in items), np.uint8).reshape(F, -1).copy()).to(dev)
+        pn = torch.from_numpy(np.stack([i[1] for i in items])).to(dev)
+        hp = torch.from_numpy(np.tile(self._hdr_pn_packed, (F, 1))).to(dev)
+        band = torch.tensor([i[2] for i in items], dtype=torch.int32, device=dev)
+        lo16 = torch.tensor([i[3] for i in items], dtype=torch.int32, device=dev)
+        return tx_gpu.frames(pay, pn, hp, band, lo16, K=self.p.K).cpu().numpy()
+
+    def _make_frames(self, nframes: int) -> np.ndarray:
+        """Generate the next `nframes` frames and advance frame_ctr (the loop of rtwm/embedder.py:54-58)."""
+        items = []
+        for _ in range(nframes):
+            items.append(self._frame_inputs(self.frame_ctr, self._build_payload()))
+            self.frame_ctr = (self.frame_ctr + 1) % (2 ** 32)
+        return self._synth(items)
+
+    def _make_frame_chips(self) -> np.ndarray:
+        """One frame for the current counter; does NOT advance frame_ctr (rtwm/embedder.py:78-151)."""
+        return self._synth([self._frame_inputs(self.frame_ctr, self._build_payload())])[0]
+
+    def _build_payload(self) -> bytes:
+        """rtwm/embedder.py:153-168: "ESAL" | ctr_be32 | session nonce(8) | 11 random -> sealed 55 bytes."""
+        meta = b"ESAL" + self.frame_ctr.to_bytes(4, "big") + self._session_nonce + secrets.token_bytes(11)
+        assert len(meta) == 27
+        blob = self.sec.seal(meta)
+        assert len(blob) == 55
+        return blob
