@@ -18,7 +18,7 @@ import torch
 
 from . import polar_gpu, rx_gpu
 from .crypto import SecureChannel
-from .utils import BAND_PLAN, choose_band, hop_table, mseq_63, resample_ratio
+from .utils import BAND_PLAN, choose_band, mseq_63, resample_ratio
 
 PRE_BITS = mseq_63()
 PRE_L = len(PRE_BITS)
@@ -34,65 +34,51 @@ MAX_TRIES = 400       # rtwm/detector.py:107
 PEAK_LIMIT = 25       # rtwm/detector.py:108
 
 
-class _KeyCtx:
-    """Host-side per-key material: AEAD / PN channel, hop table, packed header PN."""
-
-    def __init__(self, key32: bytes):
-        self.sec = SecureChannel(key32)
-        self.band_key = getattr(self.sec, "band_key", key32)          # rtwm/detector.py:31 (quirk 9)
-        self.hdr_pn_bits = self.sec.pn_bits(0, HDR_L)
-        self.hdr_pn_packed = np.packbits(self.hdr_pn_bits)            # 16 bytes
-        self._hop = np.zeros(0, np.uint8)
-
-    def hop(self, hi: int) -> np.ndarray:
-        """band index of every counter in [0, hi)"""
-        if self._hop.size < hi:
-            grow = max(hi, 2 * self._hop.size, 512)
-            self._hop = np.concatenate([self._hop, hop_table(self.band_key, self._hop.size, grow)])
-        return self._hop
-
-
-def _candidate_counters(start: int, hdr_ok: bool, ctr_lo16: int, band_idx: int, kc: _KeyCtx) -> list[int]:
-    """rtwm/detector.py:117-142"""
-    ctr_est = int(round(start / FRAME_LEN))
-    lo, hi = max(0, ctr_est - WIDE_DELTA), ctr_est + WIDE_DELTA + 1
-    hop = kc.hop(hi)
-    if hdr_ok:
-        c = np.arange(lo, hi)
-        return [int(v) for v in c[((c & 0xFFFF) == ctr_lo16) & (hop[lo:hi] == band_idx)]]
-    tl, th = max(0, ctr_est - TIGHT_DELTA), ctr_est + TIGHT_DELTA + 1
-    c = np.arange(tl, th)
-    c = c[hop[tl:th] == band_idx]
-    if c.size == 0:
-        c = np.arange(lo, hi)
-        c = c[hop[lo:hi] == band_idx]
-    return [int(v) for v in c]
-
-
 class RxResult:
     """Per-clip intermediates of one batch pass (sync offsets, thresholds, header tuples, attempts)."""
     __slots__ = ("verdict", "peaks", "npeaks", "stats", "hdr", "attempts", "payload", "nonce", "n_scl")
 
 
-def _validate(kc: _KeyCtx, payload: bytes, ctr: int):
-    """The reference's validator + post-checks (rtwm/detector.py:168-175, 197-221): AEAD open, magic,
-    counter.  Returns the plaintext or None."""
-    try:
-        pt = kc.sec.open(payload)
-    except Exception:
-        return None
-    if not pt.startswith(b"ESAL"):
-        return None
-    if int.from_bytes(pt[4:8], "big") != ctr:
-        return None
-    return pt
+def _bank_for(keys):
+    """KeyBank over the distinct keys + key index per clip."""
+    from .host_feeder import KeyBank
+    uniq, idx = {}, np.empty(len(keys), np.int32)
+    for i, k in enumerate(keys):
+        k = bytes(k)
+        j = uniq.get(k)
+        if j is None:
+            j = uniq[k] = len(uniq)
+        idx[i] = j
+    return KeyBank(list(uniq)), idx
+
+
+def _decode_phase(bank, key_idx_sub, enum, mf_aligned, list_size, nonce_state, dev):
+    """K5 + K6 for every enumerated item, then the host AEAD validation in the reference's order.
+    Returns (verdict u8[nb], plaintext u8[nb,27])."""
+    I = int(enum["item_peak"].size)
+    hit_cw = np.zeros(0, np.int64); hit_slot = np.zeros(0, np.int32); hit_pay = np.zeros((0, 55), np.uint8)
+    if I:
+        ip = torch.from_numpy(enum["item_peak"]).to(dev)
+        pn = torch.from_numpy(enum["pn"]).to(dev)
+        llr = rx_gpu.llr(mf_aligned, ip, pn)                       # [2I,1024]: variant 0 / 1 per item
+        pay_h, crc_h = polar_gpu.hard_decide(llr, neg_mode=1)      # 4I codewords: +v0, -v0, +v1, -v1
+        out = polar_gpu.list_decode(llr, list_size=list_size, neg_mode=1)
+        # only CRC-passing candidates travel back: (codeword, slot) with slot 0 = hard decision, 1.. = list rank+1
+        flags = torch.cat([crc_h[:, None], out["crc"]], dim=1)
+        idx = torch.nonzero(flags, as_tuple=False)                 # row-major = sorted by (codeword, slot)
+        if idx.numel():
+            allpay = torch.cat([pay_h[:, None, :], out["payload"]], dim=1)
+            hit_pay = allpay[idx[:, 0], idx[:, 1]].cpu().numpy()
+            idx_h = idx.cpu().numpy()
+            hit_cw = idx_h[:, 0].astype(np.int64); hit_slot = idx_h[:, 1].astype(np.int32)
+    return bank.rx_validate(key_idx_sub, enum, hit_cw, hit_slot, hit_pay, nonce_state)
 
 
 def verify_batch(keys, audio, *, fs_target: int = 48_000, list_size: int = 8, mf_taps=None,
-                 session_nonces=None, sub_batch: int = 256, details: bool = False):
+                 session_nonces=None, sub_batch: int = 512, details: bool = False, bank=None, key_idx=None):
     """Verify B clips (already at fs_target) in one pass.
 
-    keys   : list of B 32-byte keys (or one key for all clips)
+    keys   : list of B 32-byte keys (or one key for all clips); or pass a prebuilt (bank, key_idx)
     audio  : float32 [B, n] numpy array (host; copied through pinned memory) or CUDA tensor
     returns: bool[B] (and a list of RxResult when details=True)
     The per-clip semantics are exactly those of WatermarkDetector.verify (rtwm/detector.py:44-152):
@@ -106,28 +92,32 @@ def verify_batch(keys, audio, *, fs_target: int = 48_000, list_size: int = 8, mf
     is_tensor = isinstance(audio, torch.Tensor)
     B = int(audio.shape[0])
     n = int(audio.shape[1]) if audio.ndim == 2 else 0
-    if isinstance(keys, (bytes, bytearray)):
-        keys = [bytes(keys)] * B
-    if len(keys) != B:
-        raise ValueError("need one key per clip")
-    kcs = {}
-    for k in keys:
-        if k not in kcs:
-            kcs[k] = _KeyCtx(k)
+    if bank is None:
+        if isinstance(keys, (bytes, bytearray)):
+            keys = [bytes(keys)] * B
+        if len(keys) != B:
+            raise ValueError("need one key per clip")
+        bank, key_idx = _bank_for(keys)
+    key_idx = np.ascontiguousarray(key_idx, np.int32)
     if mf_taps is None:
         mf_taps = [rx_gpu.matched_filter_taps(b, fs_target) for b in BAND_PLAN]
     rx_gpu.set_filters(fs_target, mf_taps)
     verdicts = np.zeros(B, bool)
     results = [None] * B
-    if session_nonces is None:
-        session_nonces = [None] * B
+    nonce_state = np.zeros((B, 9), np.uint8)
+    if session_nonces is not None:
+        for i, sn in enumerate(session_nonces):
+            if sn:
+                nonce_state[i, 0] = 1
+                nonce_state[i, 1:] = np.frombuffer(sn, np.uint8)
     dev = torch.device("cuda", torch.cuda.current_device())
     for s0 in range(0, B, sub_batch):
         s1 = min(B, s0 + sub_batch)
         nb = s1 - s0
+        kidx = key_idx[s0:s1]
         if n < PRE_L:      # rtwm/detector.py:72-73: shorter than the template -> False for every band
-            for i in range(s0, s1):
-                if details:
+            if details:
+                for i in range(s0, s1):
                     r = RxResult(); r.verdict = False; r.peaks = np.full((4, PEAK_LIMIT), -1, np.int32)
                     r.npeaks = np.zeros(4, np.int32); r.stats = np.zeros((4, 4)); r.hdr = np.zeros((4, PEAK_LIMIT, 4), np.float32)
                     r.attempts = [[] for _ in range(4)]; r.payload = None; r.nonce = None; r.n_scl = 0
@@ -138,7 +128,7 @@ def verify_batch(keys, audio, *, fs_target: int = 48_000, list_size: int = 8, mf
         else:
             host = torch.from_numpy(np.ascontiguousarray(audio[s0:s1], dtype=np.float32)).pin_memory()
             x = host.to(dev, non_blocking=True)
-        hdr_pn = torch.from_numpy(np.stack([kcs[keys[i]].hdr_pn_packed for i in range(s0, s1)])).to(dev)
+        hdr_pn = torch.from_numpy(bank.hdr_pn(kidx)).to(dev)
         # ---- phase 1: scan (K1-K3) + per-peak front end (K4)
         y = rx_gpu.bandpass(x)
         corr = rx_gpu.ncc(y)
@@ -146,101 +136,34 @@ def verify_batch(keys, audio, *, fs_target: int = 48_000, list_size: int = 8, mf
         del corr
         fr = rx_gpu.frames(y, pk, npk, hdr_pn)
         del y
-        pk_h = pk.cpu().numpy(); npk_h = npk.cpu().numpy(); st_h = st.cpu().numpy()
-        hdr_h = fr["hdr"].cpu().numpy()
-        # ---- host: candidate counters, budget, PN (rtwm/detector.py:105-151)
-        item_peak, item_ctr, item_clip = [], [], []
-        attempts = [[[] for _ in range(4)] for _ in range(nb)]
-        pn_rows = []
-        for ci in range(nb):
-            kc = kcs[keys[s0 + ci]]
-            ctrs_clip = []
-            for bi in range(4):
-                tried = 0
-                for slot in range(int(npk_h[ci, bi])):
-                    start = int(pk_h[ci, bi, slot])
-                    if start < 0 or start + FRAME_LEN > n:
-                        continue
-                    ok = hdr_h[ci, bi, slot, 0] > 0.5
-                    val = int(hdr_h[ci, bi, slot, 1])
-                    stop = False
-                    for ctr in _candidate_counters(start, ok, val, bi, kc):
-                        item_peak.append((ci * 4 + bi) * PEAK_LIMIT + slot)
-                        item_ctr.append(ctr); item_clip.append(ci)
-                        attempts[ci][bi].append((start, ctr))
-                        ctrs_clip.append(ctr)
-                        tried += 1
-                        if tried >= MAX_TRIES:
-                            stop = True
-                            break
-                    if stop:
-                        break
-            if ctrs_clip:
-                pn_rows.append(kc.sec.pn_bytes_batch(np.array(ctrs_clip, np.uint64), FRAME_LEN))
-        I = len(item_peak)
-        hits = {}
-        if I:
-            ip = torch.tensor(item_peak, dtype=torch.int32, device=dev)
-            pn = torch.from_numpy(np.ascontiguousarray(np.concatenate(pn_rows, axis=0))).to(dev)
-            # ---- phase 2: despread -> LLR (K5) -> SCL-8 (K6), 4 codewords per item
-            llr = rx_gpu.llr(fr["mf_aligned"], ip, pn)
-            pay_h, crc_h = polar_gpu.hard_decide(llr, neg_mode=1)
-            out = polar_gpu.list_decode(llr, list_size=list_size, neg_mode=1)
-            # CRC-passing candidates only travel back: [codeword, slot (0 = hard, 1.. = list rank+1)]
-            flags = torch.cat([crc_h[:, None], out["crc"]], dim=1)
-            idx = torch.nonzero(flags, as_tuple=False)
-            if idx.numel():
-                allpay = torch.cat([pay_h[:, None, :], out["payload"]], dim=1)
-                sel = allpay[idx[:, 0], idx[:, 1]].cpu().numpy()
-                idx_h = idx.cpu().numpy()
-                for (w, sl), p in zip(idx_h, sel):
-                    hits.setdefault(int(w), []).append((int(sl), p.tobytes()))
-        # ---- host: first candidate that passes the AEAD validator, in the reference's order
-        item_base = np.zeros(nb + 1, np.int64)
-        for ci in item_clip:
-            item_base[ci + 1] += 1
-        item_base = np.cumsum(item_base)
-        for ci in range(nb):
-            gi = s0 + ci
-            kc = kcs[keys[gi]]
-            hop0 = int(kc.hop(1)[0])
-            order = [hop0] + [b for b in range(4) if b != hop0]
-            # items of this clip are stored band-major in BAND_PLAN order
-            offs = {}
-            o = int(item_base[ci])
-            for bi in range(4):
-                offs[bi] = o
-                o += len(attempts[ci][bi])
-            verdict, found_payload, nonce = False, None, session_nonces[gi]
-            for bi in order:
-                for a_i, (start, ctr) in enumerate(attempts[ci][bi]):
-                    it = offs[bi] + a_i
-                    good = None
-                    for v in range(4):
-                        for sl, p in sorted(hits.get(4 * it + v, [])):
-                            pt = _validate(kc, p, ctr)
-                            if pt is not None:
-                                good = pt
-                                break
-                        if good is not None:
-                            break
-                    if good is None:
-                        continue
-                    fn = good[8:16]                       # session-nonce latch (rtwm/detector.py:223-233)
-                    if nonce is None or fn == nonce:
-                        nonce = fn
-                        verdict, found_payload = True, good
-                        break
-                if verdict:
-                    break
-            verdicts[gi] = verdict
-            session_nonces[gi] = nonce
-            if details:
+        pk_h = pk.cpu().numpy(); npk_h = npk.cpu().numpy(); hdr_h = fr["hdr"].cpu().numpy()
+        # ---- host: candidate counters, 400-try budget, PN bits (native, threaded)
+        enum = bank.rx_enumerate(kidx, n, pk_h, npk_h, hdr_h)
+        # ---- phase 2: despread/LLR (K5), SCL-8 (K6), AEAD validation of CRC-passing candidates
+        ns = np.ascontiguousarray(nonce_state[s0:s1])
+        v, pt = _decode_phase(bank, kidx, enum, fr["mf_aligned"], list_size, ns, dev)
+        nonce_state[s0:s1] = ns
+        verdicts[s0:s1] = v.astype(bool)
+        if details:
+            st_h = st.cpu().numpy()
+            for ci in range(nb):
                 r = RxResult()
-                r.verdict = verdict; r.peaks = pk_h[ci]; r.npeaks = npk_h[ci]; r.stats = st_h[ci]
-                r.hdr = hdr_h[ci]; r.attempts = attempts[ci]; r.payload = found_payload; r.nonce = nonce
-                r.n_scl = 4 * sum(len(a) for a in attempts[ci])
-                results[gi] = r
+                r.verdict = bool(v[ci]); r.peaks = pk_h[ci]; r.npeaks = npk_h[ci]; r.stats = st_h[ci]; r.hdr = hdr_h[ci]
+                o = int(enum["item_offset"][ci])
+                r.attempts = []
+                for bi in range(4):
+                    c = int(enum["band_count"][ci, bi])
+                    pidx = enum["item_peak"][o:o + c]
+                    starts = pk_h[ci].reshape(-1)[pidx - ci * 4 * PEAK_LIMIT] if c else []
+                    r.attempts.append([(int(a), int(b)) for a, b in zip(starts, enum["item_ctr"][o:o + c])])
+                    o += c
+                r.payload = pt[ci].tobytes() if v[ci] else None
+                r.nonce = ns[ci, 1:].tobytes() if ns[ci, 0] else None
+                r.n_scl = 4 * int(enum["band_count"][ci].sum())
+                results[s0 + ci] = r
+    if session_nonces is not None:
+        for i in range(B):
+            session_nonces[i] = nonce_state[i, 1:].tobytes() if nonce_state[i, 0] else None
     if details:
         return verdicts, results
     return verdicts
@@ -250,21 +173,22 @@ class WatermarkDetector:
     """Recover EchoSeal watermark from a >= 3 s recording (rtwm/detector.py:24)."""
 
     def __init__(self, key32: bytes, *, fs_target: int = 48_000, list_size: int = 8) -> None:
-        self._kc = _KeyCtx(key32)                    # raises ValueError for a key that is not 32 bytes
+        self.sec = SecureChannel(key32)              # raises ValueError for a key that is not 32 bytes
         self._key = bytes(key32)
-        self.sec = self._kc.sec
         self.fs_target = fs_target
         self.session_nonce: bytes | None = None
-        self._band_key = self._kc.band_key
+        self._band_key = getattr(self.sec, "band_key", key32)      # rtwm/detector.py:31 (quirk 9)
         self._mf_cache = {}
         self._list_size = int(list_size)
         if not (1 <= self._list_size <= 8):
             raise ValueError("list_size must be in 1..8 on the B200 path (north_star: SCL-8)")
         self._aead = getattr(self.sec, "_aead", None)
         self._pre_sy = 2.0 * PRE_BITS.astype(np.float32) - 1.0
-        self._hdr_pn_sy = 2.0 * self._kc.hdr_pn_bits.astype(np.float32) - 1.0
+        self._hdr_pn_bits = self.sec.pn_bits(0, HDR_L)
+        self._hdr_pn_sy = 2.0 * self._hdr_pn_bits.astype(np.float32) - 1.0
         if self._hdr_pn_sy.size != HDR_L:
             raise RuntimeError(f"Header PN length {self._hdr_pn_sy.size} != expected {HDR_L}")
+        self._bank, _ = _bank_for([self._key])
         self.last_result: RxResult | None = None
 
     # ------------------------------------------------------------------ helpers
@@ -283,17 +207,23 @@ class WatermarkDetector:
     def _resample(self, audio: np.ndarray, fs_in: int) -> np.ndarray:
         if fs_in == self.fs_target:
             return audio
-        from scipy.signal import resample_poly     # TODO(K9): device polyphase resampler
+        from scipy.signal import resample_poly     # host path for now; the device resampler is §8f-2 ("next")
         up, down = resample_ratio(self.fs_target, fs_in)
         return resample_poly(audio, up, down)
+
+    def _dev(self):
+        if not torch.cuda.is_available():
+            raise RuntimeError("echoseal_b200 needs a CUDA device (no CPU fallback)")
+        return torch.device("cuda", torch.cuda.current_device())
 
     # ------------------------------------------------------------------ API
     def verify(self, audio: np.ndarray, fs_in: int) -> bool:
         """rtwm/detector.py:44-53"""
         signal = np.asarray(self._resample(np.asarray(audio), fs_in), dtype=np.float32).reshape(1, -1)
         nonces = [self.session_nonce]
-        v, res = verify_batch([self._key], signal, fs_target=self.fs_target, list_size=self._list_size,
-                              mf_taps=self._taps(), session_nonces=nonces, details=True)
+        v, res = verify_batch(None, signal, fs_target=self.fs_target, list_size=self._list_size,
+                              mf_taps=self._taps(), session_nonces=nonces, details=True,
+                              bank=self._bank, key_idx=np.zeros(1, np.int32))
         self.session_nonce = nonces[0]
         self.last_result = res[0]
         return bool(v[0])
@@ -302,5 +232,104 @@ class WatermarkDetector:
         """Additive API: B clips with this detector's key; no session-nonce latch across clips."""
         if fs_in is not None and fs_in != self.fs_target:
             audio = np.stack([self._resample(a, fs_in) for a in np.asarray(audio)])
-        return verify_batch([self._key] * int(audio.shape[0]), audio, fs_target=self.fs_target,
-                            list_size=self._list_size, mf_taps=self._taps())
+        B = int(audio.shape[0])
+        return verify_batch(None, audio, fs_target=self.fs_target, list_size=self._list_size, mf_taps=self._taps(),
+                            bank=self._bank, key_idx=np.zeros(B, np.int32))
+
+    # ---- single-frame / single-band entry points of the reference -------------------------------
+    def _frame_front(self, frame: np.ndarray, band_idx: int):
+        """K4 on one already band-passed 1215-sample frame placed in row `band_idx`."""
+        frame = np.asarray(frame, dtype=np.float64).reshape(-1)
+        if frame.size != FRAME_LEN:
+            raise ValueError(f"the B200 path takes exactly {FRAME_LEN}-sample frames here (got {frame.size})")
+        dev = self._dev()
+        rx_gpu.set_filters(self.fs_target, self._taps())
+        y = torch.zeros((1, 4, FRAME_LEN), dtype=torch.float64, device=dev)
+        y[0, band_idx] = torch.from_numpy(frame).to(dev)
+        pk = torch.full((1, 4, PEAK_LIMIT), -1, dtype=torch.int32, device=dev)
+        npk = torch.zeros((1, 4), dtype=torch.int32, device=dev)
+        pk[0, band_idx, 0] = 0
+        npk[0, band_idx] = 1
+        hdr_pn = torch.from_numpy(np.packbits(self._hdr_pn_bits)[None]).to(dev)
+        return rx_gpu.frames(y, pk, npk, hdr_pn), band_idx * PEAK_LIMIT
+
+    def _decode_header(self, frame: np.ndarray, band) -> tuple[bool, int, float]:
+        """rtwm/detector.py:452-515 -> (ok, ctr_lo16, score)"""
+        fr, pidx = self._frame_front(frame, BAND_PLAN.index(tuple(band)))
+        h = fr["hdr"].reshape(-1, 4)[pidx].cpu().numpy()
+        return bool(h[0] > 0.5), int(h[1]), float(h[2])
+
+    def _llr(self, frame: np.ndarray, frame_id: int, pn_variant: int = 0) -> np.ndarray:
+        """rtwm/detector.py:296-416 -> float32[1024]; the matched filter is the one of
+        choose_band(key, frame_id) (quirk 8)."""
+        band_idx = BAND_PLAN.index(choose_band(self._band_key, frame_id))
+        fr, pidx = self._frame_front(frame, band_idx)
+        dev = self._dev()
+        pn = torch.from_numpy(self._bank.pn(0, [frame_id])).to(dev)
+        out = rx_gpu.llr(fr["mf_aligned"], torch.tensor([pidx], dtype=torch.int32, device=dev), pn)
+        return out[1 if pn_variant else 0].cpu().numpy()
+
+    def _try_decode_frame(self, frame: np.ndarray, frame_ctr: int) -> bool:
+        """rtwm/detector.py:154-233: the 4-variant SCL ladder with the AEAD validator, magic / counter
+        checks and the session-nonce latch, for one band-passed frame and one counter."""
+        band_idx = BAND_PLAN.index(choose_band(self._band_key, frame_ctr))
+        fr, pidx = self._frame_front(frame, band_idx)
+        enum = dict(band_count=np.zeros((1, 4), np.int32), item_offset=np.array([0, 1], np.int64),
+                    item_peak=np.array([pidx], np.int32), item_ctr=np.array([frame_ctr], np.uint32),
+                    item_clip=np.zeros(1, np.int32), pn=self._bank.pn(0, [frame_ctr]))
+        enum["band_count"][0, band_idx] = 1
+        ns = np.zeros((1, 9), np.uint8)
+        if self.session_nonce:
+            ns[0, 0] = 1; ns[0, 1:] = np.frombuffer(self.session_nonce, np.uint8)
+        v, _ = _decode_phase(self._bank, np.zeros(1, np.int32), enum, fr["mf_aligned"], self._list_size, ns, self._dev())
+        if ns[0, 0]:
+            self.session_nonce = ns[0, 1:].tobytes()
+        return bool(v[0])
+
+    def _scan_band_multi_frame(self, signal: np.ndarray, band) -> bool:
+        """rtwm/detector.py:56-152 for ONE band of one recording."""
+        bi = BAND_PLAN.index(tuple(band))
+        signal = np.asarray(signal, dtype=np.float32).reshape(1, -1)
+        n = signal.shape[1]
+        if n < PRE_L:
+            return False
+        dev = self._dev()
+        rx_gpu.set_filters(self.fs_target, self._taps())
+        x = torch.from_numpy(signal).to(dev)
+        y = rx_gpu.bandpass(x)
+        pk, npk, st = rx_gpu.peaks(rx_gpu.ncc(y))
+        keep = torch.zeros_like(npk); keep[0, bi] = npk[0, bi]      # only this band's peaks are tried
+        hdr_pn = torch.from_numpy(np.packbits(self._hdr_pn_bits)[None]).to(dev)
+        fr = rx_gpu.frames(y, pk, keep, hdr_pn)
+        enum = self._bank.rx_enumerate(np.zeros(1, np.int32), n, pk.cpu().numpy(), keep.cpu().numpy(), fr["hdr"].cpu().numpy())
+        ns = np.zeros((1, 9), np.uint8)
+        if self.session_nonce:
+            ns[0, 0] = 1; ns[0, 1:] = np.frombuffer(self.session_nonce, np.uint8)
+        v, _ = _decode_phase(self._bank, np.zeros(1, np.int32), enum, fr["mf_aligned"], self._list_size, ns, dev)
+        if ns[0, 0]:
+            self.session_nonce = ns[0, 1:].tobytes()
+        return bool(v[0])
+
+    def _scan_band(self, signal: np.ndarray, band, skip_filtering=False) -> bool:
+        """Legacy alias (rtwm/detector.py:247-249)."""
+        return self._scan_band_multi_frame(signal, band)
+
+    def _try_window(self, frame: np.ndarray, ctr0: int, delta: int) -> bool:
+        """rtwm/detector.py:252-257"""
+        for ctr in range(max(0, ctr0 - delta), ctr0 + delta + 1):
+            if self._try_decode_frame(frame, ctr):
+                return True
+        return False
+
+    def verify_raw_frame(self, signal: np.ndarray) -> bool:
+        """rtwm/detector.py:235-245"""
+        signal = np.asarray(signal)
+        if len(signal) == FRAME_LEN:
+            dev = self._dev()
+            rx_gpu.set_filters(self.fs_target, self._taps())
+            y = rx_gpu.bandpass(torch.from_numpy(signal.astype(np.float32)[None]).to(dev))[0].cpu().numpy()
+            for ctr in range(4):
+                bi = BAND_PLAN.index(choose_band(self._band_key, ctr))
+                if self._try_decode_frame(y[bi], ctr):
+                    return True
+        return self._scan_band_multi_frame(signal, choose_band(self._band_key, 0))

@@ -126,3 +126,51 @@ def test_edge_cases(env):
     assert rx.verify(np.ones(70, np.float32), 48000) is False          # corr shorter than a frame
     with pytest.raises(ValueError):
         detector.WatermarkDetector(b"short")
+
+
+def test_positive_verdict_identity_channel_fixture(env):
+    """with an identity matched filter and ideal +-1 symbols the downstream chain
+    (despread -> LLR -> SCL -> AEAD -> magic / counter / nonce latch) must say True, exactly like the
+    reference's _try_decode_frame does with the same fixture."""
+    torch, rx_gpu, detector, clips, taps = env
+    from oracle import tx_oracle as txo
+    from echoseal_b200.utils import BAND_PLAN
+    key = bytes([0x5A]) * 32
+    k = txo.Keys(key)
+    rx = detector.WatermarkDetector(key, list_size=8)
+    for lo, hi in BAND_PLAN:
+        rx._mf_cache[(lo, hi, 48000)] = np.array([1.0], np.float32)
+    rng = np.random.default_rng(3)
+    sn = b"NONCE123"
+    for ctr, sigma in ((0, 0.0), (5, 0.05), (1234, 0.12)):
+        payload = txo.build_payload(k, ctr, sn, bytes(11), bytes(range(12)))
+        sym = txo.frame_symbols(k, ctr, payload).astype(np.float64) + sigma * rng.standard_normal(1215)
+        rx.session_nonce = None
+        assert rx._try_decode_frame(sym, ctr) is True
+        assert rx.session_nonce == sn                       # latched
+        assert rx._try_decode_frame(sym, ctr) is True       # repeat nonce accepted
+        assert rx._try_decode_frame(sym, ctr + 1) is False  # wrong counter (different PN, and ctr check)
+        rx.session_nonce = b"OTHERNON"
+        assert rx._try_decode_frame(sym, ctr) is False      # nonce mismatch
+        # stage taps on the same frame
+        l0 = rx._llr(sym, ctr, 0)
+        assert l0.dtype == np.float32 and l0.shape == (1024,)
+        from oracle import detector_oracle as do
+        ref, _ = do.llr(sym, np.array([1.0], np.float32), k.pn_bits(ctr, 1215)[191:])
+        assert np.abs(l0 - ref).max() <= 1e-4 * 12.0
+        ok, val, score = rx._decode_header(sym, BAND_PLAN[k.band_index(ctr)])
+        rok, rval, rscore, _, _ = do.decode_header(sym, np.array([1.0], np.float32), 2.0 * k.pn_bits(0, 128).astype(np.float32) - 1.0)
+        assert (ok, val) == (rok, rval) and abs(score - rscore) <= 2e-3 * abs(rscore)
+        assert val == (~ctr) & 0xFFFF                       # inverted header bit sense (quirk 2)
+
+
+def test_batch_matches_single_and_details(env):
+    torch, rx_gpu, detector, clips, taps = env
+    names = ["chirp_aa", "noise_44", "bench_17", "plain_noise"]
+    audio = np.stack([clips[n][0] for n in names])
+    keys = [clips[n][1] for n in names]
+    v, res = detector.verify_batch(keys, audio, details=True, sub_batch=3)
+    assert not v.any()
+    for n, r in zip(names, res):
+        for bi in range(4):
+            assert [c for _, c in r.attempts[bi]] == list(G[f"{n}/b{bi}/att_ctr"])
