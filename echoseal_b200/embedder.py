@@ -118,3 +118,57 @@ class WatermarkEmbedder:
         blob = self.sec.seal(meta)
         assert len(blob) == 55
         return blob
+
+
+class EmbedderBank:
+    """Additive batched TX: S concurrent streams (one key, frame counter, session nonce and chip FIFO
+    each) advanced in lock-step, one kernel launch per stage for all of them (SURVEY.md §8d config 5:
+    4096 streams x 1024-sample blocks).  Per-stream semantics are those of WatermarkEmbedder.process
+    (rtwm/embedder.py:44-75): frames are generated on demand, the mix level is computed per block.
+    The host side (payload sealing, PN bits, hop bands) runs in the native threaded feeder."""
+
+    def __init__(self, keys: list[bytes], params: TxParams | None = None, rand=None):
+        from .host_feeder import KeyBank
+        import os
+        self.p = params or TxParams()
+        if self.p.N != N_DEFAULT or self.p.K != K_DEFAULT:
+            raise ValueError("the B200 bank implements Polar(1024,448) frames")
+        self.S = len(keys)
+        self.bank = KeyBank(list(keys))
+        self._rand = rand or os.urandom
+        self.frame_ctr = np.zeros(self.S, np.uint32)
+        self.session_nonce = np.frombuffer(self._rand(8 * self.S), np.uint8).reshape(self.S, 8).copy()
+        self._fifo = None          # device tensor [S, avail]
+        self._kidx = np.arange(self.S, dtype=np.int32)
+
+    def make_frames(self, nframes: int) -> torch.Tensor:
+        """Next `nframes` frames of every stream -> device float32 [S, nframes*1215]; advances frame_ctr."""
+        dev = _dev()
+        tx_gpu.set_filters(self.p.fs, self.p.preamble)
+        S, F = self.S, self.S * nframes
+        ctr = (self.frame_ctr[:, None].astype(np.uint64) + np.arange(nframes, dtype=np.uint64)[None, :]) % (2 ** 32)
+        rnd = np.frombuffer(self._rand(23 * F), np.uint8).reshape(F, 23)
+        prep = self.bank.tx_prepare(np.repeat(self._kidx, nframes), ctr.reshape(-1).astype(np.uint32),
+                                    np.repeat(self.session_nonce, nframes, axis=0), rnd)
+        chips = tx_gpu.frames(*(torch.from_numpy(prep[k]).to(dev, non_blocking=True)
+                                for k in ("payload", "pn", "hdr_pn", "band", "ctr_lo16")), K=self.p.K)
+        self.frame_ctr = ((self.frame_ctr.astype(np.uint64) + nframes) % (2 ** 32)).astype(np.uint32)
+        return chips.view(S, nframes * FRAME_LEN)
+
+    def process(self, x):
+        """x float32 [S, B] (numpy -> numpy, CUDA tensor -> CUDA tensor): one block of every stream."""
+        dev = _dev()
+        is_np = not isinstance(x, torch.Tensor)
+        xd = torch.from_numpy(np.ascontiguousarray(x, np.float32)).to(dev) if is_np else x.to(dev, torch.float32).contiguous()
+        if xd.dim() != 2 or xd.shape[0] != self.S:
+            raise ValueError(f"x must be [S={self.S}, B]")
+        B = int(xd.shape[1])
+        avail = 0 if self._fifo is None else int(self._fifo.shape[1])
+        if avail < B:
+            nf = (B - avail + FRAME_LEN - 1) // FRAME_LEN
+            new = self.make_frames(nf)
+            self._fifo = new if self._fifo is None else torch.cat([self._fifo, new], dim=1)
+        chips = self._fifo[:, :B].contiguous()
+        self._fifo = self._fifo[:, B:]
+        out, _ = tx_gpu.mix(xd, chips, db_to_lin(self.p.target_rel_db), db_to_lin(self.p.floor_rel_dbfs))
+        return out.cpu().numpy() if is_np else out

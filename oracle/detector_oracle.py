@@ -226,3 +226,79 @@ def candidate_counters(start: int, hdr_ok: bool, ctr_lo16: int, band_idx: int, b
                 if band_of_ctr(ctr) == band_idx:
                     cands.append(ctr)
     return cands
+
+
+def verify(audio: np.ndarray, key32: bytes, list_size: int = 8, fs: int = 48000, session_nonce=None,
+           return_details: bool = False):
+    """Full restatement of WatermarkDetector.verify (rtwm/detector.py:44-233) for audio already at `fs`:
+    hop-0 band first, then the others; per band the scan, <= 25 peaks, header, candidate counters, the
+    400-try budget and the 4-variant SCL ladder with the AEAD validator / magic / counter / nonce latch.
+    The SCL decodes of one band are batched through the C oracle (same results, validator applied in
+    the reference's order afterwards)."""
+    from . import tx_oracle as txo
+    k = txo.Keys(key32)
+    hdr_pn = 2.0 * k.pn_bits(0, 128).astype(np.float32) - 1.0
+    hop = {}
+
+    def band_of(c):
+        v = hop.get(c)
+        if v is None:
+            v = hop[c] = k.band_index(c)
+        return v
+
+    hop0 = band_of(0)
+    details = dict(attempts={}, n_scl=0)
+    for bi in [hop0] + [b for b in range(4) if b != hop0]:
+        band = BAND_PLAN[bi]
+        r = scan_band(audio, band, fs)
+        if r is None:
+            continue
+        h = matched_filter_taps(band, fs)
+        att = []
+        tried, stop = 0, False
+        for start in r["peaks"][:PEAK_LIMIT]:
+            if start + FRAME_LEN > r["y"].size:
+                continue
+            frame = r["y"][start:start + FRAME_LEN]
+            ok, val, _, _, _ = decode_header(frame, h, hdr_pn)
+            for ctr in candidate_counters(start, ok, val, bi, band_of):
+                att.append((start, ctr)); tried += 1
+                if tried >= MAX_TRIES:
+                    stop = True
+                    break
+            if stop:
+                break
+        details["attempts"][bi] = att
+        if not att:
+            continue
+        llrs = np.empty((4 * len(att), 1024), np.float32)
+        for a_i, (start, ctr) in enumerate(att):
+            frame = r["y"][start:start + FRAME_LEN]
+            pn_full = k.pn_bits(ctr, FRAME_LEN)
+            l0, _ = llr(frame, h, pn_full[PRE_L + HDR_L:])
+            l1, _ = llr(frame, h, pn_full[:N_POLAR])
+            llrs[4 * a_i + 0] = l0; llrs[4 * a_i + 1] = -l0
+            llrs[4 * a_i + 2] = l1; llrs[4 * a_i + 3] = -l1
+        res = _po.scl_batch(llrs, L=list_size)
+        details["n_scl"] += llrs.shape[0]
+        for a_i, (start, ctr) in enumerate(att):
+            def validator(payload, ctr=ctr):
+                try:
+                    pt = k.open(payload)
+                except Exception:
+                    return False
+                return pt.startswith(b"ESAL") and int.from_bytes(pt[4:8], "big") == ctr
+            blob = None
+            for v in range(4):
+                bits, okv = _po.select(res, 4 * a_i + v, validator)
+                if okv:
+                    blob = np.packbits(bits).tobytes()
+                    break
+            if blob is None:
+                continue
+            pt = k.open(blob)
+            nonce = pt[8:16]
+            if session_nonce is None or nonce == session_nonce:
+                details["nonce"] = nonce
+                return (True, details) if return_details else True
+    return (False, details) if return_details else False

@@ -67,3 +67,41 @@ def test_bad_key_raises():
     from echoseal_b200 import embedder
     with pytest.raises(ValueError):
         embedder.WatermarkEmbedder(b"123")
+
+
+def test_embedder_bank_matches_single_stream_semantics():
+    """Lock-step multi-stream TX == S independent reference-style embedders (frames bit-for-bit given the
+    same randomness; mix within float32 round-off), and the detector side can open what it seals."""
+    import torch
+    from echoseal_b200 import embedder
+    from oracle import tx_oracle as txo
+    keys = [bytes([i + 1]) * 32 for i in range(5)]
+    stream = np.random.default_rng(0).integers(0, 256, 1 << 16, dtype=np.uint8).tobytes()
+    pos = [0]
+    def rand(n):
+        b = stream[pos[0]:pos[0] + n]; pos[0] += n
+        return b
+    bank = embedder.EmbedderBank(keys, rand=rand)
+    sn = bank.session_nonce.copy()
+    bank.frame_ctr[:] = [0, 7, 1000, 65535, 2 ** 32 - 1]
+    ctr0 = bank.frame_ctr.copy()
+    rng = np.random.default_rng(1)
+    x = (0.1 * rng.standard_normal((5, 3000))).astype(np.float32)
+    # the bank draws 23 random bytes per frame, frame-major over (stream, frame): replay them for the oracle
+    start = pos[0]
+    out = bank.process(x)
+    nf = 3                                      # ceil(3000 / 1215)
+    rnd = np.frombuffer(stream[start:start + 23 * 5 * nf], np.uint8).reshape(5, nf, 23)
+    for s in range(5):
+        k = txo.Keys(keys[s])
+        chips = np.concatenate([
+            txo.frame_chips(k, (int(ctr0[s]) + f) % 2 ** 32,
+                            txo.build_payload(k, (int(ctr0[s]) + f) % 2 ** 32, sn[s].tobytes(),
+                                              rnd[s, f, :11].tobytes(), rnd[s, f, 11:].tobytes()))
+            for f in range(nf)])
+        ref = txo.mix(x[s], chips[:3000])
+        assert np.abs(out[s] - ref).max() <= 1e-6
+    assert list(bank.frame_ctr) == [3, 10, 1003, 65538, 2]
+    # second block continues from the FIFO remainder
+    out2 = bank.process(x[:, :500])
+    assert out2.shape == (5, 500) and list(bank.frame_ctr) == [3, 10, 1003, 65538, 2]
