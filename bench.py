@@ -1,0 +1,381 @@
+#!/usr/bin/env python3
+"""bench.py — RX verify throughput of the B200 hot path (BASELINE.json metric: "RX audio-sec
+verified/s"), workload = configs[1]: a batch of synthetic 3 s 48 kHz clips, RX verify
+(band-pass + sync + despread + SCL-8 + AEAD validation), sharded over the GPUs of one node with no
+data-path collective (weak scaling: every rank verifies its own `--clips` clips; a final verdict
+gather is the only NCCL traffic).
+
+    python bench.py [--gpus N --steps K --warmup W --clips B]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...      # CPU arm: the oracle port on all host cores
+
+One JSON line on stdout (rank 0).  Everything else goes to stderr."""
+from __future__ import annotations
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np
+
+FS, SECS, FRAME_LEN = 48_000, 3.0, 1215
+N_SAMPLES = int(FS * SECS)
+ALG_BYTES_PER_AUDIO_S = 4 * FS             # RX reads each float32 input sample once
+SCL_ALG_BYTES_PER_CW = 4096 + 55           # fp32 LLR in + payload out
+SCL_NODE_UPDATES_PER_CW = 81920            # N log2 N * L
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def bench_key(i: int) -> bytes:
+    import hashlib
+    return hashlib.sha256(b"echoseal-bench" + int(i).to_bytes(4, "big")).digest()
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic workload: clip i: key_i = SHA-256("echoseal-bench"||i); host =
+# 0.05 N(0,1) (i%4 != 3) or 0.3 chirp + 0.02 N(0,1) (i%4 == 3); 80 % watermarked from a random frame
+# counter in [0,2000) at a random chip phase, 20 % (i%5 == 4) un-watermarked.
+# ------------------------------------------------------------------------------------------------
+def make_clips_gpu(first: int, count: int, dev, chunk: int = 1000):
+    import torch
+    from echoseal_b200 import tx_gpu
+    from echoseal_b200.host_feeder import KeyBank
+    from echoseal_b200.utils import db_to_lin
+    keys = [bench_key(first + i) for i in range(count)]
+    bank = KeyBank(keys)
+    clips = torch.empty((count, N_SAMPLES), dtype=torch.float32, device=dev)
+    nfr = N_SAMPLES // FRAME_LEN + 2
+    tx_gpu.set_filters(FS)
+    t = torch.arange(N_SAMPLES, device=dev, dtype=torch.float64) / FS
+    chirp = (0.3 * torch.cos(2 * np.pi * (300.0 * t + (3500.0 - 300.0) / (2 * SECS) * t * t))).float()
+    for c0 in range(0, count, chunk):
+        c1 = min(count, c0 + chunk)
+        m = c1 - c0
+        rng = np.random.default_rng(1_000_003 * (first + c0) + 17)
+        g = torch.Generator(device=dev).manual_seed(int(first + c0) * 7919 + 1)
+        noise = torch.randn((m, N_SAMPLES), device=dev, generator=g)
+        idx = torch.arange(first + c0, first + c1, device=dev)
+        is_chirp = (idx % 4 == 3)[:, None]
+        host = torch.where(is_chirp, chirp[None, :] + 0.02 * noise, 0.05 * noise)
+        ctr0 = rng.integers(0, 2000, m).astype(np.uint64)
+        phase = rng.integers(0, FRAME_LEN, m)
+        ctr = (ctr0[:, None] + np.arange(nfr, dtype=np.uint64)[None, :]).reshape(-1).astype(np.uint32)
+        sn = np.repeat(rng.integers(0, 256, (m, 8), dtype=np.uint8), nfr, axis=0)
+        rnd = rng.integers(0, 256, (m * nfr, 23), dtype=np.uint8)
+        prep = bank.tx_prepare(np.repeat(np.arange(c0, c1, dtype=np.int32), nfr), ctr, sn, rnd)
+        chips = tx_gpu.frames(*(torch.from_numpy(prep[k]).to(dev) for k in ("payload", "pn", "hdr_pn", "band", "ctr_lo16")))
+        chips = chips.view(m, nfr * FRAME_LEN)
+        ar = torch.arange(N_SAMPLES, device=dev)[None, :] + torch.from_numpy(phase).to(dev)[:, None]
+        chips = torch.gather(chips, 1, ar).contiguous()
+        wm, _ = tx_gpu.mix(host.contiguous(), chips, db_to_lin(-10.0), db_to_lin(-35.0))
+        plain = (idx % 5 == 4)[:, None]
+        clips[c0:c1] = torch.where(plain, host, wm)
+    torch.cuda.synchronize()
+    return keys, bank, clips
+
+
+def make_clips_cpu(first: int, count: int):
+    """Same recipe on the CPU with the TX oracle (reference arm: none of our kernels on that path)."""
+    from oracle import tx_oracle as txo
+    out, keys = [], []
+    t = np.arange(N_SAMPLES, dtype=np.float64) / FS
+    chirp = 0.3 * np.cos(2 * np.pi * (300.0 * t + (3500.0 - 300.0) / (2 * SECS) * t * t))
+    for i in range(first, first + count):
+        rng = np.random.default_rng(i)
+        key = bench_key(i)
+        noise = rng.standard_normal(N_SAMPLES)
+        host = (chirp + 0.02 * noise if i % 4 == 3 else 0.05 * noise).astype(np.float32)
+        if i % 5 != 4:
+            tx = txo.Embedder(key, txo.seeded_rand(i))
+            tx.frame_ctr = int(rng.integers(0, 2000))
+            ph = int(rng.integers(0, FRAME_LEN))
+            tx.buf = tx.make_frame()[ph:]          # start at a random chip phase
+            tx.frame_ctr += 1
+            host = tx.process(host).astype(np.float32)
+        out.append(host); keys.append(key)
+    return keys, np.stack(out)
+
+
+def _oracle_verify_one(args):
+    audio, key = args
+    from oracle import detector_oracle as do
+    t0 = time.perf_counter()
+    v, d = do.verify(audio, key, list_size=8, return_details=True)
+    return bool(v), int(d["n_scl"]), time.perf_counter() - t0
+
+
+def oracle_verify_pool(audio: np.ndarray, keys, procs: int):
+    """The CPU port (oracle) on `procs` host cores.  Returns (verdicts, n_scl, wall seconds)."""
+    from oracle import polar_oracle as po
+    po.build()
+    import multiprocessing as mp
+    os.environ["ES_ORACLE_THREADS"] = "1"
+    t0 = time.perf_counter()
+    if procs <= 1:
+        res = [_oracle_verify_one((audio[i], keys[i])) for i in range(len(keys))]
+    else:
+        with mp.get_context("fork").Pool(procs) as pool:
+            res = pool.map(_oracle_verify_one, [(audio[i], keys[i]) for i in range(len(keys))], chunksize=1)
+    wall = time.perf_counter() - t0
+    return [r[0] for r in res], [r[1] for r in res], wall
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 7:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference path's CPU implementation (the oracle port: numpy restatement of
+    rtwm/detector.py + the C restatement of rtwm/fastpolar.py) on all host cores, same metric/config."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    per_step = max(cores, 8)
+    keys, audio = make_clips_cpu(0, per_step)
+    for _ in range(args.warmup if args.warmup < 2 else 1):      # CPU code needs no long warm-up; keep it bounded
+        oracle_verify_pool(audio[:cores], keys[:cores], cores)
+    t_tot, scl = 0.0, 0
+    for _ in range(args.steps):
+        v, n_scl, wall = oracle_verify_pool(audio, keys, cores)
+        t_tot += wall; scl += sum(n_scl)
+    value = args.steps * per_step * SECS / t_tot
+    line = {"impl": "reference", "metric": "rx_audio_seconds_verified_per_second", "value": value,
+            "unit": "audio-s/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * t_tot / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"configs[1] sample: {per_step} synthetic 3 s 48 kHz clips per step, RX verify "
+                                   "(filter+sync+despread+SCL-8+AEAD), 80% watermarked", "list_size": 8},
+            "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": "port",
+                             "sample": f"{per_step} clips x {args.steps} steps, {scl} SCL-8 decodes"},
+            "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--clips", type=int, default=10_000, help="clips per GPU per step (configs[1]: 10k)")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--sub-batch", type=int, default=1000)
+    ap.add_argument("--cpu-sample", type=int, default=0, help="clips for the cpu_baseline leg (0 = 2 x cores)")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl=ours) needs a CUDA device: there is no CPU fallback")
+    import __graft_entry__ as ge
+    if rank == 0:
+        ge.build()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+        dist.barrier()
+    from echoseal_b200 import _native as N, detector, rx_gpu
+    from echoseal_b200.utils import BAND_PLAN
+    cores = os.cpu_count() or 1
+    host_threads = max(1, cores // world)
+
+    t0 = time.perf_counter()
+    keys, _, clips = make_clips_gpu(rank * args.clips, args.clips, dev)
+    from echoseal_b200.host_feeder import KeyBank
+    log(f"[rank {rank}] generated {args.clips} clips in {time.perf_counter() - t0:.1f}s; host threads {host_threads}")
+    taps = [rx_gpu.matched_filter_taps(b, FS) for b in BAND_PLAN]
+    key_idx = np.arange(args.clips, dtype=np.int32)
+
+    def step(audio, want_details=False):
+        # a fresh key bank per step: key derivation and hop tables are part of verifying a clip
+        bank = KeyBank(keys, nthreads=host_threads)
+        return detector.verify_batch(None, audio, list_size=8, mf_taps=taps, sub_batch=args.sub_batch,
+                                     bank=bank, key_idx=key_idx, details=want_details)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- warm-up (also yields the per-clip details used by the CPU cross-check)
+    verdicts, det = step(clips, want_details=True)
+    for _ in range(max(0, args.warmup - 1)):
+        step(clips)
+    n_scl_step = int(sum(r.n_scl for r in det))
+
+    # ---------------- timed: device-resident inputs
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    barrier()
+    N.KERNEL_TIMES = {}
+    launches0 = N.LAUNCHES
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        v = step(clips)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = N.LAUNCHES - launches0
+    ktimes = {k: [a.elapsed_time(b) for a, b in v_] for k, v_ in N.KERNEL_TIMES.items()}
+    N.KERNEL_TIMES = None
+    clocks = sampler.stop() if sampler else None
+    assert (v == verdicts).all()
+
+    # ---------------- timed: end to end from pinned host memory (H2D of every clip + D2H of verdicts)
+    e2e_steps = max(1, min(args.steps, 2))
+    host_clips = torch.empty((args.clips, N_SAMPLES), dtype=torch.float32, pin_memory=True)
+    host_clips.copy_(clips)
+    host_np = host_clips.numpy()
+    step(host_np)                                           # warm the pinned path
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(e2e_steps):
+        v2 = step(host_np)
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    assert (v2 == verdicts).all()
+
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+    vd = torch.from_numpy(verdicts.astype(np.uint8)).to(dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)                      # max over ranks
+        allv = torch.empty((world * args.clips,), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(allv, vd)                         # the final verdict gather
+    else:
+        allv = vd
+    ms, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    total_audio_s = world * args.clips * SECS
+    value = args.steps * total_audio_s / (ms / 1e3)
+    e2e_value = e2e_steps * total_audio_s / (ms_e2e / 1e3)
+    peaks, peak_kind = measured_peaks()
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+
+    # ---------------- roofline of the dominant kernel (SCL list decoder), measured live with CUDA events
+    scl_ms = ktimes.get("scl_list", [])
+    n_launch = max(1, len(scl_ms))
+    scl_avg_ms = float(np.mean(scl_ms)) if scl_ms else float("nan")
+    cw_per_launch = n_scl_step * args.steps / n_launch
+    scl_cw_s = cw_per_launch / (scl_avg_ms / 1e3)
+    achieved_gbs = cw_per_launch * SCL_ALG_BYTES_PER_CW / (scl_avg_ms / 1e3) / 1e9
+    sm_mhz = float(peaks.get("sm_max_mhz", 1965.0))
+    fp64_lane_rate = 148 * 64 * sm_mhz * 1e6            # DFMA lanes/s
+    kshare = {k: float(np.sum(v_)) for k, v_ in ktimes.items()}
+    ksum = sum(kshare.values()) or 1.0
+    scan_ms = sum(kshare.get(k, 0.0) for k in ("bandpass", "ncc", "peaks"))
+    scan_gbs = args.steps * args.clips * N_SAMPLES * 4 / (scan_ms / 1e3) / 1e9 if scan_ms else None
+
+    # ---------------- CPU baseline on a bounded sample of the SAME clips + cross-check
+    m = args.cpu_sample or max(8, 2 * cores)
+    m = min(m, args.clips)
+    sample = clips[:m].cpu().numpy()
+    cv, cn, cwall = oracle_verify_pool(sample, keys[:m], cores)
+    agree_v = int(sum(int(a == bool(b)) for a, b in zip(cv, verdicts[:m])))
+    agree_n = int(sum(int(a == r.n_scl) for a, r in zip(cn, det[:m])))
+    cpu_value = m * SECS / cwall
+
+    line = {
+        "metric": "rx_audio_seconds_verified_per_second", "value": value, "unit": "audio-s/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"configs[1]: {args.clips} synthetic 3 s 48 kHz clips per GPU per step, RX verify "
+                               "(4-band fp64 band-pass + preamble sync + despread/LLR + SCL-8 + AEAD validation), "
+                               "80% watermarked, one key per clip",
+                   "clips_per_gpu": args.clips, "list_size": 8, "scl_decodes_per_step_per_gpu": n_scl_step,
+                   "verified_true": int(allv.sum().item()),
+                   "l2": "inputs (5.76 GB per 10k clips) and every intermediate exceed the 126 MB L2"},
+        "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": args.clips * N_SAMPLES * 4,
+                "d2h_bytes_per_step": args.clips, "steps": e2e_steps},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"kernel": "scl_list_kernel", "bound": "hbm", "achieved": achieved_gbs, "peak": hbm, "unit": "GB/s",
+                     "frac": achieved_gbs / hbm, "traffic": None, "peak_source": peak_kind,
+                     "note": "the SCL decoder is FP64-issue bound, not HBM bound; see roofline_issue"},
+        "roofline_issue": {"kernel": "scl_list_kernel", "bound": "fp64_issue", "achieved": scl_cw_s, "unit": "codewords/s",
+                           "avg_launch_ms": scl_avg_ms, "codewords_per_launch": cw_per_launch,
+                           "node_updates_per_s": scl_cw_s * SCL_NODE_UPDATES_PER_CW,
+                           "stated_bound_cw_s": fp64_lane_rate / (86016 * 29),
+                           "frac": scl_cw_s / (fp64_lane_rate / (86016 * 29)),
+                           "bound_def": "148 SM x 64 FP64 lanes x sm_max_mhz / (86016 phi evaluations x 29 FP64 instr)"},
+        "roofline_scan": {"kernels": "bandpass+ncc+peaks", "bound": "hbm", "achieved": scan_gbs, "peak": hbm, "unit": "GB/s",
+                          "frac": (scan_gbs / hbm) if scan_gbs else None,
+                          "alg_bytes_per_audio_s": ALG_BYTES_PER_AUDIO_S},
+        "kernel_time_share": {k: v_ / ksum for k, v_ in sorted(kshare.items(), key=lambda kv: -kv[1])},
+        "kernel_ms_per_step": {k: v_ / args.steps for k, v_ in kshare.items()},
+        "cpu_baseline": {"value": cpu_value, "unit": "audio-s/s", "cores": cores, "kind": "port",
+                         "sample": f"first {m} clips of the same batch, oracle verify on {cores} processes, {cwall:.1f} s",
+                         "verdict_agreement": f"{agree_v}/{m}", "scl_attempt_count_agreement": f"{agree_n}/{m}"},
+        "host_threads_per_rank": host_threads,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -29,6 +29,34 @@ def lib():
     return _lib
 
 
+LAUNCHES = 0        # kernels launched through the C-ABI since import (bench.py reports the delta)
+KERNEL_TIMES = None  # when set to a dict, wrappers append (start_event, end_event) per kernel name
+
+
+def count_launch(n: int = 1):
+    global LAUNCHES
+    LAUNCHES += n
+
+
+class timed:
+    """with timed("name"): <one launch>  — records CUDA events on the current (launching) stream when
+    KERNEL_TIMES is enabled; otherwise only counts the launch."""
+    def __init__(self, name, n=1):
+        self.name, self.n = name, n
+    def __enter__(self):
+        count_launch(self.n)
+        if KERNEL_TIMES is not None:
+            import torch
+            self.e0 = torch.cuda.Event(enable_timing=True); self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+    def __exit__(self, *a):
+        if KERNEL_TIMES is not None:
+            self.e1.record()
+            KERNEL_TIMES.setdefault(self.name, []).append((self.e0, self.e1))
+        return False
+
+
 def check(rc: int, what: str = ""):
     if rc != 0:
         msg = lib().es_last_error().decode("utf-8", "replace")

@@ -46,8 +46,9 @@ def hard_decide(llr: torch.Tensor, neg_mode: int = 0, K: int = 448):
     ncw = llr.shape[0] * (2 if neg_mode else 1)
     pay = torch.empty((ncw, (K - 8) // 8), dtype=torch.uint8, device=llr.device)
     crc = torch.empty((ncw,), dtype=torch.uint8, device=llr.device)
-    N.check(N.lib().es_scl_hard(N.ptr(llr), C.c_int(ncw), C.c_int(neg_mode), N.ptr(pay), N.ptr(crc),
-                                N.stream_ptr()), "es_scl_hard")
+    with N.timed("scl_hard"):
+        N.check(N.lib().es_scl_hard(N.ptr(llr), C.c_int(ncw), C.c_int(neg_mode), N.ptr(pay), N.ptr(crc),
+                                    N.stream_ptr()), "es_scl_hard")
     return pay, crc
 
 
@@ -79,10 +80,11 @@ def list_decode(llr: torch.Tensor, list_size: int = 8, neg_mode: int = 0, index:
     if n == 0:
         return out
     scratch = _get_scratch(dev)
-    N.check(N.lib().es_scl_list(N.ptr(llr), N.ptr(index), C.c_int(n), C.c_int(neg_mode), C.c_int(list_size),
-                                N.ptr(scratch), C.c_size_t(scratch.numel()),
-                                N.ptr(out["payload"]), N.ptr(out["crc"]), N.ptr(out["metric"]),
-                                N.ptr(out["npaths"]), N.stream_ptr()), "es_scl_list")
+    with N.timed("scl_list"):
+        N.check(N.lib().es_scl_list(N.ptr(llr), N.ptr(index), C.c_int(n), C.c_int(neg_mode), C.c_int(list_size),
+                                    N.ptr(scratch), C.c_size_t(scratch.numel()),
+                                    N.ptr(out["payload"]), N.ptr(out["crc"]), N.ptr(out["metric"]),
+                                    N.ptr(out["npaths"]), N.stream_ptr()), "es_scl_list")
     return out
 
 
@@ -96,6 +98,7 @@ def encode(payload: torch.Tensor, K: int = 448, want_bits: bool = True, want_wor
     n = payload.shape[0]
     bits = torch.empty((n, 1024), dtype=torch.uint8, device=payload.device) if want_bits else None
     words = torch.empty((n, 32), dtype=torch.int32, device=payload.device) if want_words else None
-    N.check(N.lib().es_polar_encode(N.ptr(payload), C.c_int(n), N.ptr(bits), N.ptr(words), N.stream_ptr()),
-            "es_polar_encode")
+    with N.timed("polar_encode"):
+        N.check(N.lib().es_polar_encode(N.ptr(payload), C.c_int(n), N.ptr(bits), N.ptr(words), N.stream_ptr()),
+                "es_polar_encode")
     return bits, words

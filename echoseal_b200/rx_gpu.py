@@ -69,8 +69,9 @@ def bandpass(x: torch.Tensor) -> torch.Tensor:
     N.require_cuda(x)
     B, n = x.shape
     y = torch.empty((B, 4, n), dtype=torch.float64, device=x.device)
-    N.check(N.lib().es_rx_bandpass(N.ptr(x), C.c_int(B), C.c_int(n), C.c_longlong(x.stride(0)), N.ptr(y),
-                                   N.stream_ptr()), "es_rx_bandpass")
+    with N.timed("bandpass"):
+        N.check(N.lib().es_rx_bandpass(N.ptr(x), C.c_int(B), C.c_int(n), C.c_longlong(x.stride(0)), N.ptr(y),
+                                       N.stream_ptr()), "es_rx_bandpass")
     return y
 
 
@@ -81,7 +82,8 @@ def ncc(y: torch.Tensor) -> torch.Tensor:
     nc = max(0, n - (PRE_L - 1))
     corr = torch.empty((B, 4, nc), dtype=torch.float64, device=y.device)
     if nc > 0:
-        N.check(N.lib().es_rx_ncc(N.ptr(y), C.c_int(B), C.c_int(n), N.ptr(corr), N.stream_ptr()), "es_rx_ncc")
+        with N.timed("ncc"):
+            N.check(N.lib().es_rx_ncc(N.ptr(y), C.c_int(B), C.c_int(n), N.ptr(corr), N.stream_ptr()), "es_rx_ncc")
     return corr
 
 
@@ -94,8 +96,9 @@ def peaks(corr: torch.Tensor):
     npk = torch.zeros((B, 4), dtype=torch.int32, device=corr.device)
     st = torch.zeros((B, 4, 4), dtype=torch.float64, device=corr.device)
     if nc > 0:
-        N.check(N.lib().es_rx_peaks(N.ptr(corr), C.c_int(B), C.c_int(nc), N.ptr(pk), N.ptr(npk), N.ptr(st),
-                                    N.stream_ptr()), "es_rx_peaks")
+        with N.timed("peaks"):
+            N.check(N.lib().es_rx_peaks(N.ptr(corr), C.c_int(B), C.c_int(nc), N.ptr(pk), N.ptr(npk), N.ptr(st),
+                                        N.stream_ptr()), "es_rx_peaks")
     return pk, npk, st
 
 
@@ -112,9 +115,10 @@ def frames(y: torch.Tensor, pk: torch.Tensor, npk: torch.Tensor, hdr_pn: torch.T
         hdr=torch.zeros((B, 4, PEAK_LIMIT, 4), dtype=torch.float32, device=dev),
         hdr_best_s=torch.zeros((B, 4, PEAK_LIMIT), dtype=torch.int32, device=dev),
     )
-    N.check(N.lib().es_rx_frames(N.ptr(y), C.c_int(B), C.c_int(n), N.ptr(pk), N.ptr(npk), N.ptr(hdr_pn),
-                                 N.ptr(out["mf_aligned"]), N.ptr(out["llr_best_s"]), N.ptr(out["hdr"]),
-                                 N.ptr(out["hdr_best_s"]), N.stream_ptr()), "es_rx_frames")
+    with N.timed("frames"):
+        N.check(N.lib().es_rx_frames(N.ptr(y), C.c_int(B), C.c_int(n), N.ptr(pk), N.ptr(npk), N.ptr(hdr_pn),
+                                     N.ptr(out["mf_aligned"]), N.ptr(out["llr_best_s"]), N.ptr(out["hdr"]),
+                                     N.ptr(out["hdr_best_s"]), N.stream_ptr()), "es_rx_frames")
     return out
 
 
@@ -127,6 +131,7 @@ def llr(mf_aligned: torch.Tensor, item_peak: torch.Tensor, pn_packed: torch.Tens
     if I:
         if pn_packed.shape != (I, 152) or pn_packed.dtype != torch.uint8:
             raise ValueError("pn_packed must be uint8 [items,152]")
-        N.check(N.lib().es_rx_llr(N.ptr(mf_aligned), N.ptr(item_peak), N.ptr(pn_packed), C.c_int(I), N.ptr(out),
-                                  N.stream_ptr()), "es_rx_llr")
+        with N.timed("llr"):
+            N.check(N.lib().es_rx_llr(N.ptr(mf_aligned), N.ptr(item_peak), N.ptr(pn_packed), C.c_int(I), N.ptr(out),
+                                      N.stream_ptr()), "es_rx_llr")
     return out

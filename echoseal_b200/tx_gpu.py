@@ -44,8 +44,9 @@ def frames(payload: torch.Tensor, pn: torch.Tensor, hdr_pn: torch.Tensor, band: 
         raise ValueError("band / ctr_lo16 must be int32")
     polar_gpu.set_code(1024, K)
     chips = torch.empty((F, FRAME_LEN), dtype=torch.float32, device=payload.device)
-    N.check(N.lib().es_tx_frames(N.ptr(payload), N.ptr(pn), N.ptr(hdr_pn), N.ptr(band), N.ptr(ctr_lo16),
-                                 C.c_int(F), N.ptr(chips), N.stream_ptr()), "es_tx_frames")
+    with N.timed("tx_frames"):
+        N.check(N.lib().es_tx_frames(N.ptr(payload), N.ptr(pn), N.ptr(hdr_pn), N.ptr(band), N.ptr(ctr_lo16),
+                                     C.c_int(F), N.ptr(chips), N.stream_ptr()), "es_tx_frames")
     return chips
 
 
@@ -57,6 +58,7 @@ def mix(x: torch.Tensor, chips: torch.Tensor, alpha: float, floor_scale: float):
     S, B = x.shape
     out = torch.empty_like(x)
     scale = torch.empty((S,), dtype=torch.float32, device=x.device)
-    N.check(N.lib().es_tx_mix(N.ptr(x), N.ptr(chips), C.c_int(S), C.c_int(B), C.c_double(alpha),
-                              C.c_double(floor_scale), N.ptr(out), N.ptr(scale), N.stream_ptr()), "es_tx_mix")
+    with N.timed("tx_mix"):
+        N.check(N.lib().es_tx_mix(N.ptr(x), N.ptr(chips), C.c_int(S), C.c_int(B), C.c_double(alpha),
+                                  C.c_double(floor_scale), N.ptr(out), N.ptr(scale), N.stream_ptr()), "es_tx_mix")
     return out, scale
