@@ -30,6 +30,7 @@ N_SAMPLES = int(FS * SECS)
 ALG_BYTES_PER_AUDIO_S = 4 * FS             # RX reads each float32 input sample once
 SCL_ALG_BYTES_PER_CW = 4096 + 55           # fp32 LLR in + payload out
 SCL_NODE_UPDATES_PER_CW = 81920            # N log2 N * L
+SCL_DRAM_BYTES_PER_CW = 684e3              # dram read+write per codeword, ncu --set full (profiles/r01_scl_list_ncu_full.txt)
 
 
 def log(*a):
@@ -354,7 +355,7 @@ def main():
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"kernel": "scl_list_kernel", "bound": "hbm", "achieved": achieved_gbs, "peak": hbm, "unit": "GB/s",
-                     "frac": achieved_gbs / hbm, "traffic": None, "peak_source": peak_kind,
+                     "frac": achieved_gbs / hbm, "traffic": cw_per_launch * SCL_DRAM_BYTES_PER_CW, "peak_source": peak_kind,
                      "note": "the SCL decoder is FP64-issue bound, not HBM bound; see roofline_issue"},
         "roofline_issue": {"kernel": "scl_list_kernel", "bound": "fp64_issue", "achieved": scl_cw_s, "unit": "codewords/s",
                            "avg_launch_ms": scl_avg_ms, "codewords_per_launch": cw_per_launch,

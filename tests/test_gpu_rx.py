@@ -174,3 +174,16 @@ def test_batch_matches_single_and_details(env):
     for n, r in zip(names, res):
         for bi in range(4):
             assert [c for _, c in r.attempts[bi]] == list(G[f"{n}/b{bi}/att_ctr"])
+
+
+def test_verdicts_match_unmodified_reference(env):
+    """tests/golden/rx_verdicts.json: verdicts of the reference's own verify() (list_size=8, real
+    fastpolar decoder, 2-7 CPU-minutes per clip)."""
+    import json
+    torch, rx_gpu, detector, clips, taps = env
+    ref = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "rx_verdicts.json")))
+    names = list(ref)
+    audio = [clips[n][0] for n in names]
+    for n, a in zip(names, audio):
+        rx = detector.WatermarkDetector(clips[n][1], list_size=8)
+        assert rx.verify(a, 48000) is ref[n]["verdict"], n
