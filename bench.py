@@ -37,6 +37,18 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# The contract is ONE JSON line on stdout.  Libraries (NCCL's "NCCL version ..." banner, nvcc, pytest-free
+# helpers) write to fd 1 too, so fd 1 is pointed at stderr for the whole run and the JSON line goes to the
+# saved descriptor at the end.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+sys.stdout = os.fdopen(os.dup(2), "w", buffering=1)
+
+
+def emit(line: dict):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
 def bench_key(i: int) -> bytes:
     import hashlib
     return hashlib.sha256(b"echoseal-bench" + int(i).to_bytes(4, "big")).digest()
@@ -199,7 +211,7 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": cores, "kind": "port",
                              "sample": f"{per_step} clips x {args.steps} steps, {scl} SCL-8 decodes"},
             "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -373,7 +385,7 @@ def main():
                          "verdict_agreement": f"{agree_v}/{m}", "scl_attempt_count_agreement": f"{agree_n}/{m}"},
         "host_threads_per_rank": host_threads,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
