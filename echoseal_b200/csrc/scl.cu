@@ -57,6 +57,19 @@ __device__ __forceinline__ double fcomb(double a, double b, uint32_t tab)
     return np_logaddexp(a, b, tab) - np_logaddexp(0.0, a + b, tab);
 }
 
+// same value as fcomb(a, b), also handing out the two phi terms: fm = phi(|a-b|), fp = phi(|a+b|).
+// They are exactly the phi values the reference's penalty needs for the NEXT (odd) leaf, whose LLR is
+// b-a or b+a (rtwm/fastpolar.py:26-40) — so that penalty costs nothing.
+__device__ __forceinline__ double fcomb_parts(double a, double b, uint32_t tab, double& fm, double& fp)
+{
+    const double d = a - b, s = a + b;
+    fm = phi_fast(d, tab);
+    fp = phi_fast(s, tab);
+    const double A = ((d > 0.0) ? a : b) + fm;
+    const double B = (((0.0 - s) > 0.0) ? 0.0 : s) + fp;
+    return A - B;
+}
+
 // ---------------------------------------------------------------------------------------------
 // per-lane state
 // ---------------------------------------------------------------------------------------------
@@ -82,7 +95,7 @@ struct Lane {
     double* g0;          // global level-0 copy of this warp's 4 codewords, [k][4] (+codeword)
     uint32_t tab;        // shared-window address of the phi tables
     int lane, p, gbase;
-    double m, leaf;
+    double m;
     uint32_t ptr, bptr, bs;
     int ord;
     bool active;
@@ -174,7 +187,7 @@ template <int S>
 __device__ __forceinline__ void spine(Lane& L)
 {
 #pragma unroll 1
-    for (int lv = 1; lv <= 10; ++lv) {
+    for (int lv = 1; lv <= 8; ++lv) {
         const int s = 1 << (10 - lv);
         const LvlRef src = lvl_ref<S>(L, lv - 1, 0);
         const LvlRef dst = lvl_ref<S>(L, lv, 0);
@@ -186,13 +199,15 @@ __device__ __forceinline__ void spine(Lane& L)
     L.ptr = 0;
 }
 
+// levels 1..8 for the quad starting at bit i (i % 4 == 0, i > 0): one g node, then f nodes down to level 8.
+// Levels 9 and 10 never touch memory: the quad routine in the kernel keeps them in registers.
 template <int S>
-__device__ __forceinline__ void llr_update(Lane& L, int i)
+__device__ __forceinline__ void llr_update8(Lane& L, int i)
 {
-    const int l0 = 11 - __ffs(i);    // i > 0: level of the g node
+    const int l0 = 11 - __ffs(i);    // <= 8
     g_level<S>(L, l0);
 #pragma unroll 1
-    for (int lv = l0 + 1; lv <= 10; ++lv) f_level<S>(L, lv);
+    for (int lv = l0 + 1; lv <= 8; ++lv) f_level<S>(L, lv);
 }
 
 __device__ __forceinline__ int nth_set8(uint32_t mask, int n)
@@ -207,24 +222,30 @@ __device__ __forceinline__ int nth_set8(uint32_t mask, int n)
     return r;
 }
 
+// quad-local values that must follow a path through a clone
+struct Carry { double c0, c1, c2, c3; uint32_t qb; };
+
 // information-bit step: rank the 2*np candidates, keep list_size, clone into free lanes.
-// pen0/pen1 = penalties of deciding 0 / 1 (rtwm/fastpolar.py:32-40).
-__device__ __forceinline__ int info_step(Lane& L, int list_size, double pen0, double pen1)
+// pen0/pen1 = penalties of deciding 0 / 1 (rtwm/fastpolar.py:32-40).  Metrics are non-negative finite
+// doubles, so their bit patterns order like unsigned integers; the reference's stable tie-break
+// (candidate index 2*ord+bit) folds into the comparison as  (kj < k) + (kj == k && c) == (kj < k + c).
+template <bool CARRY>
+__device__ __forceinline__ int info_step(Lane& L, int list_size, double pen0, double pen1, Carry& cy)
 {
     const unsigned full = 0xffffffffu;
     const double m0 = L.m + pen0, m1 = L.m + pen1;
+    const unsigned long long k0 = L.active ? (unsigned long long)__double_as_longlong(m0) : ~0ull;
+    const unsigned long long k1 = L.active ? (unsigned long long)__double_as_longlong(m1) : ~0ull;
     int r0 = 0, r1 = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        const int aj = __shfl_sync(full, (int)L.active, j, 8);
-        const double m0j = __shfl_sync(full, m0, j, 8);
-        const double m1j = __shfl_sync(full, m1, j, 8);
+        const unsigned long long k0j = __shfl_sync(full, k0, j, 8);
+        const unsigned long long k1j = __shfl_sync(full, k1, j, 8);
         const int oj = __shfl_sync(full, L.ord, j, 8);
-        if (aj) {
-            const bool lt = oj < L.ord, le = oj <= L.ord;
-            r0 += (m0j < m0) + (m1j < m0) + ((m0j == m0) && lt) + ((m1j == m0) && lt);
-            r1 += (m0j < m1) + (m1j < m1) + ((m0j == m1) && le) + ((m1j == m1) && lt);
-        }
+        const unsigned long long lt = (oj < L.ord) ? 1ull : 0ull, le = (oj <= L.ord) ? 1ull : 0ull;
+        const unsigned long long a0 = k0 + lt, a1 = k1 + le, a2 = k1 + lt;
+        r0 += (k0j < a0) + (k1j < a0);
+        r1 += (k0j < a1) + (k1j < a2);
     }
     const bool s0 = L.active && (r0 < list_size);
     const bool s1 = L.active && (r1 < list_size);
@@ -239,34 +260,59 @@ __device__ __forceinline__ int info_step(Lane& L, int list_size, double pen0, do
     const uint32_t cptr = __shfl_sync(full, L.ptr, src, 8);
     const uint32_t cbptr = __shfl_sync(full, L.bptr, src, 8);
     const uint32_t cbs = __shfl_sync(full, L.bs, src, 8);
+    const uint32_t cqb = __shfl_sync(full, cy.qb, src, 8);
+    double q0 = 0, q1 = 0, q2 = 0, q3 = 0;
+    if (CARRY) {
+        q0 = __shfl_sync(full, cy.c0, src, 8); q1 = __shfl_sync(full, cy.c1, src, 8);
+        q2 = __shfl_sync(full, cy.c2, src, 8); q3 = __shfl_sync(full, cy.c3, src, 8);
+    }
     int bit = 0;
     if (s0) { L.m = m0; L.ord = r0; bit = 0; }
     else if (s1) { L.m = m1; L.ord = r1; bit = 1; }
-    else if (take) { L.m = cm1; L.ord = cr1; L.ptr = cptr; L.bptr = cbptr; L.bs = cbs; bit = 1; L.active = true; }
-    else { L.active = false; }
+    else if (take) {
+        L.m = cm1; L.ord = cr1; L.ptr = cptr; L.bptr = cbptr; L.bs = cbs; bit = 1; L.active = true;
+        cy.qb = cqb;
+        if (CARRY) { cy.c0 = q0; cy.c1 = q1; cy.c2 = q2; cy.c3 = q3; }
+    } else { L.active = false; }
     return bit;
 }
 
-// partial-sum update after deciding `bit` at index i (see tests/model_scl_lanes.py for the model)
-__device__ __forceinline__ void beta_update(Lane& L, int i, int bit, uint32_t* xroot)
+// one decision (frozen or information bit) given the leaf LLR and phi(|leaf|)
+template <bool CARRY>
+__device__ __forceinline__ int decide(Lane& L, bool frozen, double leaf, double ph, int list_size, Carry& cy)
 {
-    if ((i & 1) == 0) { L.bs = (L.bs & ~2u) | ((uint32_t)bit << 1); return; }
-    const int t1 = __ffs(~i) - 1;            // trailing ones, 1..10
-    uint32_t X = (uint32_t)bit;
-    const int tr = t1 < 5 ? t1 : 5;
-    for (int j = 0; j < tr; ++j) {
-        const int s = 1 << j;
+    const double al = fabs(leaf);
+    const bool pref1 = (leaf >= 0.0);
+    const double pen0 = pref1 ? (ph + al) : ph;    // deciding 0 against a non-negative LLR costs |l| more
+    const double pen1 = pref1 ? ph : (ph + al);
+    if (frozen) {
+        if (L.active) L.m += pen0;
+        return 0;
+    }
+    return info_step<CARRY>(L, list_size, pen0, pen1, cy);
+}
+
+// partial-sum update after a quad (bits 4q..4q+3): X = the 4 partial sums of the finished level-8 node
+// (see tests/model_scl_lanes.py for the bit-level model of the chain)
+__device__ __forceinline__ void beta_update_quad(Lane& L, int q, uint32_t X, uint32_t* xroot)
+{
+    if ((q & 1) == 0) { L.bs = (L.bs & ~0xf0u) | (X << 4); return; }      // level-8 left child
+    const int t1 = __ffs(~q) - 1;            // trailing ones of q, 1..8
+    const int tr = t1 < 3 ? t1 : 3;
+    for (int j = 0; j < tr; ++j) {           // levels 8, 7, 6 live in the bs register
+        const int s = 4 << j;
         const uint32_t Lb = (L.bs >> s) & ((1u << s) - 1u);
         X = (Lb ^ X) | (X << s);
     }
-    if (t1 <= 4) {
-        const int s = 1 << t1;
-        L.bs = (L.bs & ~(((1u << s) - 1u) << s)) | (X << s);
-    } else if (t1 == 5) {
+    if (t1 <= 2) {
+        const int s = 4 << t1;
+        const uint32_t mask = (s == 16) ? 0xffff0000u : (((1u << s) - 1u) << s);
+        L.bs = (L.bs & ~mask) | (X << s);
+    } else if (t1 == 3) {
         L.sb[L.lane] = X;                       // level 5, word offset 0
         L.bptr = (L.bptr & ~(7u << 12)) | ((uint32_t)L.p << 12);
     } else {
-        const int lstar = 10 - t1;              // 4..0
+        const int lstar = 8 - t1;               // 4..0
         uint32_t* D = (lstar == 0) ? (xroot + L.lane) : (L.sb + ((1 << (5 - lstar)) - 1) * 32 + L.lane);
         D[0] = X;
         int n = 1;
@@ -357,33 +403,47 @@ __global__ void __launch_bounds__(W * 32, 4) scl_list_kernel(SclParams P)
 #pragma unroll 4
             for (int k = L.p; k < 1024; k += 8) dst[k * 4] = (double)(sgn * __ldg(src + k));
         }
-        L.m = 0.0; L.leaf = 0.0; L.ptr = 0; L.bptr = 0; L.bs = 0; L.ord = 0;
+        L.m = 0.0; L.ptr = 0; L.bptr = 0; L.bs = 0; L.ord = 0;
         L.active = (L.p == 0);
         __syncwarp();
 
 #pragma unroll 1
-        for (int i = 0; i < 1024; ++i) {
-            if (i == 0) spine<S>(L);
-            else llr_update<S>(L, i);
+        for (int q = 0; q < 256; ++q) {
+            const int i = q << 2;
+            if (q == 0) spine<S>(L);
+            else llr_update8<S>(L, i);
             __syncwarp();
-            // leaf LLR of this lane's path: level-10 row, slot from the pointer word (own slot unless i == 0)
-            {
-                const int ls = (i == 0) ? 0 : L.p;
-                L.leaf = lvl_ref<S>(L, 10, ls).base[0];
+            const uint32_t fz = (c_frozen[i >> 5] >> (i & 31)) & 15u;       // frozen flags of bits i..i+3
+            Carry cy; cy.qb = 0;
+#pragma unroll 1
+            for (int h = 0; h < 2; ++h) {
+                // level-9 node h of the current level-8 node, read through the (possibly re-pointed) slot
+                const double* l8 = lvl_ref<S>(L, 8, (L.ptr >> 21) & 7).base;
+                const double a0 = l8[0], a1 = l8[32], a2 = l8[64], a3 = l8[96];
+                double x0, x1;
+                if (h == 0) {
+                    x0 = fcomb(a0, a2, L.tab); x1 = fcomb(a1, a3, L.tab);
+                } else {
+                    const uint32_t u0 = cy.qb & 1u, u1 = (cy.qb >> 1) & 1u;
+                    x0 = (u0 ^ u1) ? (a2 - a0) : (a2 + a0);
+                    x1 = u1 ? (a3 - a1) : (a3 + a1);
+                }
+                // even leaf: f of the pair; its two phi terms are the odd leaf's penalty terms
+                double fm, fp;
+                const double leaf0 = fcomb_parts(x0, x1, L.tab, fm, fp);
+                cy.c0 = x0; cy.c1 = x1; cy.c2 = fm; cy.c3 = fp;
+                const int be = decide<true>(L, (fz >> (2 * h)) & 1u, leaf0, phi_fast(leaf0, L.tab), P.list_size, cy);
+                cy.qb |= (uint32_t)be << (2 * h);
+                // odd leaf: g of the pair
+                const double leaf1 = be ? (cy.c1 - cy.c0) : (cy.c1 + cy.c0);
+                const double ph1 = be ? cy.c2 : cy.c3;
+                const int bo = decide<false>(L, (fz >> (2 * h + 1)) & 1u, leaf1, ph1, P.list_size, cy);
+                cy.qb |= (uint32_t)bo << (2 * h + 1);
             }
-            const double al = fabs(L.leaf);
-            const double ph = phi_fast(L.leaf, L.tab);
-            const bool pref1 = (L.leaf >= 0.0);
-            const double pen0 = pref1 ? (ph + al) : ph;    // deciding 0 against a non-negative LLR costs |l| more
-            const double pen1 = pref1 ? ph : (ph + al);
-            int bit = 0;
-            const bool frozen = (c_frozen[i >> 5] >> (i & 31)) & 1u;
-            if (frozen) {
-                if (L.active) L.m += pen0;
-            } else {
-                bit = info_step(L, P.list_size, pen0, pen1);
-            }
-            beta_update(L, i, bit, xroot);
+            uint32_t X = cy.qb;
+            X ^= (X >> 1) & 0x5u;
+            X ^= (X >> 2) & 0x3u;
+            beta_update_quad(L, q, X, xroot);
             __syncwarp();
         }
 
