@@ -15,6 +15,7 @@
 //                 interval 0 is centred on 1 (invc=1, logc=0) so tiny t keeps full relative accuracy.
 #pragma once
 #include <stdint.h>
+#include <string.h>
 
 #ifndef PHI_FN
 #ifdef __CUDACC__
@@ -47,6 +48,28 @@ static inline uint64_t PHI_D2U(double x) { uint64_t u; memcpy(&u, &x, 8); return
 static inline double PHI_U2D(uint64_t u) { double x; memcpy(&x, &u, 8); return x; }
 #endif
 
+// scalar coefficients.  On the device they are read from __constant__ memory so that they are free
+// instruction operands (c[bank][offset]) instead of immediates re-materialised inside hot loops.
+#define PHI_NK 12
+#define PHI_K_VALUES { \
+    92.332482616893656768 /* 0: 64/ln2, exact bits set below */, 0.0 /* 1: ln2/64 hi */, 0.0 /* 2: ln2/64 lo */, \
+    1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, \
+    1.0 / 7.0, -1.0 / 6.0, 0.2, 1.0 / 3.0, 0.0 }
+#ifdef __CUDACC__
+__constant__ double c_phi_k[PHI_NK];
+#define PHI_K(i) c_phi_k[i]
+#else
+static double g_phi_k[PHI_NK];
+#define PHI_K(i) g_phi_k[i]
+#endif
+static inline void phi_fill_k(double* k)
+{
+    const double v[PHI_NK] = PHI_K_VALUES;
+    for (int i = 0; i < PHI_NK; ++i) k[i] = v[i];
+    const uint64_t b0 = 0x40571547652b82feULL, b1 = 0x3f862e42fef00000ULL, b2 = 0x3d7473de6af278edULL;
+    memcpy(&k[0], &b0, 8); memcpy(&k[1], &b1, 8); memcpy(&k[2], &b2, 8);
+}
+
 // tables: [0,64) exp hi, [64,128) exp lo, then 257-entry log tables (entry 256 serves u == 2.0)
 #define PHI_NLT 257
 #define PHI_OFF_EXP_HI 0
@@ -58,9 +81,9 @@ static inline double PHI_U2D(uint64_t u) { double x; memcpy(&x, &u, 8); return x
 
 PHI_FN double phi_fast(double d, phi_tab_t tab)
 {
-    const double INVLN2N = PHI_U2D(0x40571547652b82feULL);   // 64/ln2
-    const double LN2HIN = PHI_U2D(0x3f862e42fef00000ULL);    // ln2/64, 33 significant bits
-    const double LN2LON = PHI_U2D(0x3d7473de6af278edULL);
+    const double INVLN2N = PHI_K(0);                         // 64/ln2
+    const double LN2HIN = PHI_K(1);                          // ln2/64, 33 significant bits
+    const double LN2LON = PHI_K(2);
     const double SHIFT = 6755399441055744.0;                 // 1.5 * 2^52
     // ---- t = exp(-|d|); |d| clamped to < 1401 on the high word (exp(-1400) == 0 either way)
     const uint64_t db = PHI_D2U(d);
@@ -75,9 +98,9 @@ PHI_FN double phi_fast(double d, phi_tab_t tab)
     const int j = ki & 63;
     const int e = ki >> 6;                                    // -2020 .. 0
     const double r2 = r * r;
-    double q = PHI_FMA(r, 1.0 / 720.0, 1.0 / 120.0);
-    q = PHI_FMA(r, q, 1.0 / 24.0);
-    q = PHI_FMA(r, q, 1.0 / 6.0);
+    double q = PHI_FMA(r, PHI_K(3), PHI_K(4));
+    q = PHI_FMA(r, q, PHI_K(5));
+    q = PHI_FMA(r, q, PHI_K(6));
     q = PHI_FMA(r, q, 0.5);
     const double p = PHI_FMA(r2, q, r);                       // exp(r) - 1
     const double th = PHI_LD(tab, PHI_OFF_EXP_HI + j), tl = PHI_LD(tab, PHI_OFF_EXP_LO + j);
@@ -93,10 +116,10 @@ PHI_FN double phi_fast(double d, phi_tab_t tab)
     const int i = (int)(uint32_t)(PHI_D2U(u) >> 44) - 0x3ff00;  // 0..255, 256 iff u == 2.0
     const double ic = PHI_LD(tab, PHI_OFF_INVC + i);
     const double rr = PHI_FMA(u, ic, -1.0);
-    double w = PHI_FMA(rr, 1.0 / 7.0, -1.0 / 6.0);
-    w = PHI_FMA(rr, w, 0.2);
+    double w = PHI_FMA(rr, PHI_K(7), PHI_K(8));
+    w = PHI_FMA(rr, w, PHI_K(9));
     w = PHI_FMA(rr, w, -0.25);
-    w = PHI_FMA(rr, w, 1.0 / 3.0);
+    w = PHI_FMA(rr, w, PHI_K(10));
     w = PHI_FMA(rr, w, -0.5);
     const double ci = c * ic;                                 // c/u to first order ...
     double tail = PHI_FMA(-ci, rr, ci) + PHI_LD(tab, PHI_OFF_LOGC_LO + i);   // ... times (1 - rr)
@@ -119,5 +142,8 @@ static void phi_fill_table(double* tab)
         memcpy(&tab[PHI_OFF_LOGC_LO + i], &PHI_LOGC_LO[i], 8);
     }
     tab[PHI_TAB_DOUBLES - 1] = 0.0;
+#ifndef __CUDACC__
+    phi_fill_k(g_phi_k);
+#endif
 }
 #endif

@@ -229,7 +229,6 @@ struct Carry { double c0, c1, c2, c3; uint32_t qb; };
 // pen0/pen1 = penalties of deciding 0 / 1 (rtwm/fastpolar.py:32-40).  Metrics are non-negative finite
 // doubles, so their bit patterns order like unsigned integers; the reference's stable tie-break
 // (candidate index 2*ord+bit) folds into the comparison as  (kj < k) + (kj == k && c) == (kj < k + c).
-template <bool CARRY>
 __device__ __forceinline__ int info_step(Lane& L, int list_size, double pen0, double pen1, Carry& cy)
 {
     const unsigned full = 0xffffffffu;
@@ -261,24 +260,20 @@ __device__ __forceinline__ int info_step(Lane& L, int list_size, double pen0, do
     const uint32_t cbptr = __shfl_sync(full, L.bptr, src, 8);
     const uint32_t cbs = __shfl_sync(full, L.bs, src, 8);
     const uint32_t cqb = __shfl_sync(full, cy.qb, src, 8);
-    double q0 = 0, q1 = 0, q2 = 0, q3 = 0;
-    if (CARRY) {
-        q0 = __shfl_sync(full, cy.c0, src, 8); q1 = __shfl_sync(full, cy.c1, src, 8);
-        q2 = __shfl_sync(full, cy.c2, src, 8); q3 = __shfl_sync(full, cy.c3, src, 8);
-    }
+    const double q0 = __shfl_sync(full, cy.c0, src, 8), q1 = __shfl_sync(full, cy.c1, src, 8);
+    const double q2 = __shfl_sync(full, cy.c2, src, 8), q3 = __shfl_sync(full, cy.c3, src, 8);
     int bit = 0;
     if (s0) { L.m = m0; L.ord = r0; bit = 0; }
     else if (s1) { L.m = m1; L.ord = r1; bit = 1; }
     else if (take) {
         L.m = cm1; L.ord = cr1; L.ptr = cptr; L.bptr = cbptr; L.bs = cbs; bit = 1; L.active = true;
         cy.qb = cqb;
-        if (CARRY) { cy.c0 = q0; cy.c1 = q1; cy.c2 = q2; cy.c3 = q3; }
+        cy.c0 = q0; cy.c1 = q1; cy.c2 = q2; cy.c3 = q3;
     } else { L.active = false; }
     return bit;
 }
 
 // one decision (frozen or information bit) given the leaf LLR and phi(|leaf|)
-template <bool CARRY>
 __device__ __forceinline__ int decide(Lane& L, bool frozen, double leaf, double ph, int list_size, Carry& cy)
 {
     const double al = fabs(leaf);
@@ -289,7 +284,7 @@ __device__ __forceinline__ int decide(Lane& L, bool frozen, double leaf, double 
         if (L.active) L.m += pen0;
         return 0;
     }
-    return info_step<CARRY>(L, list_size, pen0, pen1, cy);
+    return info_step(L, list_size, pen0, pen1, cy);
 }
 
 // partial-sum update after a quad (bits 4q..4q+3): X = the 4 partial sums of the finished level-8 node
@@ -415,30 +410,34 @@ __global__ void __launch_bounds__(W * 32, 4) scl_list_kernel(SclParams P)
             __syncwarp();
             const uint32_t fz = (c_frozen[i >> 5] >> (i & 31)) & 15u;       // frozen flags of bits i..i+3
             Carry cy; cy.qb = 0;
+            double fm = 0.0, fp = 0.0;
+            int prev = 0;
 #pragma unroll 1
-            for (int h = 0; h < 2; ++h) {
-                // level-9 node h of the current level-8 node, read through the (possibly re-pointed) slot
-                const double* l8 = lvl_ref<S>(L, 8, (L.ptr >> 21) & 7).base;
-                const double a0 = l8[0], a1 = l8[32], a2 = l8[64], a3 = l8[96];
-                double x0, x1;
-                if (h == 0) {
-                    x0 = fcomb(a0, a2, L.tab); x1 = fcomb(a1, a3, L.tab);
+            for (int t = 0; t < 4; ++t) {
+                double leaf, ph;
+                if ((t & 1) == 0) {
+                    // level-9 node t/2 of the current level-8 node, read through the (possibly re-pointed) slot
+                    const double* l8 = lvl_ref<S>(L, 8, (L.ptr >> 21) & 7).base;
+                    const double a0 = l8[0], a1 = l8[32], a2 = l8[64], a3 = l8[96];
+                    double x0, x1;
+                    if (t == 0) {
+                        x0 = fcomb(a0, a2, L.tab); x1 = fcomb(a1, a3, L.tab);
+                    } else {
+                        const uint32_t u0 = cy.qb & 1u, u1 = (cy.qb >> 1) & 1u;
+                        x0 = (u0 ^ u1) ? (a2 - a0) : (a2 + a0);
+                        x1 = u1 ? (a3 - a1) : (a3 + a1);
+                    }
+                    // even leaf: f of the pair; its two phi terms are the odd leaf's penalty terms
+                    leaf = fcomb_parts(x0, x1, L.tab, fm, fp);
+                    ph = phi_fast(leaf, L.tab);
+                    cy.c0 = x0; cy.c1 = x1; cy.c2 = fm; cy.c3 = fp;
                 } else {
-                    const uint32_t u0 = cy.qb & 1u, u1 = (cy.qb >> 1) & 1u;
-                    x0 = (u0 ^ u1) ? (a2 - a0) : (a2 + a0);
-                    x1 = u1 ? (a3 - a1) : (a3 + a1);
+                    // odd leaf: g of the pair
+                    leaf = prev ? (cy.c1 - cy.c0) : (cy.c1 + cy.c0);
+                    ph = prev ? cy.c2 : cy.c3;
                 }
-                // even leaf: f of the pair; its two phi terms are the odd leaf's penalty terms
-                double fm, fp;
-                const double leaf0 = fcomb_parts(x0, x1, L.tab, fm, fp);
-                cy.c0 = x0; cy.c1 = x1; cy.c2 = fm; cy.c3 = fp;
-                const int be = decide<true>(L, (fz >> (2 * h)) & 1u, leaf0, phi_fast(leaf0, L.tab), P.list_size, cy);
-                cy.qb |= (uint32_t)be << (2 * h);
-                // odd leaf: g of the pair
-                const double leaf1 = be ? (cy.c1 - cy.c0) : (cy.c1 + cy.c0);
-                const double ph1 = be ? cy.c2 : cy.c3;
-                const int bo = decide<false>(L, (fz >> (2 * h + 1)) & 1u, leaf1, ph1, P.list_size, cy);
-                cy.qb |= (uint32_t)bo << (2 * h + 1);
+                prev = decide(L, (fz >> t) & 1u, leaf, ph, P.list_size, cy);
+                cy.qb |= (uint32_t)prev << t;
             }
             uint32_t X = cy.qb;
             X ^= (X >> 1) & 0x5u;
@@ -626,6 +625,9 @@ static int scl_configure()
     // phi tables (phi_impl.h layout)
     static double tab[PHI_TAB_DOUBLES];
     phi_fill_table(tab);
+    double kk[PHI_NK];
+    phi_fill_k(kk);
+    ES_CUDA_OK(cudaMemcpyToSymbol(c_phi_k, kk, sizeof(kk)));
     ES_CUDA_OK(cudaMalloc(&g_phi_tab_dev, sizeof(tab)));
     ES_CUDA_OK(cudaMemcpy(g_phi_tab_dev, tab, sizeof(tab), cudaMemcpyHostToDevice));
     g_scl_ctas_per_sm = nb;
