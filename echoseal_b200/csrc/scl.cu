@@ -90,7 +90,8 @@ struct SclParams {
 
 struct Lane {
     double* sa;          // shared alpha rows (+gbase)
-    uint32_t* sb;        // shared beta words (row stride 32 words)
+    uint32_t* sb;        // shared beta words, levels 3..5 (row stride 32 words)
+    uint32_t* gb;        // global beta words, levels 1..2 (rarely touched)
     double* ga;          // global alpha rows, levels 1..S-1 (+gbase)
     double* g0;          // global level-0 copy of this warp's 4 codewords, [k][4] (+codeword)
     uint32_t tab;        // shared-window address of the phi tables
@@ -102,6 +103,13 @@ struct Lane {
 };
 
 struct LvlRef { double* base; int stride; };
+
+// row 0 of the left-child partial-sum words of level l (1..5): 2^(5-l) rows of 32 words
+__device__ __forceinline__ uint32_t* beta_rows(const Lane& L, int l)
+{
+    // shared: level 5 -> row 0, level 4 -> rows 1..2, level 3 -> rows 3..6 ; global: level 2 -> rows 0..7, level 1 -> rows 8..23
+    return (l >= 3) ? L.sb + ((1 << (5 - l)) - 1) * 32 : L.gb + ((l == 2) ? 0 : 8) * 32;
+}
 
 // element k of level lv in `slot` lives at ref.base[k * ref.stride]
 template <int S> __device__ __forceinline__ LvlRef lvl_ref(const Lane& L, int lv, int slot)
@@ -155,16 +163,20 @@ __device__ __forceinline__ void g_level(Lane& L, int l0)
     const LvlRef dst = lvl_ref<S>(L, l0, L.p);
     const double* pa = src.base;
     const double* pb = src.base + s * src.stride;
-    if (s <= 16) {   // levels 6..10: bits in the bs register
+    if (s <= 16) {   // levels 6..8: bits in the bs register; all loads first (s = 4, 8 or 16)
         const uint32_t bits = L.bs >> s;
 #pragma unroll 1
-        for (int k = 0; k < s; ++k) {
-            const double a = pa[k * src.stride], b = pb[k * src.stride];
-            dst.base[k * dst.stride] = ((bits >> k) & 1u) ? (b - a) : (b + a);
+        for (int k0 = 0; k0 < s; k0 += 4) {
+            double va[4], vb[4];
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) { va[kk] = pa[(k0 + kk) * src.stride]; vb[kk] = pb[(k0 + kk) * src.stride]; }
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+                dst.base[(k0 + kk) * dst.stride] = ((bits >> (k0 + kk)) & 1u) ? (vb[kk] - va[kk]) : (vb[kk] + va[kk]);
         }
     } else {         // levels 1..5: bits in pointer-indirected words; 16 elements (32 loads) in flight
         const int bsl = (L.bptr >> (3 * (l0 - 1))) & 7;
-        const uint32_t* bw = L.sb + ((1 << (5 - l0)) - 1) * 32 + L.gbase + bsl;
+        const uint32_t* bw = beta_rows(L, l0) + L.gbase + bsl;
 #pragma unroll 1
         for (int k0 = 0; k0 < s; k0 += 16) {
             const uint32_t word = bw[(k0 >> 5) * 32] >> (k0 & 31);
@@ -308,12 +320,12 @@ __device__ __forceinline__ void beta_update_quad(Lane& L, int q, uint32_t X, uin
         L.bptr = (L.bptr & ~(7u << 12)) | ((uint32_t)L.p << 12);
     } else {
         const int lstar = 8 - t1;               // 4..0
-        uint32_t* D = (lstar == 0) ? (xroot + L.lane) : (L.sb + ((1 << (5 - lstar)) - 1) * 32 + L.lane);
+        uint32_t* D = (lstar == 0) ? (xroot + L.lane) : (beta_rows(L, lstar) + L.lane);
         D[0] = X;
         int n = 1;
         for (int l = 5; l > lstar; --l) {
             const int bsl = (L.bptr >> (3 * (l - 1))) & 7;
-            const uint32_t* Lp = L.sb + ((1 << (5 - l)) - 1) * 32 + L.gbase + bsl;
+            const uint32_t* Lp = beta_rows(L, l) + L.gbase + bsl;
             for (int w = 0; w < n; ++w) {
                 const uint32_t x = D[w * 32];
                 D[(n + w) * 32] = x;
@@ -345,11 +357,13 @@ __device__ __forceinline__ uint8_t crc8_step_bit(uint8_t reg, uint32_t bit)
 // list decoder kernel: W warps per CTA share the phi tables; each warp decodes 4 codewords at a time
 // ---------------------------------------------------------------------------------------------
 template <int S> struct SclLayout {
-    static constexpr int AROWS = (1 << (11 - S)) - 2 + 1;            // levels S..9 + one row for the leaves
-    static constexpr int WARP_BYTES = AROWS * 256 + 31 * 128;
+    static constexpr int AROWS = (1 << (11 - S)) - 4;                   // levels S..8 (9 and 10 live in registers)
+    static constexpr int BROWS_S = 7;                                    // beta words of levels 3..5 in shared memory
+    static constexpr int BROWS_G = 24;                                   // beta words of levels 1..2 in global memory
+    static constexpr int WARP_BYTES = AROWS * 256 + BROWS_S * 128;
     static constexpr int TAB_BYTES = PHI_TAB_DOUBLES * 8;
-    static constexpr size_t G_ROWS = 1024 - (1 << (11 - S));           // global rows, levels 1..S-1
-    static constexpr size_t G_DOUBLES = G_ROWS * 32 + 1024 * 4;        // + level-0 copy [1024][4]
+    static constexpr size_t G_ROWS = 1024 - (1 << (11 - S));           // global alpha rows, levels 1..S-1
+    static constexpr size_t G_DOUBLES = G_ROWS * 32 + 1024 * 4 + BROWS_G * 16;   // + level-0 copy [1024][4] + beta rows
     static_assert(AROWS * 256 >= 32 * 128, "alpha region must hold the root partial sums");
 };
 
@@ -380,6 +394,7 @@ __global__ void __launch_bounds__(W * 32, 4) scl_list_kernel(SclParams P)
     double* gscr = P.scratch + (size_t)gwarp * P.scratch_stride;
     L.ga = gscr + L.gbase;
     L.g0 = gscr + LY::G_ROWS * 32 + (L.lane >> 3);
+    L.gb = reinterpret_cast<uint32_t*>(gscr + LY::G_ROWS * 32 + 1024 * 4);
     const int K = c_K;
     const int nbytes = (K - 8) >> 3;
     const int ngroups = (P.ncw + 3) >> 2;
