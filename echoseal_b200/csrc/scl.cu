@@ -121,26 +121,24 @@ template <int S> __device__ __forceinline__ LvlRef lvl_ref(const Lane& L, int lv
     return r;
 }
 
-// the one place the f-combine is evaluated: dst[k*ds] = f(a[k*ss], b[k*ss]), k < count.
-// Two elements per trip (4 independent phi chains) with the next pair's operands prefetched.
+// the one place the f-combine of a whole level is evaluated: dst[k*ds] = f(a[k*ss], b[k*ss]), k < count,
+// count even (callers guarantee it).  Two elements per trip (4 independent phi chains) with the next
+// pair's operands prefetched.  ONE copy on purpose: the kernel is instruction-cache sensitive.
 __device__ __noinline__ void f_loop(const double* a, const double* b, int ss, double* dst, int ds, int count,
                                     uint32_t tab)
 {
-    int k = 0;
-    if (count >= 2) {
-        double a0 = a[0], b0 = b[0], a1 = a[ss], b1 = b[ss];
+    if (count < 2) return;
+    double a0 = a[0], b0 = b[0], a1 = a[ss], b1 = b[ss];
 #pragma unroll 1
-        for (; k + 2 <= count; k += 2) {
-            const int kn = (k + 4 <= count) ? (k + 2) : k;      // prefetch (re-reads the last pair at the end)
-            const double na0 = a[kn * ss], nb0 = b[kn * ss], na1 = a[(kn + 1) * ss], nb1 = b[(kn + 1) * ss];
-            const double r0 = fcomb(a0, b0, tab);
-            const double r1 = fcomb(a1, b1, tab);
-            dst[k * ds] = r0;
-            dst[(k + 1) * ds] = r1;
-            a0 = na0; b0 = nb0; a1 = na1; b1 = nb1;
-        }
+    for (int k = 0; k + 2 <= count; k += 2) {
+        const int kn = (k + 4 <= count) ? (k + 2) : k;      // prefetch (re-reads the last pair at the end)
+        const double na0 = a[kn * ss], nb0 = b[kn * ss], na1 = a[(kn + 1) * ss], nb1 = b[(kn + 1) * ss];
+        const double r0 = fcomb(a0, b0, tab);
+        const double r1 = fcomb(a1, b1, tab);
+        dst[k * ds] = r0;
+        dst[(k + 1) * ds] = r1;
+        a0 = na0; b0 = nb0; a1 = na1; b1 = nb1;
     }
-    if (k < count) dst[k * ds] = fcomb(a[k * ss], b[k * ss], tab);
 }
 
 template <int S>
@@ -203,9 +201,10 @@ __device__ __forceinline__ void spine(Lane& L)
         const int s = 1 << (10 - lv);
         const LvlRef src = lvl_ref<S>(L, lv - 1, 0);
         const LvlRef dst = lvl_ref<S>(L, lv, 0);
-        const int count = (s > L.p) ? ((s - L.p + 7) >> 3) : 0;
+        const int P = (s >= 16) ? 8 : (s >> 1);              // participating lanes; each gets an even count
+        const int count = (L.p < P) ? (s / P) : 0;
         const double* pa = src.base + L.p * src.stride;
-        f_loop(pa, pa + s * src.stride, 8 * src.stride, dst.base + L.p * dst.stride, 8 * dst.stride, count, L.tab);
+        f_loop(pa, pa + s * src.stride, P * src.stride, dst.base + L.p * dst.stride, P * dst.stride, count, L.tab);
         __syncwarp();
     }
     L.ptr = 0;
