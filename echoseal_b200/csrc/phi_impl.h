@@ -38,6 +38,9 @@ __device__ __forceinline__ double phi_lds(uint32_t addr)
 #define PHI_FMA(a, b, c) __fma_rn((a), (b), (c))
 #define PHI_D2U(x) ((uint64_t)__double_as_longlong(x))
 #define PHI_U2D(x) __longlong_as_double((long long)(x))
+#define PHI_HI(x) ((uint32_t)__double2hiint(x))
+#define PHI_LO(x) ((uint32_t)__double2loint(x))
+#define PHI_HILO(hi, lo) __hiloint2double((int)(hi), (int)(lo))
 #else
 #include <math.h>
 #include <string.h>
@@ -46,6 +49,9 @@ typedef const double* phi_tab_t;
 #define PHI_FMA(a, b, c) fma((a), (b), (c))
 static inline uint64_t PHI_D2U(double x) { uint64_t u; memcpy(&u, &x, 8); return u; }
 static inline double PHI_U2D(uint64_t u) { double x; memcpy(&x, &u, 8); return x; }
+#define PHI_HI(x) ((uint32_t)(PHI_D2U(x) >> 32))
+#define PHI_LO(x) ((uint32_t)PHI_D2U(x))
+#define PHI_HILO(hi, lo) PHI_U2D(((uint64_t)(uint32_t)(hi) << 32) | (uint32_t)(lo))
 #endif
 
 // scalar coefficients.  On the device they are read from __constant__ memory so that they are free
@@ -86,12 +92,11 @@ PHI_FN double phi_fast(double d, phi_tab_t tab)
     const double LN2LON = PHI_K(2);
     const double SHIFT = 6755399441055744.0;                 // 1.5 * 2^52
     // ---- t = exp(-|d|); |d| clamped to < 1401 on the high word (exp(-1400) == 0 either way)
-    const uint64_t db = PHI_D2U(d);
-    uint32_t dhi = (uint32_t)(db >> 32) & 0x7fffffffu;
+    uint32_t dhi = PHI_HI(d) & 0x7fffffffu;
     dhi = dhi < 0x4095e000u ? dhi : 0x4095e000u;             // 0x4095e000_00000000 = 1400.0
-    const double dd = PHI_U2D(((uint64_t)dhi << 32) | (db & 0xffffffffu));
+    const double dd = PHI_HILO(dhi, PHI_LO(d));
     double kd = PHI_FMA(-dd, INVLN2N, SHIFT);
-    const int32_t ki = (int32_t)(uint32_t)PHI_D2U(kd);
+    const int32_t ki = (int32_t)PHI_LO(kd);
     kd -= SHIFT;
     double r = PHI_FMA(kd, -LN2HIN, -dd);
     r = PHI_FMA(kd, -LN2LON, r);
@@ -108,12 +113,12 @@ PHI_FN double phi_fast(double d, phi_tab_t tab)
     // t = tm * 2^e in two exact steps (2^e1 on the exponent field, 2^e2 as a factor): the product with
     // 2^e2 is folded into the two fmas below, so a subnormal t is rounded exactly once
     const int e1 = e >> 1, e2 = e - e1;                       // both >= -1010
-    const double t1 = PHI_U2D(PHI_D2U(tm) + ((uint64_t)(int64_t)e1 << 52));
-    const double s2 = PHI_U2D((uint64_t)(1023 + e2) << 52);
+    const double t1 = PHI_HILO(PHI_HI(tm) + ((uint32_t)e1 << 20), PHI_LO(tm));
+    const double s2 = PHI_HILO((uint32_t)(1023 + e2) << 20, 0u);
     // ---- log1p(t), 0 <= t <= 1
     const double u = PHI_FMA(t1, s2, 1.0);
     const double c = PHI_FMA(t1, s2, -(u - 1.0));
-    const int i = (int)(uint32_t)(PHI_D2U(u) >> 44) - 0x3ff00;  // 0..255, 256 iff u == 2.0
+    const int i = (int)(PHI_HI(u) >> 12) - 0x3ff00;           // 0..255, 256 iff u == 2.0
     const double ic = PHI_LD(tab, PHI_OFF_INVC + i);
     const double rr = PHI_FMA(u, ic, -1.0);
     double w = PHI_FMA(rr, PHI_K(7), PHI_K(8));
