@@ -511,91 +511,113 @@ __global__ void __launch_bounds__(FR_THREADS) frames_kernel(const double* __rest
 }
 
 // ---------------------------------------------------------------------------------------------
-// K5: despread + LLR scaling, one CTA per (item, variant)
+// K5: despread + LLR scaling, one WARP per (item, variant): the 1024 despread chips live in registers
+// (32 per lane); the exact medians (np.median of the tail and of |tail - median|) come from a bit-wise
+// radix select over order-preserving 32-bit keys with warp-wide REDUX counts — no sort, no barriers.
 // ---------------------------------------------------------------------------------------------
-constexpr int LLR_THREADS = 256;
+constexpr int LLR_WARPS = 4;
 
-__device__ void bitonic_sort_1024(float* s, int tid)
+__device__ __forceinline__ uint32_t f32_key(float v)
 {
-    for (int k = 2; k <= 1024; k <<= 1) {
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = tid; i < 1024; i += LLR_THREADS) {
-                const int l = i ^ j;
-                if (l > i) {
-                    const float a = s[i], b = s[l];
-                    const bool up = ((i & k) == 0);
-                    if ((a > b) == up) { s[i] = b; s[l] = a; }
-                }
-            }
-            __syncthreads();
-        }
-    }
+    const uint32_t u = __float_as_uint(v);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_f32(uint32_t k)
+{
+    return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
-__device__ double block_sum(double v, double* red, int tid)
+// kth smallest (0-based) of the 32x32 keys held by the warp (invalid entries carry key 0xffffffff)
+__device__ __forceinline__ uint32_t warp_select(const uint32_t (&key)[32], int kth)
 {
+    uint32_t prefix = 0;
+#pragma unroll 1
+    for (int b = 31; b >= 0; --b) {
+        const uint32_t cand = prefix | (1u << b);
+        int cnt = 0;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    __syncthreads();
-    if ((tid & 31) == 0) red[tid >> 5] = v;
-    __syncthreads();
-    double t = 0.0;
-    for (int q = 0; q < LLR_THREADS / 32; ++q) t += red[q];
-    return t;
+        for (int j = 0; j < 32; ++j) cnt += (key[j] < cand) ? 1 : 0;
+        cnt = __reduce_add_sync(0xffffffffu, cnt);
+        if (cnt <= kth) prefix = cand;
+    }
+    return prefix;
 }
 
-__global__ void __launch_bounds__(LLR_THREADS) llr_kernel(const float* __restrict__ mf_aligned,
-                                                          const int32_t* __restrict__ item_peak,
-                                                          const uint8_t* __restrict__ pn_packed /*[items][152]*/,
-                                                          float* __restrict__ llr)
+// np.median semantics on the valid keys: middle element, or the float32 mean of the two middle ones
+__device__ __forceinline__ float warp_median(const uint32_t (&key)[32], int nt)
 {
-    __shared__ float desp[NPAY];
-    __shared__ float srt[NPAY];
-    __shared__ double red[LLR_THREADS / 32];
-    const int item = blockIdx.x >> 1, variant = blockIdx.x & 1;
-    const int tid = threadIdx.x;
+    if (nt & 1) return key_f32(warp_select(key, nt >> 1));
+    const int k1 = (nt >> 1) - 1;
+    const uint32_t q1 = warp_select(key, k1);
+    int le = 0;
+    uint32_t nxt = 0xffffffffu;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        le += (key[j] <= q1) ? 1 : 0;
+        if (key[j] > q1) nxt = min(nxt, key[j]);
+    }
+    le = __reduce_add_sync(0xffffffffu, le);
+    nxt = __reduce_min_sync(0xffffffffu, nxt);
+    const uint32_t q2 = (le > k1 + 1) ? q1 : nxt;
+    return (key_f32(q1) + key_f32(q2)) * 0.5f;
+}
+
+__global__ void __launch_bounds__(LLR_WARPS * 32) llr_kernel(const float* __restrict__ mf_aligned,
+                                                             const int32_t* __restrict__ item_peak,
+                                                             const uint8_t* __restrict__ pn_packed /*[items][152]*/,
+                                                             int nwork, float* __restrict__ llr)
+{
+    const int lane = threadIdx.x & 31;
+    const int work = blockIdx.x * LLR_WARPS + (threadIdx.x >> 5);
+    if (work >= nwork) return;
+    const int item = work >> 1, variant = work & 1;
     const int pidx = item_peak[item];
     const int band = (pidx / PEAK_LIMIT) & 3;
     const int nh = c_mf_len[band];
     const int guard = min(NPAY / 4, max(nh / 2, 24));
+    const int nt = NPAY - guard;
     const float* mf = mf_aligned + (long long)pidx * NPAY;
     const uint8_t* pn = pn_packed + (long long)item * 152;
     const int pn_off = variant ? 0 : (PRE_L + HDR_L);      // variant 0: bits [191,1215) ; variant 1: bits [0,1024)
-    for (int t = tid; t < NPAY; t += LLR_THREADS) {
-        const int q = pn_off + t;
-        const float s = ((pn[q >> 3] >> (7 - (q & 7))) & 1) ? 1.0f : -1.0f;
-        desp[t] = mf[t] * s;
-    }
-    __syncthreads();
-    const int nt = NPAY - guard;
-    // mean of the tail
+    float d[32];
+    uint32_t key[32];
     double acc = 0.0;
-    for (int t = guard + tid; t < NPAY; t += LLR_THREADS) acc += (double)desp[t];
-    const float mu = (float)(block_sum(acc, red, tid) / nt);
-    // median of the tail (float32; even count -> mean of the two middle values in float32)
-    for (int t = tid; t < NPAY; t += LLR_THREADS) srt[t] = (t < nt) ? desp[guard + t] : CUDART_INF_F;
-    __syncthreads();
-    bitonic_sort_1024(srt, tid);
-    const float medv = (nt & 1) ? srt[nt >> 1] : (srt[(nt >> 1) - 1] + srt[nt >> 1]) * 0.5f;
-    __syncthreads();
-    for (int t = tid; t < NPAY; t += LLR_THREADS) srt[t] = (t < nt) ? fabsf(desp[guard + t] - medv) : CUDART_INF_F;
-    __syncthreads();
-    bitonic_sort_1024(srt, tid);
-    const float madv = (nt & 1) ? srt[nt >> 1] : (srt[(nt >> 1) - 1] + srt[nt >> 1]) * 0.5f;
-    // std of the tail (population, float32 semantics approximated in fp64)
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const int t = j * 32 + lane;
+        const int q = pn_off + t;
+        const float s = ((__ldg(pn + (q >> 3)) >> (7 - (q & 7))) & 1) ? 1.0f : -1.0f;
+        d[j] = __ldg(mf + t) * s;
+        const bool tail = t >= guard;
+        key[j] = tail ? f32_key(d[j]) : 0xffffffffu;
+        if (tail) acc += (double)d[j];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    const float mu = (float)(acc / nt);
+    const float medv = warp_median(key, nt);
     double a2 = 0.0;
-    for (int t = guard + tid; t < NPAY; t += LLR_THREADS) { const double e = (double)desp[t] - (double)mu; a2 += e * e; }
-    const float sd = (float)sqrt(block_sum(a2, red, tid) / nt);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const bool tail = (j * 32 + lane) >= guard;
+        key[j] = tail ? f32_key(fabsf(d[j] - medv)) : 0xffffffffu;
+        if (tail) { const double e = (double)d[j] - (double)mu; a2 += e * e; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    const float madv = warp_median(key, nt);
+    const float sd = (float)sqrt(a2 / nt);
     const double sigma_mad = 1.4826 * ((double)madv + 1e-12);
     const double sigma_std = (double)sd + 1e-12;
     const double sigma = fmax(fmax(sigma_mad, sigma_std), 0.1);
     double scale = 2.0 / (sigma * sigma);
     scale = fmin(fmax(scale, 0.5), 30.0);
     const float fscale = (float)scale;
-    float* out = llr + ((long long)item * 2 + variant) * NPAY;
-    for (int t = tid; t < NPAY; t += LLR_THREADS) {
-        const float v = (desp[t] - mu) * fscale;
-        out[t] = fminf(fmaxf(v, -12.0f), 12.0f);
+    float* out = llr + (long long)work * NPAY;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const float v = (d[j] - mu) * fscale;
+        out[j * 32 + lane] = fminf(fmaxf(v, -12.0f), 12.0f);
     }
 }
 
@@ -670,7 +692,8 @@ int es_rx_llr(const float* mf_aligned, const int32_t* item_peak, const uint8_t* 
 {
     if (!g_rx_ready) { set_error("es_rx_llr: call es_rx_set_filters first"); return ES_ENOTREADY; }
     if (nitems <= 0) return ES_OK;
-    llr_kernel<<<nitems * 2, LLR_THREADS, 0, (cudaStream_t)stream>>>(mf_aligned, item_peak, pn_packed, llr);
+    const int nwork = nitems * 2;
+    llr_kernel<<<(nwork + LLR_WARPS - 1) / LLR_WARPS, LLR_WARPS * 32, 0, (cudaStream_t)stream>>>(mf_aligned, item_peak, pn_packed, nwork, llr);
     ES_CUDA_OK(cudaGetLastError());
     return ES_OK;
 }
