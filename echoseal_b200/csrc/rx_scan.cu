@@ -33,39 +33,70 @@ __constant__ int c_mf_len[NBANDS];
 static int g_rx_ready = 0;
 
 // ---------------------------------------------------------------------------------------------
-// K1: band-pass.  One thread per (chunk, band, clip): direct-form II transposed, the operation
+// K1: band-pass.  One LANE per (clip, band, 2048-sample chunk): direct-form II transposed, the operation
 // order of scipy's lfilter, states in registers; chunks other than the first start from zero state
-// BP_WARM samples early (the filter's impulse response has decayed below 1e-12 by then).
+// BP_WARM samples early (the filter's impulse response has decayed below 1e-12 by then; samples before
+// the clip start are zeros, which keep the zero state exactly).  A warp owns 32 consecutive chunks and
+// moves data through shared-memory tiles so that every global access is a full 128-byte (input) or
+// 256-byte (output) row: the per-lane streams themselves would touch 32 different lines per instruction.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) bandpass_kernel(const float* __restrict__ x, int nclips, int n,
-                                                       long long x_stride, double* __restrict__ y)
+constexpr int BP_WARPS = 3;
+struct BpWarpShared {
+    float xin[32][33];
+    double yout[32][33];
+};
+
+__global__ void __launch_bounds__(BP_WARPS * 32) bandpass_kernel(const float* __restrict__ x, int nclips, int n,
+                                                                 long long x_stride, double* __restrict__ y)
 {
+    __shared__ BpWarpShared SH[BP_WARPS];
+    const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+    BpWarpShared& S = SH[wl];
     const int nchunks = (n + BP_CHUNK - 1) / BP_CHUNK;
-    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long total = (long long)nclips * NBANDS * nchunks;
-    if (tid >= total) return;
-    const int chunk = (int)(tid % nchunks);
-    const int band = (int)((tid / nchunks) % NBANDS);
-    const int clip = (int)(tid / ((long long)nchunks * NBANDS));
+    const int groups = (nchunks + 31) / 32;                       // warps per (clip, band)
+    const long long wid = (long long)blockIdx.x * BP_WARPS + wl;
+    if (wid >= (long long)nclips * NBANDS * groups) return;
+    const int grp = (int)(wid % groups);
+    const int band = (int)((wid / groups) % NBANDS);
+    const int clip = (int)(wid / ((long long)groups * NBANDS));
     const float* xs = x + (long long)clip * x_stride;
     double* ys = y + ((long long)clip * NBANDS + band) * n;
-    double b[9], a[9];
+    double b[9], a[9], z[8];
 #pragma unroll
     for (int i = 0; i < 9; ++i) { b[i] = c_bp_b[band][i]; a[i] = c_bp_a[band][i]; }
-    double z[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) z[i] = 0.0;
-    const int out0 = chunk * BP_CHUNK;
-    const int out1 = min(n, out0 + BP_CHUNK);
-    const int j0 = max(0, out0 - BP_WARM);
+    const int chunk0 = grp * 32;
+    // step s covers samples [out0 - BP_WARM + 32 s, +32) of every lane's chunk
+    const int nsteps = (BP_WARM + BP_CHUNK) / 32;
 #pragma unroll 1
-    for (int j = j0; j < out1; ++j) {
-        const double xn = (double)__ldg(xs + j);
-        const double yn = fma(b[0], xn, z[0]);
+    for (int st = 0; st < nsteps; ++st) {
+        const int rel = -BP_WARM + st * 32;                        // offset from each chunk's first output
+        // cooperative load: row r = chunk chunk0+r, 32 consecutive samples
+#pragma unroll 4
+        for (int r = 0; r < 32; ++r) {
+            const long long j = (long long)(chunk0 + r) * BP_CHUNK + rel + lane;
+            S.xin[r][lane] = (j >= 0 && j < n && chunk0 + r < nchunks) ? __ldg(xs + j) : 0.0f;
+        }
+        __syncwarp();
+#pragma unroll 4
+        for (int t = 0; t < 32; ++t) {
+            const double xn = (double)S.xin[lane][t];
+            const double yn = fma(b[0], xn, z[0]);
 #pragma unroll
-        for (int i = 0; i < 7; ++i) z[i] = fma(-a[i + 1], yn, fma(b[i + 1], xn, z[i + 1]));
-        z[7] = fma(-a[8], yn, b[8] * xn);
-        if (j >= out0) ys[j] = yn;
+            for (int i = 0; i < 7; ++i) z[i] = fma(-a[i + 1], yn, fma(b[i + 1], xn, z[i + 1]));
+            z[7] = fma(-a[8], yn, b[8] * xn);
+            S.yout[lane][t] = yn;
+        }
+        __syncwarp();
+        if (rel >= 0) {
+#pragma unroll 4
+            for (int r = 0; r < 32; ++r) {
+                const long long j = (long long)(chunk0 + r) * BP_CHUNK + rel + lane;
+                if (chunk0 + r < nchunks && j < n) ys[j] = S.yout[r][lane];
+            }
+        }
+        __syncwarp();
     }
 }
 
@@ -646,9 +677,8 @@ int es_rx_bandpass(const float* x, int nclips, int n, long long x_stride, double
     if (!g_rx_ready) { set_error("es_rx_bandpass: call es_rx_set_filters first"); return ES_ENOTREADY; }
     if (nclips <= 0 || n <= 0) return ES_OK;
     const long long nchunks = (n + BP_CHUNK - 1) / BP_CHUNK;
-    const long long total = (long long)nclips * NBANDS * nchunks;
-    const int threads = 128;
-    bandpass_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(x, nclips, n, x_stride, y);
+    const long long warps = (long long)nclips * NBANDS * ((nchunks + 31) / 32);
+    bandpass_kernel<<<(unsigned)((warps + BP_WARPS - 1) / BP_WARPS), BP_WARPS * 32, 0, (cudaStream_t)stream>>>(x, nclips, n, x_stride, y);
     ES_CUDA_OK(cudaGetLastError());
     return ES_OK;
 }
