@@ -155,10 +155,10 @@ struct SelShared {
     unsigned int hist[SEL_BINS];
     double buf[SEL_CAP];
     unsigned int count;
-    int bin;
-    unsigned int below;
+    int bin, bin2;
+    unsigned int below, below2, topcount;
     unsigned long long prefix;
-    double result;
+    double result, result2;
 };
 
 // value(v) = MODE ? |v - center| : v
@@ -174,50 +174,12 @@ template <int MODE> __device__ __forceinline__ int sel_bin(double val)
     return b;
 }
 
-// k-th smallest (0-based) of value(c[i]), i < nc.  All threads of the CTA call it; result broadcast.
+// exact MSB radix select (8 bits per pass) restricted to one linear bin; used when a bin overflows the
+// shared buffer (degenerate distributions, e.g. silence: every value equal)
 template <int MODE>
-__device__ double select_kth(const double* __restrict__ c, int nc, int k, double center, SelShared& S)
+__device__ double radix_select_in_bin(const double* __restrict__ c, int nc, int bin, int kk, double center, SelShared& S)
 {
     const int tid = threadIdx.x;
-    for (int b = tid; b < SEL_BINS; b += PK_THREADS) S.hist[b] = 0;
-    if (tid == 0) S.count = 0;
-    __syncthreads();
-    for (int i = tid; i < nc; i += PK_THREADS) atomicAdd(&S.hist[sel_bin<MODE>(sel_value<MODE>(c[i], center))], 1u);
-    __syncthreads();
-    if (tid == 0) {
-        unsigned int acc = 0;
-        int b = 0;
-        for (; b < SEL_BINS; ++b) {
-            if (acc + S.hist[b] > (unsigned)k) break;
-            acc += S.hist[b];
-        }
-        S.bin = b; S.below = acc;
-    }
-    __syncthreads();
-    const int bin = S.bin;
-    const unsigned int m = S.hist[bin];
-    const int kk = k - (int)S.below;               // rank inside the bin
-    if (m <= (unsigned)SEL_CAP) {
-        for (int i = tid; i < nc; i += PK_THREADS) {
-            const double v = sel_value<MODE>(c[i], center);
-            if (sel_bin<MODE>(v) == bin) S.buf[atomicAdd(&S.count, 1u)] = v;
-        }
-        __syncthreads();
-        // rank counting: the kk-th smallest is the value v with  #less <= kk < #less + #equal
-        for (int i = tid; i < (int)m; i += PK_THREADS) {
-            const double v = S.buf[i];
-            int less = 0, eq = 0;
-            for (int j = 0; j < (int)m; ++j) {
-                const double w = S.buf[j];
-                less += (w < v); eq += (w == v);
-            }
-            if (less <= kk && kk < less + eq) S.result = v;    // all writers write the same value
-        }
-        __syncthreads();
-        return S.result;
-    }
-    // degenerate distribution (e.g. silence: every value equal): MSB radix select on the raw bits,
-    // restricted to the selected bin, 8 bits per pass
     unsigned long long prefix = 0, mask = 0;
     int kr = kk;
     for (int shift = 56; shift >= 0; shift -= 8) {
@@ -249,8 +211,83 @@ __device__ double select_kth(const double* __restrict__ c, int nc, int k, double
     return key_f64(prefix);
 }
 
+// np.median of value(c[i]): the middle element, or the mean of the two middle ones (ranks k1 <= k2 = k1+1).
+// Two passes over the data: a 2048-bin monotone histogram, then a gather of the bin(s) holding the two
+// ranks and an exact rank count in shared memory.  `topbin` (MODE 0 only): smallest bin b with
+// count(bins >= b) >= min(5, nc) — used by the top-k fallback.  All threads call it; result broadcast.
+template <int MODE>
+__device__ double median_of(const double* __restrict__ c, int nc, double center, SelShared& S, int* topbin)
+{
+    const int tid = threadIdx.x;
+    const int k2 = nc >> 1, k1 = (nc - 1) >> 1;
+    for (int b = tid; b < SEL_BINS; b += PK_THREADS) S.hist[b] = 0;
+    if (tid == 0) S.count = 0;
+    __syncthreads();
+    for (int i = tid; i < nc; i += PK_THREADS) atomicAdd(&S.hist[sel_bin<MODE>(sel_value<MODE>(c[i], center))], 1u);
+    __syncthreads();
+    if (tid == 0) {
+        unsigned int acc = 0;
+        int b = 0;
+        for (; b < SEL_BINS; ++b) {
+            if (acc + S.hist[b] > (unsigned)k1) break;
+            acc += S.hist[b];
+        }
+        S.bin = b; S.below = acc;
+        int b2 = b;
+        unsigned int acc2 = acc;
+        for (; b2 < SEL_BINS; ++b2) {
+            if (acc2 + S.hist[b2] > (unsigned)k2) break;
+            acc2 += S.hist[b2];
+        }
+        S.bin2 = b2; S.below2 = acc2;
+        if (topbin) {
+            const unsigned int want = nc < 5 ? (unsigned)nc : 5u;
+            unsigned int t = 0;
+            int tb = SEL_BINS - 1;
+            for (; tb > 0; --tb) { t += S.hist[tb]; if (t >= want) break; }
+            if (tb == 0) t += S.hist[0];
+            *topbin = tb;
+            S.topcount = t;
+        }
+    }
+    __syncthreads();
+    const int b1 = S.bin, b2 = S.bin2;
+    const unsigned int m = S.hist[b1] + ((b2 != b1) ? S.hist[b2] : 0u);
+    const int kk1 = k1 - (int)S.below;
+    if (m <= (unsigned)SEL_CAP) {
+        for (int i = tid; i < nc; i += PK_THREADS) {
+            const double v = sel_value<MODE>(c[i], center);
+            const int bb = sel_bin<MODE>(v);
+            if (bb == b1 || bb == b2) S.buf[atomicAdd(&S.count, 1u)] = v;
+        }
+        __syncthreads();
+        // the kk-th smallest of the gathered values is the v with  #less <= kk < #less + #equal
+        const int kk2 = kk1 + (k2 - k1);
+        for (int i = tid; i < (int)m; i += PK_THREADS) {
+            const double v = S.buf[i];
+            int less = 0, eq = 0;
+            for (int j = 0; j < (int)m; ++j) {
+                const double w = S.buf[j];
+                less += (w < v); eq += (w == v);
+            }
+            if (less <= kk1 && kk1 < less + eq) S.result = v;      // all writers write the same value
+            if (less <= kk2 && kk2 < less + eq) S.result2 = v;
+        }
+        __syncthreads();
+        return (S.result + S.result2) * 0.5;
+    }
+    const int kk2r = k2 - (int)S.below2;
+    __syncthreads();
+    const double v1 = radix_select_in_bin<MODE>(c, nc, b1, kk1, center, S);
+    __syncthreads();
+    const double v2 = (k2 == k1) ? v1 : radix_select_in_bin<MODE>(c, nc, b2, kk2r, center, S);
+    __syncthreads();
+    return (v1 + v2) * 0.5;
+}
+
 struct PeakShared {
     SelShared sel;
+    int topbin;
     int cand[NMS_BLOCK];
     unsigned int ncand;
     int found[NMS_BLOCK];
@@ -277,17 +314,13 @@ __global__ void __launch_bounds__(PK_THREADS) peaks_kernel(const double* __restr
         return;
     }
     // ---- median, MAD, threshold (rtwm/detector.py:83-86)
-    const int k2 = nc >> 1, k1 = (nc - 1) >> 1;
-    const double v2 = select_kth<0>(c, nc, k2, 0.0, S.sel);
+    const double med = median_of<0>(c, nc, 0.0, S.sel, &S.topbin);
     __syncthreads();
-    const double v1 = (k1 == k2) ? v2 : select_kth<0>(c, nc, k1, 0.0, S.sel);
+    const int topbin = S.topbin;
+    const unsigned int topcount = S.sel.topcount;
     __syncthreads();
-    const double med = (v1 + v2) * 0.5;
-    const double w2 = select_kth<1>(c, nc, k2, med, S.sel);
+    const double mad = median_of<1>(c, nc, med, S.sel, nullptr) + 1e-12;
     __syncthreads();
-    const double w1 = (k1 == k2) ? w2 : select_kth<1>(c, nc, k1, med, S.sel);
-    __syncthreads();
-    const double mad = (w1 + w2) * 0.5 + 1e-12;
     double thr = med + (4.5 * 1.4826) * mad;
     thr = thr < 0.95 ? thr : 0.95;
     // ---- NMS in ascending index blocks until 25 peaks are found (rtwm/detector.py:87-97, 108-110)
@@ -329,6 +362,27 @@ __global__ void __launch_bounds__(PK_THREADS) peaks_kernel(const double* __restr
         // ---- top-k fallback, k = min(5, nc): descending value (ties: larger index first)
         fallback = 1;
         const int kf = nc < 5 ? nc : 5;
+        if (topcount <= (unsigned)NMS_BLOCK) {
+            // one pass: everything in the top histogram bins (it holds >= kf values), ranked in shared memory
+            if (tid == 0) S.ncand = 0;
+            __syncthreads();
+            for (int i = tid; i < nc; i += PK_THREADS)
+                if (sel_bin<0>(c[i]) >= topbin) S.cand[atomicAdd(&S.ncand, 1u)] = i;
+            __syncthreads();
+            const int m = (int)S.ncand;
+            for (int q = tid; q < m; q += PK_THREADS) {
+                const int i = S.cand[q];
+                const double v = c[i];
+                int r = 0;
+                for (int j = 0; j < m; ++j) {
+                    const int ij = S.cand[j];
+                    const double w = c[ij];
+                    r += (w > v) || (w == v && ij > i);
+                }
+                if (r < kf) pk[r] = i;
+            }
+            __syncthreads();
+        } else {
         for (int r = 0; r < kf; ++r) {
             double bv = -CUDART_INF; int bi = -1;
             for (int i = tid; i < nc; i += PK_THREADS) {
@@ -351,6 +405,7 @@ __global__ void __launch_bounds__(PK_THREADS) peaks_kernel(const double* __restr
                 pk[r] = bi;
             }
             __syncthreads();
+        }
         }
         np = kf;
     }
