@@ -118,17 +118,23 @@ __global__ void __launch_bounds__(256) ncc_kernel(const double* __restrict__ y, 
     }
     __syncthreads();
     double* cs = corr + (long long)cb * nc;
-    for (int t = threadIdx.x; t < NCC_TILE; t += 256) {
-        const int i = i0 + t;
-        if (i >= nc) break;
-        double e = 0.0, d = 0.0;
-#pragma unroll 9
-        for (int k = 0; k < PRE_L; ++k) {
-            const double v = sy[t + k];
-            e = fma(v, v, e);
-            d = fma(v, c_tpl[band][k], d);
+    // four outputs per thread, interleaved: 8 independent fp64 accumulation chains hide the DFMA latency
+    const int t0 = threadIdx.x;
+    double e[4] = {0.0, 0.0, 0.0, 0.0}, d[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll 3
+    for (int k = 0; k < PRE_L; ++k) {
+        const double w = c_tpl[band][k];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const double v = sy[t0 + 256 * q + k];
+            e[q] = fma(v, v, e[q]);
+            d[q] = fma(v, w, d[q]);
         }
-        cs[i] = d / (sqrt(e) + 1e-12);
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int i = i0 + t0 + 256 * q;
+        if (i < nc) cs[i] = d[q] / (sqrt(e[q]) + 1e-12);
     }
 }
 
