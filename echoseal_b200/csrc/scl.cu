@@ -571,6 +571,35 @@ __global__ void __launch_bounds__(128) scl_hard_kernel(const float* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------
+// compaction of the CRC-passing candidates (the only decoder outputs the host validator needs):
+// (codeword, slot, payload) with slot 0 = hard decision, 1.. = list rank + 1.  Unordered (atomic
+// append); the host sorts by (codeword, slot).  One thread per (codeword, slot).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) scl_collect_hits_kernel(const uint8_t* __restrict__ hard_crc,
+                                                               const uint8_t* __restrict__ path_crc,
+                                                               const uint8_t* __restrict__ hard_payload,
+                                                               const uint8_t* __restrict__ path_payload,
+                                                               long long ncw, int L, int nbytes, int cap,
+                                                               int32_t* __restrict__ counter, int64_t* __restrict__ out_cw,
+                                                               int32_t* __restrict__ out_slot, uint8_t* __restrict__ out_payload)
+{
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int nslot = L + 1;
+    if (g >= ncw * nslot) return;
+    const long long w = g / nslot;
+    const int slot = (int)(g - w * nslot);
+    const bool hit = slot == 0 ? (hard_crc[w] != 0) : (path_crc[w * L + (slot - 1)] != 0);
+    if (!hit) return;
+    const int idx = atomicAdd(counter, 1);
+    if (idx >= cap) return;
+    out_cw[idx] = w;
+    out_slot[idx] = slot;
+    const uint8_t* src = slot == 0 ? hard_payload + w * nbytes : path_payload + (w * L + (slot - 1)) * nbytes;
+    uint8_t* dst = out_payload + (long long)idx * nbytes;
+    for (int b = 0; b < nbytes; ++b) dst[b] = src[b];
+}
+
+// ---------------------------------------------------------------------------------------------
 // encoder (rtwm/fastpolar.py:237-252): one warp per payload, output one byte per code bit
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) polar_encode_kernel(const uint8_t* __restrict__ payload, int n,
@@ -724,6 +753,20 @@ int es_scl_list(const float* llr, const int32_t* index, int ncw, int neg_mode, i
     P.phi_tab = g_phi_tab_dev;
     P.path_payload = path_payload; P.path_crc = path_crc; P.path_metric = path_metric; P.npaths = npaths;
     scl_list_kernel<SCL_S, SCL_W><<<ctas, SCL_W * 32, scl_smem_bytes(), (cudaStream_t)stream>>>(P);
+    ES_CUDA_OK(cudaGetLastError());
+    return ES_OK;
+}
+
+int es_scl_collect_hits(const uint8_t* hard_crc, const uint8_t* path_crc, const uint8_t* hard_payload,
+                        const uint8_t* path_payload, long long ncw, int list_size, int cap,
+                        int32_t* counter, int64_t* out_cw, int32_t* out_slot, uint8_t* out_payload, void* stream)
+{
+    if (!g_code_ready) { set_error("es_scl_collect_hits: call es_polar_set_code first"); return ES_ENOTREADY; }
+    if (ncw <= 0) return ES_OK;
+    const int nbytes = (g_K - 8) >> 3;
+    const long long total = ncw * (list_size + 1);
+    scl_collect_hits_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        hard_crc, path_crc, hard_payload, path_payload, ncw, list_size, nbytes, cap, counter, out_cw, out_slot, out_payload);
     ES_CUDA_OK(cudaGetLastError());
     return ES_OK;
 }

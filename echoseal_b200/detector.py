@@ -52,26 +52,77 @@ def _bank_for(keys):
     return KeyBank(list(uniq)), idx
 
 
+def _pinned_like(t: torch.Tensor) -> torch.Tensor:
+    return torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+
+
+class _Decode:
+    """K5 + K6 for the enumerated items of one sub-batch, split in an enqueue half (no host
+    synchronisation) and a host half (AEAD validation in the reference's order) so that sub-batches
+    can be software-pipelined: the host half of one overlaps the SCL kernel of the next."""
+
+    def __init__(self, bank, key_idx_sub, enum, mf_aligned, list_size, dev):
+        self.bank, self.kidx, self.enum, self.mf, self.L, self.dev = bank, key_idx_sub, enum, mf_aligned, list_size, dev
+        self.I = int(enum["item_peak"].size)
+        self.llr = None
+        self.ev = None
+
+    def enqueue_llr(self):
+        if not self.I:
+            return
+        ip_h = torch.from_numpy(self.enum["item_peak"]).pin_memory()
+        pn_h = torch.from_numpy(self.enum["pn"]).pin_memory()
+        self._keep = (ip_h, pn_h)
+        ip = ip_h.to(self.dev, non_blocking=True)
+        pn = pn_h.to(self.dev, non_blocking=True)
+        self.llr = rx_gpu.llr(self.mf, ip, pn)                      # [2I,1024]: PN variant 0 / 1 per item
+
+    def enqueue_scl(self):
+        if not self.I:
+            return
+        pay_h, crc_h = polar_gpu.hard_decide(self.llr, neg_mode=1)  # 4I codewords: +v0, -v0, +v1, -v1
+        out = polar_gpu.list_decode(self.llr, list_size=self.L, neg_mode=1)
+        # only CRC-passing candidates travel back (slot 0 = hard decision, 1.. = list rank + 1); about one
+        # spurious CRC-8 pass per 28 decodes, so a capacity of one per 4 codewords is generous
+        self.cap = max(65536, self.I)
+        self._dev_out = (pay_h, crc_h, out)
+        cnt, cw, slot, pl = polar_gpu.collect_hits(pay_h, crc_h, out, self.L, self.cap)
+        self.h_cnt, self.h_cw, self.h_slot, self.h_pl = (_pinned_like(t) for t in (cnt, cw, slot, pl))
+        self.h_cnt.copy_(cnt, non_blocking=True)
+        self.h_cw.copy_(cw, non_blocking=True); self.h_slot.copy_(slot, non_blocking=True)
+        self.h_pl.copy_(pl, non_blocking=True)
+        self.ev = torch.cuda.Event()
+        self.ev.record()
+        self.llr = None
+
+    def finish(self, nonce_state):
+        """host: sort the hits by (codeword, slot) and run the validator -> (verdict u8[nb], plaintext u8[nb,27])"""
+        hit_cw = np.zeros(0, np.int64); hit_slot = np.zeros(0, np.int32); hit_pay = np.zeros((0, 55), np.uint8)
+        if self.I:
+            self.ev.synchronize()
+            n = int(self.h_cnt[0])
+            if n > self.cap:                                        # never seen; redo with room for everything
+                pay_h, crc_h, out = self._dev_out
+                cnt, cw, slot, pl = polar_gpu.collect_hits(pay_h, crc_h, out, self.L, n)
+                self.h_cw, self.h_slot, self.h_pl = cw.cpu(), slot.cpu(), pl.cpu()
+            cw = self.h_cw.numpy()[:n]; sl = self.h_slot.numpy()[:n]
+            order = np.argsort(cw * 16 + sl, kind="stable")
+            hit_cw = np.ascontiguousarray(cw[order]); hit_slot = np.ascontiguousarray(sl[order])
+            hit_pay = np.ascontiguousarray(self.h_pl.numpy()[:n][order])
+            self._dev_out = None
+        return self.bank.rx_validate(self.kidx, self.enum, hit_cw, hit_slot, hit_pay, nonce_state)
+
+
 def _decode_phase(bank, key_idx_sub, enum, mf_aligned, list_size, nonce_state, dev):
-    """K5 + K6 for every enumerated item, then the host AEAD validation in the reference's order.
-    Returns (verdict u8[nb], plaintext u8[nb,27])."""
-    I = int(enum["item_peak"].size)
-    hit_cw = np.zeros(0, np.int64); hit_slot = np.zeros(0, np.int32); hit_pay = np.zeros((0, 55), np.uint8)
-    if I:
-        ip = torch.from_numpy(enum["item_peak"]).to(dev)
-        pn = torch.from_numpy(enum["pn"]).to(dev)
-        llr = rx_gpu.llr(mf_aligned, ip, pn)                       # [2I,1024]: variant 0 / 1 per item
-        pay_h, crc_h = polar_gpu.hard_decide(llr, neg_mode=1)      # 4I codewords: +v0, -v0, +v1, -v1
-        out = polar_gpu.list_decode(llr, list_size=list_size, neg_mode=1)
-        # only CRC-passing candidates travel back: (codeword, slot) with slot 0 = hard decision, 1.. = list rank+1
-        flags = torch.cat([crc_h[:, None], out["crc"]], dim=1)
-        idx = torch.nonzero(flags, as_tuple=False)                 # row-major = sorted by (codeword, slot)
-        if idx.numel():
-            allpay = torch.cat([pay_h[:, None, :], out["payload"]], dim=1)
-            hit_pay = allpay[idx[:, 0], idx[:, 1]].cpu().numpy()
-            idx_h = idx.cpu().numpy()
-            hit_cw = idx_h[:, 0].astype(np.int64); hit_slot = idx_h[:, 1].astype(np.int32)
-    return bank.rx_validate(key_idx_sub, enum, hit_cw, hit_slot, hit_pay, nonce_state)
+    """K5 + K6 + host validation, unpipelined (single frames / single bands)."""
+    d = _Decode(bank, key_idx_sub, enum, mf_aligned, list_size, dev)
+    d.enqueue_llr(); d.enqueue_scl()
+    return d.finish(nonce_state)
+
+
+class _Sub:
+    """one sub-batch in flight"""
+    pass
 
 
 def verify_batch(keys, audio, *, fs_target: int = 48_000, list_size: int = 8, mf_taps=None,
@@ -84,7 +135,11 @@ def verify_batch(keys, audio, *, fs_target: int = 48_000, list_size: int = 8, mf
     The per-clip semantics are exactly those of WatermarkDetector.verify (rtwm/detector.py:44-152):
     hop-0 band first, then the other bands in BAND_PLAN order; per band the first 25 peaks in time
     order, header-gated / +-3 / +-200 counter candidates, a 400-try budget, and for every candidate the
-    ladder SCL(llr0), SCL(-llr0), SCL(llr1), SCL(-llr1) with the AEAD validator."""
+    ladder SCL(llr0), SCL(-llr0), SCL(llr1), SCL(-llr1) with the AEAD validator.
+
+    Sub-batches are software-pipelined on one stream: scan(k+1) is queued before the long SCL kernel of
+    sub-batch k, so the host work of k+1 (candidate enumeration, PN) and of k-1 (AEAD validation) runs
+    while the GPU decodes k."""
     if not torch.cuda.is_available():
         raise RuntimeError("echoseal_b200 needs a CUDA device (no CPU fallback)")
     if not (1 <= int(list_size) <= 8):
@@ -111,44 +166,61 @@ def verify_batch(keys, audio, *, fs_target: int = 48_000, list_size: int = 8, mf
                 nonce_state[i, 0] = 1
                 nonce_state[i, 1:] = np.frombuffer(sn, np.uint8)
     dev = torch.device("cuda", torch.cuda.current_device())
-    for s0 in range(0, B, sub_batch):
-        s1 = min(B, s0 + sub_batch)
-        nb = s1 - s0
-        kidx = key_idx[s0:s1]
-        if n < PRE_L:      # rtwm/detector.py:72-73: shorter than the template -> False for every band
-            if details:
-                for i in range(s0, s1):
-                    r = RxResult(); r.verdict = False; r.peaks = np.full((4, PEAK_LIMIT), -1, np.int32)
-                    r.npeaks = np.zeros(4, np.int32); r.stats = np.zeros((4, 4)); r.hdr = np.zeros((4, PEAK_LIMIT, 4), np.float32)
-                    r.attempts = [[] for _ in range(4)]; r.payload = None; r.nonce = None; r.n_scl = 0
-                    results[i] = r
-            continue
+
+    if n < PRE_L:          # rtwm/detector.py:72-73: shorter than the template -> False for every band
+        if details:
+            for i in range(B):
+                r = RxResult(); r.verdict = False; r.peaks = np.full((4, PEAK_LIMIT), -1, np.int32)
+                r.npeaks = np.zeros(4, np.int32); r.stats = np.zeros((4, 4)); r.hdr = np.zeros((4, PEAK_LIMIT, 4), np.float32)
+                r.attempts = [[] for _ in range(4)]; r.payload = None; r.nonce = None; r.n_scl = 0
+                results[i] = r
+            return verdicts, results
+        return verdicts
+
+    def scan(s0):
+        """enqueue K1-K4 for clips [s0, s1) and the asynchronous read-back of peaks / header tuples"""
+        sb = _Sub()
+        sb.s0, sb.s1 = s0, min(B, s0 + sub_batch)
+        sb.kidx = key_idx[sb.s0:sb.s1]
         if is_tensor:
-            x = audio[s0:s1].to(device=dev, dtype=torch.float32).contiguous()
+            x = audio[sb.s0:sb.s1].to(device=dev, dtype=torch.float32).contiguous()
         else:
-            host = torch.from_numpy(np.ascontiguousarray(audio[s0:s1], dtype=np.float32)).pin_memory()
+            host = torch.from_numpy(np.ascontiguousarray(audio[sb.s0:sb.s1], dtype=np.float32)).pin_memory()
+            sb._keep = host
             x = host.to(dev, non_blocking=True)
-        hdr_pn = torch.from_numpy(bank.hdr_pn(kidx)).to(dev)
-        # ---- phase 1: scan (K1-K3) + per-peak front end (K4)
+        hdr_pn = torch.from_numpy(bank.hdr_pn(sb.kidx)).to(dev)
         y = rx_gpu.bandpass(x)
         corr = rx_gpu.ncc(y)
-        pk, npk, st = rx_gpu.peaks(corr)
+        sb.pk, sb.npk, sb.st = rx_gpu.peaks(corr)
         del corr
-        fr = rx_gpu.frames(y, pk, npk, hdr_pn)
+        sb.fr = rx_gpu.frames(y, sb.pk, sb.npk, hdr_pn)
         del y
-        pk_h = pk.cpu().numpy(); npk_h = npk.cpu().numpy(); hdr_h = fr["hdr"].cpu().numpy()
-        # ---- host: candidate counters, 400-try budget, PN bits (native, threaded)
-        enum = bank.rx_enumerate(kidx, n, pk_h, npk_h, hdr_h)
-        # ---- phase 2: despread/LLR (K5), SCL-8 (K6), AEAD validation of CRC-passing candidates
-        ns = np.ascontiguousarray(nonce_state[s0:s1])
-        v, pt = _decode_phase(bank, kidx, enum, fr["mf_aligned"], list_size, ns, dev)
-        nonce_state[s0:s1] = ns
-        verdicts[s0:s1] = v.astype(bool)
+        sb.pk_h, sb.npk_h, sb.hdr_h = _pinned_like(sb.pk), _pinned_like(sb.npk), _pinned_like(sb.fr["hdr"])
+        sb.pk_h.copy_(sb.pk, non_blocking=True); sb.npk_h.copy_(sb.npk, non_blocking=True)
+        sb.hdr_h.copy_(sb.fr["hdr"], non_blocking=True)
+        sb.ev = torch.cuda.Event()
+        sb.ev.record()
+        return sb
+
+    def enumerate_(sb):
+        """host: candidate counters, 400-try budget, PN bits (native, threaded)"""
+        sb.ev.synchronize()
+        sb.enum = bank.rx_enumerate(sb.kidx, n, sb.pk_h.numpy(), sb.npk_h.numpy(), sb.hdr_h.numpy())
+        sb.dec = _Decode(bank, sb.kidx, sb.enum, sb.fr["mf_aligned"], list_size, dev)
+
+    def finish(sb):
+        ns = np.ascontiguousarray(nonce_state[sb.s0:sb.s1])
+        v, pt = sb.dec.finish(ns)
+        nonce_state[sb.s0:sb.s1] = ns
+        verdicts[sb.s0:sb.s1] = v.astype(bool)
         if details:
-            st_h = st.cpu().numpy()
-            for ci in range(nb):
+            pk_h, npk_h, hdr_h = sb.pk_h.numpy(), sb.npk_h.numpy(), sb.hdr_h.numpy()
+            st_h = sb.st.cpu().numpy()
+            enum = sb.enum
+            for ci in range(sb.s1 - sb.s0):
                 r = RxResult()
-                r.verdict = bool(v[ci]); r.peaks = pk_h[ci]; r.npeaks = npk_h[ci]; r.stats = st_h[ci]; r.hdr = hdr_h[ci]
+                r.verdict = bool(v[ci]); r.peaks = pk_h[ci].copy(); r.npeaks = npk_h[ci].copy()
+                r.stats = st_h[ci]; r.hdr = hdr_h[ci].copy()
                 o = int(enum["item_offset"][ci])
                 r.attempts = []
                 for bi in range(4):
@@ -160,7 +232,24 @@ def verify_batch(keys, audio, *, fs_target: int = 48_000, list_size: int = 8, mf
                 r.payload = pt[ci].tobytes() if v[ci] else None
                 r.nonce = ns[ci, 1:].tobytes() if ns[ci, 0] else None
                 r.n_scl = 4 * int(enum["band_count"][ci].sum())
-                results[s0 + ci] = r
+                results[sb.s0 + ci] = r
+        sb.fr = None; sb.dec = None
+
+    starts = list(range(0, B, sub_batch))
+    cur = scan(starts[0])
+    enumerate_(cur)
+    prev = None
+    for k in range(len(starts)):
+        cur.dec.enqueue_llr()
+        nxt = scan(starts[k + 1]) if k + 1 < len(starts) else None     # queued BEFORE the long SCL of `cur`
+        cur.dec.enqueue_scl()
+        if prev is not None:
+            finish(prev)                                               # host, overlaps SCL(cur)
+        if nxt is not None:
+            enumerate_(nxt)                                            # host, overlaps SCL(cur)
+        prev, cur = cur, nxt
+    finish(prev)
+
     if session_nonces is not None:
         for i in range(B):
             session_nonces[i] = nonce_state[i, 1:].tobytes() if nonce_state[i, 0] else None

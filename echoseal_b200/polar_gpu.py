@@ -102,3 +102,20 @@ def encode(payload: torch.Tensor, K: int = 448, want_bits: bool = True, want_wor
         N.check(N.lib().es_polar_encode(N.ptr(payload), C.c_int(n), N.ptr(bits), N.ptr(words), N.stream_ptr()),
                 "es_polar_encode")
     return bits, words
+
+
+def collect_hits(pay_h, crc_h, out, list_size: int, cap: int):
+    """Compact the CRC-passing candidates on the device (K6 epilogue).  Returns device tensors
+    (counter i32[1], cw i64[cap], slot i32[cap], payload u8[cap,nb]); entries are unordered."""
+    N.require_cuda(pay_h, crc_h, out["payload"], out["crc"])
+    dev = pay_h.device
+    ncw, nb = pay_h.shape
+    counter = torch.zeros(1, dtype=torch.int32, device=dev)
+    cw = torch.empty(cap, dtype=torch.int64, device=dev)
+    slot = torch.empty(cap, dtype=torch.int32, device=dev)
+    pl = torch.empty((cap, nb), dtype=torch.uint8, device=dev)
+    with N.timed("collect_hits"):
+        N.check(N.lib().es_scl_collect_hits(N.ptr(crc_h), N.ptr(out["crc"]), N.ptr(pay_h), N.ptr(out["payload"]),
+                                            C.c_longlong(ncw), C.c_int(list_size), C.c_int(cap), N.ptr(counter),
+                                            N.ptr(cw), N.ptr(slot), N.ptr(pl), N.stream_ptr()), "es_scl_collect_hits")
+    return counter, cw, slot, pl

@@ -43,6 +43,12 @@ int es_scl_list(const float* llr, const int32_t* index, int ncw, int neg_mode, i
                 void* scratch, size_t scratch_bytes,
                 uint8_t* path_payload /*[ncw_total][L][(K-8)/8]*/, uint8_t* path_crc /*[ncw_total][L]*/,
                 double* path_metric /*[ncw_total][L]*/, int32_t* npaths /*[ncw_total]*/, void* stream);
+/* compaction of the CRC-passing candidates (hard decision = slot 0, list rank r = slot r+1): the inputs of the
+ * validator callback of PolarCode.decode (rtwm/fastpolar.py:269-276, 335-349). Unordered; *counter may exceed cap. */
+int es_scl_collect_hits(const uint8_t* hard_crc, const uint8_t* path_crc, const uint8_t* hard_payload,
+                        const uint8_t* path_payload, long long ncw, int list_size, int cap,
+                        int32_t* counter, int64_t* out_cw /*[cap]*/, int32_t* out_slot /*[cap]*/,
+                        uint8_t* out_payload /*[cap][(K-8)/8]*/, void* stream);
 /* PolarCode.encode / polar_fast.encode (rtwm/fastpolar.py:237-252, rtwm/polar_fast.py:26-53) */
 int es_polar_encode(const uint8_t* payload /*[n][(K-8)/8]*/, int n, uint8_t* cw_bits /*[n][1024] or NULL*/,
                     uint32_t* cw_words /*[n][32] or NULL*/, void* stream);
