@@ -713,6 +713,34 @@ __global__ void __launch_bounds__(LLR_WARPS * 32) llr_kernel(const float* __rest
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// K9: polyphase resampler = scipy.signal.resample_poly(x, up, down) (rtwm/utils.py:58-66), one thread per
+// output sample.  out[m] = sum_j hp[phase + j*up] * x[i_hi - j],  t = (m + n_pre_remove)*down, i_hi = t / up,
+// phase = t % up, with hp the zero-pre-padded Kaiser(5) low-pass of 2*10*max(up,down)+1 taps scaled by `up`
+// (designed on the host, passed in polyphase order taps[phase][j]).  fp64 accumulation, float32 output.
+// ---------------------------------------------------------------------------------------------
+template <typename TIN>
+__global__ void __launch_bounds__(256) resample_kernel(const TIN* __restrict__ x, long long n_in, long long x_stride,
+                                                       int up, int down, const double* __restrict__ taps, int J,
+                                                       long long n_pre_remove, long long n_out,
+                                                       float* __restrict__ y)
+{
+    const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n_out) return;
+    const TIN* xs = x + (long long)blockIdx.y * x_stride;
+    const long long t = (m + n_pre_remove) * down;
+    const long long i_hi = t / up;
+    const int phase = (int)(t - i_hi * up);
+    const double* h = taps + (long long)phase * J;
+    double acc = 0.0;
+    for (int j = 0; j < J; ++j) {
+        const long long i = i_hi - j;
+        if (i < 0) break;
+        if (i < n_in) acc = fma(__ldg(h + j), (double)xs[i], acc);
+    }
+    y[(long long)blockIdx.y * n_out + m] = (float)acc;
+}
+
 }  // namespace es
 
 using namespace es;
@@ -785,6 +813,21 @@ int es_rx_llr(const float* mf_aligned, const int32_t* item_peak, const uint8_t* 
     if (nitems <= 0) return ES_OK;
     const int nwork = nitems * 2;
     llr_kernel<<<(nwork + LLR_WARPS - 1) / LLR_WARPS, LLR_WARPS * 32, 0, (cudaStream_t)stream>>>(mf_aligned, item_peak, pn_packed, nwork, llr);
+    ES_CUDA_OK(cudaGetLastError());
+    return ES_OK;
+}
+
+int es_rx_resample(const void* x, int x_is_f64, int nclips, long long n_in, long long x_stride, int up, int down,
+                   const double* taps /*[up][J] device*/, int J, long long n_pre_remove, long long n_out,
+                   float* y /*[clips][n_out]*/, void* stream)
+{
+    if (nclips <= 0 || n_out <= 0) return ES_OK;
+    if (up < 1 || down < 1 || J < 1) { set_error("es_rx_resample: bad up/down/J"); return ES_EINVAL; }
+    dim3 grid((unsigned)((n_out + 255) / 256), nclips);
+    if (x_is_f64)
+        resample_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>((const double*)x, n_in, x_stride, up, down, taps, J, n_pre_remove, n_out, y);
+    else
+        resample_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, n_in, x_stride, up, down, taps, J, n_pre_remove, n_out, y);
     ES_CUDA_OK(cudaGetLastError());
     return ES_OK;
 }

@@ -293,12 +293,17 @@ class WatermarkDetector:
     def _taps(self):
         return [np.asarray(self._matched_filter_taps(b), np.float32) for b in BAND_PLAN]
 
-    def _resample(self, audio: np.ndarray, fs_in: int) -> np.ndarray:
+    def _resample(self, audio: np.ndarray, fs_in: int):
+        """resample_to(fs_target, audio, fs_in) (rtwm/utils.py:58-66) on the device (K9)."""
         if fs_in == self.fs_target:
             return audio
-        from scipy.signal import resample_poly     # host path for now; the device resampler is §8f-2 ("next")
-        up, down = resample_ratio(self.fs_target, fs_in)
-        return resample_poly(audio, up, down)
+        a = np.asarray(audio)
+        if a.dtype != np.float64:
+            a = a.astype(np.float32, copy=False)
+        if a.size == 0:
+            return a.astype(np.float32)
+        x = torch.from_numpy(np.ascontiguousarray(a).reshape(1, -1)).to(self._dev())
+        return rx_gpu.resample(x, fs_in, self.fs_target)[0]
 
     def _dev(self):
         if not torch.cuda.is_available():
@@ -308,7 +313,8 @@ class WatermarkDetector:
     # ------------------------------------------------------------------ API
     def verify(self, audio: np.ndarray, fs_in: int) -> bool:
         """rtwm/detector.py:44-53"""
-        signal = np.asarray(self._resample(np.asarray(audio), fs_in), dtype=np.float32).reshape(1, -1)
+        signal = self._resample(np.asarray(audio), fs_in)
+        signal = signal.reshape(1, -1) if isinstance(signal, torch.Tensor) else np.asarray(signal, dtype=np.float32).reshape(1, -1)
         nonces = [self.session_nonce]
         v, res = verify_batch(None, signal, fs_target=self.fs_target, list_size=self._list_size,
                               mf_taps=self._taps(), session_nonces=nonces, details=True,
@@ -320,7 +326,9 @@ class WatermarkDetector:
     def verify_batch(self, audio, fs_in: int | None = None) -> np.ndarray:
         """Additive API: B clips with this detector's key; no session-nonce latch across clips."""
         if fs_in is not None and fs_in != self.fs_target:
-            audio = np.stack([self._resample(a, fs_in) for a in np.asarray(audio)])
+            a = np.asarray(audio)
+            a = a if a.dtype == np.float64 else a.astype(np.float32, copy=False)
+            audio = rx_gpu.resample(torch.from_numpy(np.ascontiguousarray(a)).to(self._dev()), fs_in, self.fs_target)
         B = int(audio.shape[0])
         return verify_batch(None, audio, fs_target=self.fs_target, list_size=self._list_size, mf_taps=self._taps(),
                             bank=self._bank, key_idx=np.zeros(B, np.int32))

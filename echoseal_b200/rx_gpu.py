@@ -135,3 +135,54 @@ def llr(mf_aligned: torch.Tensor, item_peak: torch.Tensor, pn_packed: torch.Tens
             N.check(N.lib().es_rx_llr(N.ptr(mf_aligned), N.ptr(item_peak), N.ptr(pn_packed), C.c_int(I), N.ptr(out),
                                       N.stream_ptr()), "es_rx_llr")
     return out
+
+
+_resample_cache = {}
+
+
+def resample_design(up: int, down: int, f64: bool):
+    """Host constants of scipy.signal.resample_poly(x, up, down) (rtwm/utils.py:58-66): the zero-pre-padded
+    Kaiser(5.0) low-pass scaled by `up`, in polyphase order [up][J], and the number of leading outputs to drop."""
+    from scipy.signal import firwin
+    max_rate = max(up, down)
+    half_len = 10 * max_rate
+    h = firwin(2 * half_len + 1, 1.0 / max_rate, window=("kaiser", 5.0))
+    if not f64:
+        h = h.astype(np.float32)            # scipy matches the dtype of x
+    h = h * up
+    n_pre_pad = down - half_len % down
+    n_pre_remove = (half_len + n_pre_pad) // down
+    hp = np.concatenate([np.zeros(n_pre_pad, h.dtype), h]).astype(np.float64)
+    J = -(-hp.size // up)
+    poly = np.zeros((up, J), np.float64)
+    for ph in range(up):
+        seg = hp[ph::up]
+        poly[ph, :seg.size] = seg
+    return poly, J, n_pre_remove
+
+
+def resample(x: torch.Tensor, fs_in: int, fs_out: int) -> torch.Tensor:
+    """K9: x float32/float64 [B, n_in] on the GPU -> float32 [B, n_out] at fs_out."""
+    import math
+    N.require_cuda(x)
+    if x.dtype not in (torch.float32, torch.float64) or x.dim() != 2:
+        raise ValueError("x must be float32/float64 [B, n]")
+    g = math.gcd(fs_in, fs_out)
+    up, down = fs_out // g, fs_in // g
+    if up == down == 1:
+        return x.to(torch.float32)
+    f64 = x.dtype == torch.float64
+    key = (up, down, f64, x.device.index)
+    if key not in _resample_cache:
+        poly, J, nrem = resample_design(up, down, f64)
+        _resample_cache[key] = (torch.from_numpy(poly).to(x.device), J, nrem)
+    taps, J, nrem = _resample_cache[key]
+    B, n_in = x.shape
+    n_out = n_in * up
+    n_out = n_out // down + (1 if n_out % down else 0)
+    y = torch.empty((B, n_out), dtype=torch.float32, device=x.device)
+    with N.timed("resample"):
+        N.check(N.lib().es_rx_resample(N.ptr(x), C.c_int(1 if f64 else 0), C.c_int(B), C.c_longlong(n_in),
+                                       C.c_longlong(x.stride(0)), C.c_int(up), C.c_int(down), N.ptr(taps), C.c_int(J),
+                                       C.c_longlong(nrem), C.c_longlong(n_out), N.ptr(y), N.stream_ptr()), "es_rx_resample")
+    return y

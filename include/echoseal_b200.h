@@ -76,6 +76,11 @@ int es_rx_frames(const double* y, int nclips, int n, const int32_t* peaks, const
 int es_rx_llr(const float* mf_aligned, const int32_t* item_peak /*[items]*/, const uint8_t* pn_packed /*[items][152]*/,
               int nitems, float* llr /*[2*items][1024]*/, void* stream);
 
+/* K9: resample_to / scipy.signal.resample_poly(x, up, down) (rtwm/utils.py:58-66): taps = host-designed Kaiser(5)
+ * low-pass in polyphase order [up][J] (device pointer), fp64 accumulation, float32 out */
+int es_rx_resample(const void* x, int x_is_f64, int nclips, long long n_in, long long x_stride, int up, int down,
+                   const double* taps, int J, long long n_pre_remove, long long n_out, float* y, void* stream);
+
 /* ---------------- TX (rtwm/embedder.py:44-151) ----------------------------------------------------- */
 int es_tx_set_filters(const double* bp_b /*[4][9]*/, const double* bp_a /*[4][9]*/, const uint8_t* preamble_bits /*[63]*/);
 /* K7: _make_frame_chips (rtwm/embedder.py:78-151) for a batch of frames */

@@ -187,3 +187,26 @@ def test_verdicts_match_unmodified_reference(env):
     for n, a in zip(names, audio):
         rx = detector.WatermarkDetector(clips[n][1], list_size=8)
         assert rx.verify(a, 48000) is ref[n]["verdict"], n
+
+
+def test_resampler_matches_oracle_and_scipy(env):
+    """K9 (config 3's 44.1 kHz path): device polyphase resampler vs the oracle restatement of
+    scipy.signal.resample_poly (rtwm/utils.py:58-66)."""
+    torch, rx_gpu, detector, clips, taps = env
+    from oracle import resample_oracle as ro
+    rng = np.random.default_rng(4)
+    for n_in, fs in ((44100, 44100), (5000, 32000), (9600, 96000), (7, 44100)):
+        for dt in (np.float32, np.float64):
+            x = rng.standard_normal((2, n_in)).astype(dt)
+            got = rx_gpu.resample(torch.from_numpy(x).cuda(), fs, 48000).cpu().numpy()
+            for r in range(2):
+                ref = ro.resample_poly(x[r], 48000, fs).astype(np.float32)
+                assert got[r].shape == ref.shape
+                assert np.abs(got[r] - ref).max() <= 2e-6 * max(1.0, np.abs(ref).max())
+    # through the drop-in: a 44.1 kHz clip goes through verify() (verdict False; must not raise)
+    audio, key = clips["short_1s"]
+    from scipy.signal import resample_poly
+    a441 = resample_poly(audio, 147, 160).astype(np.float32)
+    rx = detector.WatermarkDetector(key)
+    assert rx.verify(a441, 44100) is False
+    assert rx.last_result.peaks.shape == (4, 25)
