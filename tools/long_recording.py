@@ -1,0 +1,46 @@
+"""configs[2]: one 1-hour 44.1 kHz synthetic recording with +-5 % time-scale and -15 dB SNR noise through
+WatermarkDetector.verify (full +-200 counter fallback search, 400-try budget per band).  Prints one JSON line."""
+import json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import bench
+from echoseal_b200 import rx_gpu, embedder, detector, _native as N
+
+def main():
+    hours = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
+    scale = float(sys.argv[2]) if len(sys.argv) > 2 else 1.05
+    dev = torch.device("cuda", 0)
+    n48 = int(hours * 3600 * 48000)
+    key = bench.bench_key(2024)
+    g = torch.Generator(device=dev).manual_seed(2024)
+    t0 = time.perf_counter()
+    host = 0.05 * torch.randn((1, n48), device=dev, generator=g)
+    tx = embedder.EmbedderBank([key])
+    wm = tx.process(host)
+    del host
+    num, den = (21, 20) if scale > 1 else (19, 20)
+    stretched = rx_gpu.resample(wm, den, num)                      # time-scale by num/den
+    del wm
+    a441 = rx_gpu.resample(stretched, 48000, 44100)
+    del stretched
+    p = float((a441.double() ** 2).mean())
+    a441 = a441 + torch.randn(a441.shape, device=dev, generator=g) * np.sqrt(p * 10 ** 1.5)   # -15 dB SNR
+    audio = a441[0].cpu().numpy()
+    del a441
+    torch.cuda.synchronize()
+    t_gen = time.perf_counter() - t0
+    rx = detector.WatermarkDetector(key, list_size=8)
+    N.KERNEL_TIMES = {}
+    torch.cuda.synchronize(); t1 = time.perf_counter()
+    ok = rx.verify(audio, 44100)
+    torch.cuda.synchronize(); dt = time.perf_counter() - t1
+    kt = {k: float(sum(a.elapsed_time(b) for a, b in v)) for k, v in N.KERNEL_TIMES.items()}
+    r = rx.last_result
+    print(json.dumps({"workload": f"configs[2]: {hours} h 44.1 kHz recording, time-scale x{num}/{den}, -15 dB SNR",
+                      "samples_44k1": int(audio.size), "verdict": bool(ok), "verify_seconds": dt,
+                      "audio_seconds_per_second": audio.size / 44100 / dt, "scl_decodes": int(r.n_scl),
+                      "attempts_per_band": [len(a) for a in r.attempts], "npeaks": [int(v) for v in r.npeaks],
+                      "thr": [float(v) for v in r.stats[:, 2]], "kernel_ms": kt, "generate_seconds": t_gen}))
+
+if __name__ == "__main__":
+    main()
