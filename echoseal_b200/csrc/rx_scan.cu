@@ -422,6 +422,268 @@ __global__ void __launch_bounds__(PK_THREADS) peaks_kernel(const double* __restr
 }
 
 // ---------------------------------------------------------------------------------------------
+// K3, long-recording form (one long recording needs GLOBAL order statistics).  Same results
+// as peaks_kernel, but every streaming pass over corr is spread over many CTAs and the tiny decisions
+// in between run in one CTA per (clip, band).  Two-level monotone histogram (2048 x 2048 bins), gather of
+// the sub-bin(s) holding the two middle ranks, exact rank count; NMS per 4096-index block with the first
+// 25 peaks collected in index order afterwards.  Used when the correlation is longer than K3_LONG_MIN.
+// ---------------------------------------------------------------------------------------------
+constexpr int K3_LONG_MIN = 1 << 21;
+constexpr int K3_CAP = 32768;              // gathered values per (clip, band)
+constexpr int K3_CHUNK = 1 << 18;          // elements per CTA in the streaming passes
+
+struct K3Meta {
+    int b[2]; unsigned int below[2];       // level-1 bins of ranks k1, k2 and counts below them
+    int sb[2]; unsigned int sbelow[2];     // level-2 sub-bins and counts below (inside the bin)
+    unsigned int cnt;                      // gather counter of the current selection (reset by locate<1>)
+    int topbin; unsigned int topcount;     // smallest bin with >= min(5,nc) values at or above it (corr histogram)
+    unsigned int topcnt;                   // indices gathered from those bins
+    int overflow;
+    double med, mad, thr;
+};
+
+template <int MODE> __device__ __forceinline__ double k3_scaled(double val)
+{
+    return MODE ? val * 1024.0 : (val + 1.0) * 1024.0;
+}
+template <int MODE> __device__ __forceinline__ int k3_sub(double val, int bin)
+{
+    const double f = (k3_scaled<MODE>(val) - (double)bin) * 2048.0;
+    return (f >= 2047.0) ? 2047 : ((f <= 0.0) ? 0 : (int)f);
+}
+
+// LEVEL 1: hist[cb][2048] over all values.  LEVEL 2: hist2[cb][2][2048] over the values of bins b[0] / b[1].
+template <int MODE, int LEVEL>
+__global__ void __launch_bounds__(1024) k3_hist_kernel(const double* __restrict__ corr, int nc, const K3Meta* __restrict__ meta,
+                                                       unsigned int* __restrict__ hist)
+{
+    __shared__ unsigned int sh[2][2048];
+    const int cb = blockIdx.y;
+    const double* c = corr + (long long)cb * nc;
+    const K3Meta M = meta[cb];
+    const double center = MODE ? M.med : 0.0;
+    for (int b = threadIdx.x; b < 2048; b += 1024) { sh[0][b] = 0; sh[1][b] = 0; }
+    __syncthreads();
+    const long long i0 = (long long)blockIdx.x * K3_CHUNK;
+    const long long i1 = min((long long)nc, i0 + K3_CHUNK);
+    for (long long i = i0 + threadIdx.x; i < i1; i += 1024) {
+        const double v = sel_value<MODE>(c[i], center);
+        const int bin = sel_bin<MODE>(v);
+        if (LEVEL == 1) atomicAdd(&sh[0][bin], 1u);
+        else {
+            if (bin == M.b[0]) atomicAdd(&sh[0][k3_sub<MODE>(v, bin)], 1u);
+            else if (bin == M.b[1]) atomicAdd(&sh[1][k3_sub<MODE>(v, bin)], 1u);
+        }
+    }
+    __syncthreads();
+    unsigned int* out = hist + (long long)cb * (LEVEL == 1 ? 2048 : 4096);
+    for (int b = threadIdx.x; b < 2048; b += 1024) {
+        if (sh[0][b]) atomicAdd(&out[b], sh[0][b]);
+        if (LEVEL == 2 && sh[1][b]) atomicAdd(&out[2048 + b], sh[1][b]);
+    }
+}
+
+// one warp per (clip, band): locate the bins (LEVEL 1) or sub-bins (LEVEL 2) of ranks k1 <= k2
+template <int LEVEL>
+__global__ void k3_locate_kernel(const unsigned int* __restrict__ hist, int nc, K3Meta* __restrict__ meta, int want_top)
+{
+    const int cb = blockIdx.x;
+    if (threadIdx.x != 0) return;
+    K3Meta& M = meta[cb];
+    const int k2 = nc >> 1, k1 = (nc - 1) >> 1;
+    if (LEVEL == 1) {
+        const unsigned int* h = hist + (long long)cb * 2048;
+        unsigned int acc = 0; int b = 0;
+        for (; b < 2048; ++b) { if (acc + h[b] > (unsigned)k1) break; acc += h[b]; }
+        M.b[0] = b; M.below[0] = acc;
+        for (; b < 2048; ++b) { if (acc + h[b] > (unsigned)k2) break; acc += h[b]; }
+        M.b[1] = b; M.below[1] = acc;
+        if (want_top) {
+            const unsigned int want = nc < 5 ? (unsigned)nc : 5u;
+            unsigned int t = 0; int tb = 2047;
+            for (; tb > 0; --tb) { t += h[tb]; if (t >= want) break; }
+            if (tb == 0) t += h[0];
+            M.topbin = tb; M.topcount = t;
+        }
+        M.cnt = 0; M.overflow = 0;
+    } else {
+        for (int q = 0; q < 2; ++q) {
+            // when both ranks share a bin the second half of hist2 is unused: both look in half 0
+            const int half = (q == 1 && M.b[1] != M.b[0]) ? 1 : 0;
+            const unsigned int* h = hist + (long long)cb * 4096 + half * 2048;
+            const int kk = (q ? k2 : k1) - (int)M.below[half ? 1 : 0];
+            unsigned int acc = 0; int b = 0;
+            for (; b < 2048; ++b) { if (acc + h[b] > (unsigned)kk) break; acc += h[b]; }
+            M.sb[q] = b; M.sbelow[q] = acc;
+        }
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(1024) k3_gather_kernel(const double* __restrict__ corr, int nc, K3Meta* __restrict__ meta,
+                                                         double* __restrict__ buf)
+{
+    const int cb = blockIdx.y;
+    const double* c = corr + (long long)cb * nc;
+    K3Meta& M = meta[cb];
+    const int b0 = M.b[0], b1 = M.b[1], s0 = M.sb[0], s1 = M.sb[1];
+    const double center = MODE ? M.med : 0.0;
+    double* out = buf + (long long)cb * K3_CAP;
+    const long long i0 = (long long)blockIdx.x * K3_CHUNK;
+    const long long i1 = min((long long)nc, i0 + K3_CHUNK);
+    for (long long i = i0 + threadIdx.x; i < i1; i += 1024) {
+        const double v = sel_value<MODE>(c[i], center);
+        const int bin = sel_bin<MODE>(v);
+        if (bin != b0 && bin != b1) continue;
+        const int sub = k3_sub<MODE>(v, bin);
+        if ((bin == b0 && sub == s0) || (bin == b1 && sub == s1)) {
+            const unsigned int q = atomicAdd(&M.cnt, 1u);
+            if (q < (unsigned)K3_CAP) out[q] = v; else M.overflow = 1;
+        }
+    }
+}
+
+// exact ranks inside the gathered sub-bin(s) -> median (MODE 0) or MAD + threshold (MODE 1)
+template <int MODE>
+__global__ void __launch_bounds__(1024) k3_finish_kernel(const double* __restrict__ buf, int nc, K3Meta* __restrict__ meta)
+{
+    __shared__ double res[2];
+    const int cb = blockIdx.x;
+    K3Meta& M = meta[cb];
+    const double* v = buf + (long long)cb * K3_CAP;
+    const int m = (int)min(M.cnt, (unsigned)K3_CAP);
+    const int k2 = nc >> 1, k1 = (nc - 1) >> 1;
+    // ranks inside the union of the gathered sub-bins (contiguous in rank, see median_of)
+    const int base = (int)M.below[0] + (int)M.sbelow[0];
+    const int kk1 = k1 - base, kk2 = k2 - base;
+    for (int i = threadIdx.x; i < m; i += 1024) {
+        const double x = v[i];
+        int less = 0, eq = 0;
+        for (int j = 0; j < m; ++j) { const double w = v[j]; less += (w < x); eq += (w == x); }
+        if (less <= kk1 && kk1 < less + eq) res[0] = x;
+        if (less <= kk2 && kk2 < less + eq) res[1] = x;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const double md = (res[0] + res[1]) * 0.5;
+        if (MODE == 0) M.med = md;
+        else {
+            M.mad = md + 1e-12;
+            double thr = M.med + (4.5 * 1.4826) * M.mad;
+            M.thr = thr < 0.95 ? thr : 0.95;
+        }
+    }
+}
+
+// NMS per 4096-index block: up to 25 peaks of the block in index order + their count
+__global__ void __launch_bounds__(1024) k3_nms_kernel(const double* __restrict__ corr, int nc, const K3Meta* __restrict__ meta,
+                                                      int nblk, int32_t* __restrict__ blk_peaks, int32_t* __restrict__ blk_count)
+{
+    __shared__ int cand[NMS_BLOCK];
+    __shared__ int found[NMS_BLOCK];
+    __shared__ unsigned int ncand, nfound;
+    const int cb = blockIdx.y, blk = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double* c = corr + (long long)cb * nc;
+    const double thr = meta[cb].thr;
+    if (tid == 0) { ncand = 0; nfound = 0; }
+    __syncthreads();
+    const int blk0 = blk * NMS_BLOCK;
+    for (int i = blk0 + tid; i < min(nc, blk0 + NMS_BLOCK); i += 1024)
+        if (c[i] >= thr) cand[atomicAdd(&ncand, 1u)] = i;
+    __syncthreads();
+    const int nca = (int)ncand;
+    for (int q = warp; q < nca; q += 32) {
+        const int i = cand[q];
+        const double v = c[i];
+        const int lo = max(0, i - NMS_HALF), hi = min(nc, i + NMS_HALF + 1);
+        bool bigger = false;
+        for (int j = lo + lane; j < hi; j += 32) bigger |= (c[j] > v);
+        if (!__any_sync(0xffffffffu, bigger) && lane == 0) found[atomicAdd(&nfound, 1u)] = i;
+    }
+    __syncthreads();
+    const int nf = (int)nfound;
+    int32_t* out = blk_peaks + ((long long)cb * nblk + blk) * PEAK_LIMIT;
+    for (int q = tid; q < nf; q += 1024) {
+        const int i = found[q];
+        int r = 0;
+        for (int j = 0; j < nf; ++j) r += (found[j] < i);
+        if (r < PEAK_LIMIT) out[r] = i;
+    }
+    if (tid == 0) blk_count[(long long)cb * nblk + blk] = nf;
+}
+
+// first 25 peaks in index order; top-5 fallback from the top histogram bins (gathered by k3_top_kernel)
+__global__ void __launch_bounds__(1024) k3_collect_kernel(const double* __restrict__ corr, int nc, K3Meta* __restrict__ meta, int nblk,
+                                                          const int32_t* __restrict__ blk_peaks, const int32_t* __restrict__ blk_count,
+                                                          const int32_t* __restrict__ top_idx,
+                                                          int32_t* __restrict__ peaks, int32_t* __restrict__ npeaks, double* __restrict__ stats)
+{
+    const int cb = blockIdx.x, tid = threadIdx.x;
+    const double* c = corr + (long long)cb * nc;
+    K3Meta& M = meta[cb];
+    int32_t* pk = peaks + (long long)cb * PEAK_LIMIT;
+    __shared__ int np_s;
+    if (tid == 0) {
+        int np = 0;
+        for (int t = 0; t < PEAK_LIMIT; ++t) pk[t] = -1;
+        for (int blk = 0; blk < nblk && np < PEAK_LIMIT; ++blk) {
+            const int nf = blk_count[(long long)cb * nblk + blk];
+            const int32_t* src = blk_peaks + ((long long)cb * nblk + blk) * PEAK_LIMIT;
+            for (int q = 0; q < nf && q < PEAK_LIMIT && np < PEAK_LIMIT; ++q) pk[np++] = src[q];
+            if (nf > PEAK_LIMIT) np = PEAK_LIMIT;   // more than 25 peaks inside one block: the first 25 are all there
+        }
+        np_s = np;
+    }
+    __syncthreads();
+    int np = np_s, fallback = 0;
+    if (np == 0) {
+        fallback = 1;
+        const int kf = nc < 5 ? nc : 5;
+        const int m = (int)min(M.topcnt, (unsigned)K3_CAP);    // filled by k3_top_kernel
+        const int32_t* ti = top_idx + (long long)cb * K3_CAP;
+        for (int q = tid; q < m; q += 1024) {
+            const int i = ti[q];
+            const double v = c[i];
+            int r = 0;
+            for (int j = 0; j < m; ++j) { const int ij = ti[j]; const double w = c[ij]; r += (w > v) || (w == v && ij > i); }
+            if (r < kf) pk[r] = i;
+        }
+        np = kf;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        npeaks[cb] = np;
+        stats[cb * 4 + 0] = M.med; stats[cb * 4 + 1] = M.mad; stats[cb * 4 + 2] = M.thr; stats[cb * 4 + 3] = (double)fallback;
+    }
+}
+
+// indices of all values in bins >= topbin (the top-5 live there)
+__global__ void __launch_bounds__(1024) k3_top_kernel(const double* __restrict__ corr, int nc, K3Meta* __restrict__ meta,
+                                                      int32_t* __restrict__ top_idx)
+{
+    const int cb = blockIdx.y;
+    const double* c = corr + (long long)cb * nc;
+    K3Meta& M = meta[cb];
+    const int topbin = M.topbin;
+    int32_t* out = top_idx + (long long)cb * K3_CAP;
+    const long long i0 = (long long)blockIdx.x * K3_CHUNK;
+    const long long i1 = min((long long)nc, i0 + K3_CHUNK);
+    for (long long i = i0 + threadIdx.x; i < i1; i += 1024) {
+        if (sel_bin<0>(c[i]) >= topbin) {
+            const unsigned int q = atomicAdd(&M.topcnt, 1u);
+            if (q < (unsigned)K3_CAP) out[q] = (int32_t)i; else M.overflow = 1;
+        }
+    }
+}
+
+__global__ void k3_flag_kernel(const K3Meta* meta, int ncb, int32_t* overflow)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < ncb && meta[i].overflow) atomicOr(overflow, 1);
+}
+
+// ---------------------------------------------------------------------------------------------
 // K4: per-peak front end: header decode + matched filter / shift search of the payload
 // ---------------------------------------------------------------------------------------------
 constexpr int FR_THREADS = 256;
@@ -792,6 +1054,62 @@ int es_rx_peaks(const double* corr, int nclips, int nc, int32_t* peaks, int32_t*
         configured = 1;
     }
     peaks_kernel<<<nclips * NBANDS, PK_THREADS, sizeof(PeakShared), (cudaStream_t)stream>>>(corr, nc, peaks, npeaks, stats);
+    ES_CUDA_OK(cudaGetLastError());
+    return ES_OK;
+}
+
+size_t es_rx_peaks_long_scratch_bytes(int nclips, int nc)
+{
+    const size_t ncb = (size_t)nclips * NBANDS;
+    const size_t nblk = ((size_t)nc + NMS_BLOCK - 1) / NMS_BLOCK;
+    return ncb * (sizeof(K3Meta) + 2048 * 4 + 4096 * 4 + (size_t)K3_CAP * 8 + (size_t)K3_CAP * 4 + nblk * (PEAK_LIMIT + 1) * 4) + 256;
+}
+
+// long-recording form of es_rx_peaks (same outputs).  *overflow_dev (int32, device) is set non-zero when a gather
+// buffer overflowed (degenerate data): the caller then falls back to es_rx_peaks.
+int es_rx_peaks_long(const double* corr, int nclips, int nc, void* scratch, size_t scratch_bytes,
+                     int32_t* peaks, int32_t* npeaks, double* stats, int32_t* overflow_dev, void* stream)
+{
+    if (nclips <= 0 || nc <= 0) return ES_OK;
+    if (!scratch || scratch_bytes < es_rx_peaks_long_scratch_bytes(nclips, nc)) { set_error("es_rx_peaks_long: scratch too small"); return ES_EINVAL; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int ncb = nclips * NBANDS;
+    const int nblk = (nc + NMS_BLOCK - 1) / NMS_BLOCK;
+    unsigned char* p = (unsigned char*)scratch;
+    K3Meta* meta = (K3Meta*)p; p += ((size_t)ncb * sizeof(K3Meta) + 255) / 256 * 256;
+    unsigned int* hist1 = (unsigned int*)p; p += (size_t)ncb * 2048 * 4;
+    unsigned int* hist2 = (unsigned int*)p; p += (size_t)ncb * 4096 * 4;
+    double* buf = (double*)p; p += (size_t)ncb * K3_CAP * 8;
+    int32_t* top_idx = (int32_t*)p; p += (size_t)ncb * K3_CAP * 4;
+    int32_t* blk_peaks = (int32_t*)p; p += (size_t)ncb * nblk * PEAK_LIMIT * 4;
+    int32_t* blk_count = (int32_t*)p;
+    ES_CUDA_OK(cudaMemsetAsync(meta, 0, (size_t)ncb * sizeof(K3Meta), st));
+    ES_CUDA_OK(cudaMemsetAsync(overflow_dev, 0, sizeof(int32_t), st));
+    dim3 grid((unsigned)(((long long)nc + K3_CHUNK - 1) / K3_CHUNK), ncb);
+    // ---- median of corr (rtwm/detector.py:83)
+    ES_CUDA_OK(cudaMemsetAsync(hist1, 0, (size_t)ncb * 2048 * 4, st));
+    k3_hist_kernel<0, 1><<<grid, 1024, 0, st>>>(corr, nc, meta, hist1);
+    k3_locate_kernel<1><<<ncb, 32, 0, st>>>(hist1, nc, meta, 1);
+    ES_CUDA_OK(cudaMemsetAsync(hist2, 0, (size_t)ncb * 4096 * 4, st));
+    k3_hist_kernel<0, 2><<<grid, 1024, 0, st>>>(corr, nc, meta, hist2);
+    k3_locate_kernel<2><<<ncb, 32, 0, st>>>(hist2, nc, meta, 0);
+    k3_gather_kernel<0><<<grid, 1024, 0, st>>>(corr, nc, meta, buf);
+    k3_finish_kernel<0><<<ncb, 1024, 0, st>>>(buf, nc, meta);
+    // ---- candidates of the top-5 fallback (unconditional: no host round trip)
+    k3_top_kernel<<<grid, 1024, 0, st>>>(corr, nc, meta, top_idx);
+    // ---- MAD of |corr - med| and the threshold (rtwm/detector.py:84-86)
+    ES_CUDA_OK(cudaMemsetAsync(hist1, 0, (size_t)ncb * 2048 * 4, st));
+    k3_hist_kernel<1, 1><<<grid, 1024, 0, st>>>(corr, nc, meta, hist1);
+    k3_locate_kernel<1><<<ncb, 32, 0, st>>>(hist1, nc, meta, 0);
+    ES_CUDA_OK(cudaMemsetAsync(hist2, 0, (size_t)ncb * 4096 * 4, st));
+    k3_hist_kernel<1, 2><<<grid, 1024, 0, st>>>(corr, nc, meta, hist2);
+    k3_locate_kernel<2><<<ncb, 32, 0, st>>>(hist2, nc, meta, 0);
+    k3_gather_kernel<1><<<grid, 1024, 0, st>>>(corr, nc, meta, buf);
+    k3_finish_kernel<1><<<ncb, 1024, 0, st>>>(buf, nc, meta);
+    // ---- NMS per index block, then the first 25 peaks / the fallback (rtwm/detector.py:87-99, 108-110)
+    k3_nms_kernel<<<dim3(nblk, ncb), 1024, 0, st>>>(corr, nc, meta, nblk, blk_peaks, blk_count);
+    k3_collect_kernel<<<ncb, 1024, 0, st>>>(corr, nc, meta, nblk, blk_peaks, blk_count, top_idx, peaks, npeaks, stats);
+    k3_flag_kernel<<<(ncb + 255) / 256, 256, 0, st>>>(meta, ncb, overflow_dev);
     ES_CUDA_OK(cudaGetLastError());
     return ES_OK;
 }

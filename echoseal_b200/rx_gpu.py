@@ -87,18 +87,33 @@ def ncc(y: torch.Tensor) -> torch.Tensor:
     return corr
 
 
+K3_LONG_MIN = 1 << 21      # correlation length from which the multi-CTA form of K3 is used
+
+
 def peaks(corr: torch.Tensor):
     """corr float64[B,4,nc] -> (peaks i32[B,4,25] (-1 padded), npeaks i32[B,4], stats f64[B,4,4] =
-    med, mad, thr, used_fallback) (K3)."""
+    med, mad, thr, used_fallback) (K3).  Long recordings (nc >= 2^21) take the multi-CTA form."""
     N.require_cuda(corr)
     B, _, nc = corr.shape
     pk = torch.full((B, 4, PEAK_LIMIT), -1, dtype=torch.int32, device=corr.device)
     npk = torch.zeros((B, 4), dtype=torch.int32, device=corr.device)
     st = torch.zeros((B, 4, 4), dtype=torch.float64, device=corr.device)
-    if nc > 0:
-        with N.timed("peaks"):
-            N.check(N.lib().es_rx_peaks(N.ptr(corr), C.c_int(B), C.c_int(nc), N.ptr(pk), N.ptr(npk), N.ptr(st),
-                                        N.stream_ptr()), "es_rx_peaks")
+    if nc <= 0:
+        return pk, npk, st
+    if nc >= K3_LONG_MIN:
+        lib = N.lib()
+        lib.es_rx_peaks_long_scratch_bytes.restype = C.c_size_t
+        nbytes = int(lib.es_rx_peaks_long_scratch_bytes(C.c_int(B), C.c_int(nc)))
+        scratch = torch.empty(nbytes, dtype=torch.uint8, device=corr.device)
+        ovf = torch.zeros(1, dtype=torch.int32, device=corr.device)
+        with N.timed("peaks_long", 17):
+            N.check(lib.es_rx_peaks_long(N.ptr(corr), C.c_int(B), C.c_int(nc), N.ptr(scratch), C.c_size_t(nbytes),
+                                         N.ptr(pk), N.ptr(npk), N.ptr(st), N.ptr(ovf), N.stream_ptr()), "es_rx_peaks_long")
+        if int(ovf.item()) == 0:
+            return pk, npk, st
+    with N.timed("peaks"):
+        N.check(N.lib().es_rx_peaks(N.ptr(corr), C.c_int(B), C.c_int(nc), N.ptr(pk), N.ptr(npk), N.ptr(st),
+                                    N.stream_ptr()), "es_rx_peaks")
     return pk, npk, st
 
 

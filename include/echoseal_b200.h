@@ -67,6 +67,11 @@ int es_rx_ncc(const double* y, int nclips, int n, double* corr /*[clips][4][n-62
  * stats = med, mad, thr, used_fallback */
 int es_rx_peaks(const double* corr, int nclips, int nc, int32_t* peaks /*[clips][4][25]*/,
                 int32_t* npeaks /*[clips][4]*/, double* stats /*[clips][4][4]*/, void* stream);
+/* K3 for one LONG recording: same outputs, every pass spread over many CTAs; *overflow_dev != 0 means a
+ * gather buffer overflowed (degenerate data) and the caller must fall back to es_rx_peaks */
+size_t es_rx_peaks_long_scratch_bytes(int nclips, int nc);
+int es_rx_peaks_long(const double* corr, int nclips, int nc, void* scratch, size_t scratch_bytes,
+                     int32_t* peaks, int32_t* npeaks, double* stats, int32_t* overflow_dev, void* stream);
 /* K4: per peak header decode (rtwm/detector.py:452-515) + matched filter / shift search of _llr
  * (rtwm/detector.py:322-383). hdr_out = ok (-1: no frame), val, score, margin */
 int es_rx_frames(const double* y, int nclips, int n, const int32_t* peaks, const int32_t* npeaks,

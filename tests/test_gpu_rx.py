@@ -210,3 +210,26 @@ def test_resampler_matches_oracle_and_scipy(env):
     rx = detector.WatermarkDetector(key)
     assert rx.verify(a441, 44100) is False
     assert rx.last_result.peaks.shape == (4, 25)
+
+
+def test_long_recording_k3_equals_single_cta_k3(env):
+    """The multi-CTA form of K3 (long recordings) must give exactly the same thresholds, peaks and
+    fallback decisions as the one-CTA-per-band kernel; degenerate data (silence) must take the overflow
+    fallback and still agree."""
+    torch, rx_gpu, detector, clips, taps = env
+    names = list(clips)
+    audio = torch.from_numpy(np.stack([np.pad(clips[n][0], (0, 144000 - clips[n][0].size)) for n in names])).cuda()
+    audio = torch.cat([audio, torch.zeros((1, 144000), device="cuda")])          # + one silent clip
+    corr = rx_gpu.ncc(rx_gpu.bandpass(audio))
+    ref = rx_gpu.peaks(corr)
+    old = rx_gpu.K3_LONG_MIN
+    try:
+        rx_gpu.K3_LONG_MIN = 1000
+        got_all = rx_gpu.peaks(corr)                       # silent clip present -> overflow -> fallback kernel
+        got_nosil = rx_gpu.peaks(corr[:-1].contiguous())   # genuine multi-CTA path
+    finally:
+        rx_gpu.K3_LONG_MIN = old
+    for a, b in zip(ref, got_all):
+        assert torch.equal(a, b)
+    for a, b in zip(ref, got_nosil):
+        assert torch.equal(a[:-1], b)
