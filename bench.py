@@ -40,13 +40,23 @@ def log(*a):
 # The contract is ONE JSON line on stdout.  Libraries (NCCL's "NCCL version ..." banner, nvcc, pytest-free
 # helpers) write to fd 1 too, so fd 1 is pointed at stderr for the whole run and the JSON line goes to the
 # saved descriptor at the end.
-_REAL_STDOUT = os.dup(1)
-os.dup2(2, 1)
-sys.stdout = os.fdopen(os.dup(2), "w", buffering=1)
+_REAL_STDOUT = None
+
+
+def guard_stdout():
+    """point fd 1 at stderr for the rest of the run (only when bench.py is the program, not when imported)"""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+        sys.stdout = os.fdopen(os.dup(2), "w", buffering=1)
 
 
 def emit(line: dict):
-    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+    if _REAL_STDOUT is None:
+        print(json.dumps(line), flush=True)
+    else:
+        os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
 
 
 def bench_key(i: int) -> bytes:
@@ -332,6 +342,7 @@ def main():
     ap.add_argument("--codewords", type=int, default=1_000_000)
     ap.add_argument("--streams", type=int, default=4096)
     args = ap.parse_args()
+    guard_stdout()
     rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":
