@@ -35,6 +35,12 @@ __device__ __forceinline__ double phi_lds(uint32_t addr)
     return v;
 }
 #define PHI_LD(tab, idx) phi_lds((tab) + 8u * (uint32_t)(idx))
+__device__ __forceinline__ void phi_lds2(uint32_t addr, double& a, double& b)
+{
+    asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(a), "=d"(b) : "r"(addr));
+}
+// pair at doubles [2*idx, 2*idx+1] counted from double offset `off` (off even -> 16-byte aligned)
+#define PHI_LD2(tab, off, idx, a, b) phi_lds2((tab) + 8u * (uint32_t)(off) + 16u * (uint32_t)(idx), a, b)
 #define PHI_FMA(a, b, c) __fma_rn((a), (b), (c))
 #define PHI_D2U(x) ((uint64_t)__double_as_longlong(x))
 #define PHI_U2D(x) __longlong_as_double((long long)(x))
@@ -46,6 +52,7 @@ __device__ __forceinline__ double phi_lds(uint32_t addr)
 #include <string.h>
 typedef const double* phi_tab_t;
 #define PHI_LD(tab, idx) ((tab)[(idx)])
+#define PHI_LD2(tab, off, idx, a, b) do { (a) = (tab)[(off) + 2 * (idx)]; (b) = (tab)[(off) + 2 * (idx) + 1]; } while (0)
 #define PHI_FMA(a, b, c) fma((a), (b), (c))
 static inline uint64_t PHI_D2U(double x) { uint64_t u; memcpy(&u, &x, 8); return u; }
 static inline double PHI_U2D(uint64_t u) { double x; memcpy(&x, &u, 8); return x; }
@@ -76,13 +83,12 @@ static inline void phi_fill_k(double* k)
     memcpy(&k[0], &b0, 8); memcpy(&k[1], &b1, 8); memcpy(&k[2], &b2, 8);
 }
 
-// tables: [0,64) exp hi, [64,128) exp lo, then 257-entry log tables (entry 256 serves u == 2.0)
+// tables (doubles): [0,128) exp pairs (2^(j/64) hi, lo), j < 64; then 257 log pairs (invc, logc lo) and 257
+// logc hi values (entry 256 serves u == 2.0).  Pairs are read with one 16-byte load.
 #define PHI_NLT 257
-#define PHI_OFF_EXP_HI 0
-#define PHI_OFF_EXP_LO 64
-#define PHI_OFF_INVC 128
-#define PHI_OFF_LOGC_HI (128 + PHI_NLT)
-#define PHI_OFF_LOGC_LO (128 + 2 * PHI_NLT)
+#define PHI_OFF_EXP 0
+#define PHI_OFF_LOGP 128
+#define PHI_OFF_LOGC_HI (128 + 2 * PHI_NLT)
 #define PHI_TAB_DOUBLES (128 + 3 * PHI_NLT + 1)   /* 900, even */
 
 PHI_FN double phi_fast(double d, phi_tab_t tab)
@@ -108,7 +114,8 @@ PHI_FN double phi_fast(double d, phi_tab_t tab)
     q = PHI_FMA(r, q, PHI_K(6));
     q = PHI_FMA(r, q, 0.5);
     const double p = PHI_FMA(r2, q, r);                       // exp(r) - 1
-    const double th = PHI_LD(tab, PHI_OFF_EXP_HI + j), tl = PHI_LD(tab, PHI_OFF_EXP_LO + j);
+    double th, tl;
+    PHI_LD2(tab, PHI_OFF_EXP, j, th, tl);
     const double tm = th + PHI_FMA(th, p, tl);                // 2^(j/64) * exp(r), in [1,2)
     // t = tm * 2^e in two exact steps (2^e1 on the exponent field, 2^e2 as a factor): the product with
     // 2^e2 is folded into the two fmas below, so a subnormal t is rounded exactly once
@@ -119,7 +126,8 @@ PHI_FN double phi_fast(double d, phi_tab_t tab)
     const double u = PHI_FMA(t1, s2, 1.0);
     const double c = PHI_FMA(t1, s2, -(u - 1.0));
     const int i = (int)(PHI_HI(u) >> 12) - 0x3ff00;           // 0..255, 256 iff u == 2.0
-    const double ic = PHI_LD(tab, PHI_OFF_INVC + i);
+    double ic, lclo;
+    PHI_LD2(tab, PHI_OFF_LOGP, i, ic, lclo);
     const double rr = PHI_FMA(u, ic, -1.0);
     double w = PHI_FMA(rr, PHI_K(7), PHI_K(8));
     w = PHI_FMA(rr, w, PHI_K(9));
@@ -127,7 +135,7 @@ PHI_FN double phi_fast(double d, phi_tab_t tab)
     w = PHI_FMA(rr, w, PHI_K(10));
     w = PHI_FMA(rr, w, -0.5);
     const double ci = c * ic;                                 // c/u to first order ...
-    double tail = PHI_FMA(-ci, rr, ci) + PHI_LD(tab, PHI_OFF_LOGC_LO + i);   // ... times (1 - rr)
+    double tail = PHI_FMA(-ci, rr, ci) + lclo;               // ... times (1 - rr)
     tail = PHI_FMA(rr * rr, w, tail);
     return PHI_LD(tab, PHI_OFF_LOGC_HI + i) + (rr + tail);
 }
@@ -136,15 +144,14 @@ PHI_FN double phi_fast(double d, phi_tab_t tab)
 #ifdef PHI_WANT_FILL
 static void phi_fill_table(double* tab)
 {
-    for (int j = 0; j < 64; ++j) { tab[PHI_OFF_EXP_HI + j] = 0; tab[PHI_OFF_EXP_LO + j] = 0; }
     for (int j = 0; j < 64; ++j) {
-        memcpy(&tab[PHI_OFF_EXP_HI + j], &PHI_EXP_HI[j], 8);
-        memcpy(&tab[PHI_OFF_EXP_LO + j], &PHI_EXP_LO[j], 8);
+        memcpy(&tab[PHI_OFF_EXP + 2 * j], &PHI_EXP_HI[j], 8);
+        memcpy(&tab[PHI_OFF_EXP + 2 * j + 1], &PHI_EXP_LO[j], 8);
     }
     for (int i = 0; i < PHI_NLT; ++i) {
-        memcpy(&tab[PHI_OFF_INVC + i], &PHI_INVC[i], 8);
+        memcpy(&tab[PHI_OFF_LOGP + 2 * i], &PHI_INVC[i], 8);
+        memcpy(&tab[PHI_OFF_LOGP + 2 * i + 1], &PHI_LOGC_LO[i], 8);
         memcpy(&tab[PHI_OFF_LOGC_HI + i], &PHI_LOGC_HI[i], 8);
-        memcpy(&tab[PHI_OFF_LOGC_LO + i], &PHI_LOGC_LO[i], 8);
     }
     tab[PHI_TAB_DOUBLES - 1] = 0.0;
 #ifndef __CUDACC__

@@ -426,9 +426,8 @@ __global__ void __launch_bounds__(PK_THREADS) peaks_kernel(const double* __restr
 // as peaks_kernel, but every streaming pass over corr is spread over many CTAs and the tiny decisions
 // in between run in one CTA per (clip, band).  Two-level monotone histogram (2048 x 2048 bins), gather of
 // the sub-bin(s) holding the two middle ranks, exact rank count; NMS per 4096-index block with the first
-// 25 peaks collected in index order afterwards.  Used when the correlation is longer than K3_LONG_MIN.
+// 25 peaks collected in index order afterwards.  The host picks this form for correlations >= 2^21 samples.
 // ---------------------------------------------------------------------------------------------
-constexpr int K3_LONG_MIN = 1 << 21;
 constexpr int K3_CAP = 32768;              // gathered values per (clip, band)
 constexpr int K3_CHUNK = 1 << 18;          // elements per CTA in the streaming passes
 

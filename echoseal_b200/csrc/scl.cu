@@ -36,8 +36,6 @@ __constant__ int c_K;                    // info + CRC bits
 static int g_code_ready = 0;
 static int g_K = 0;
 
-constexpr double LOGE2 = 0.693147180559945309417232121458176568;
-
 // ---------------------------------------------------------------------------------------------
 // arithmetic
 // ---------------------------------------------------------------------------------------------

@@ -9,7 +9,7 @@
 
 namespace es {
 
-constexpr int TX_FRAME = 1215, TX_PRE = 63, TX_HDR = 128, TX_PAY = 1024;
+constexpr int TX_FRAME = 1215, TX_PRE = 63, TX_HDR = 128;
 constexpr int TX_SYM_WORDS = 38;          // 1216 sign bits per frame
 
 // this translation unit's copy of the polar code layout (filled by es_polar_set_code via tx_set_code)

@@ -3,7 +3,11 @@ thread-per-path, pointer-indirected alpha slots with no refcounts, bit-packed pa
 (`bs` register for levels 6..10, pointer-indirected words for levels 1..5, in-place doubling
 chain), candidate ranking with the reference's stable tie-break.  Runs on the CPU in pure
 Python so the design can be checked against the oracle without a GPU
-(tests/test_scl_lane_model.py).  Not product code, not the oracle."""
+(tests/test_scl_lane_model.py).  Not product code, not the oracle.
+
+The kernel has since moved the bottom two tree levels into registers (one "quad" of four decisions per
+trip, partial sums combined once per quad) — a re-grouping of exactly these steps; the slot-pointer,
+clone and ranking rules modelled here are unchanged."""
 from __future__ import annotations
 import math
 import numpy as np
