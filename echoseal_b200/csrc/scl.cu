@@ -32,6 +32,7 @@ namespace es {
 __constant__ uint32_t c_frozen[32];      // bit (i&31) of word (i>>5): 1 = frozen
 __constant__ uint16_t c_datapos[1024];   // ascending un-frozen positions (K entries used)
 __constant__ int c_K;                    // info + CRC bits
+__constant__ uint8_t c_crc8[256];        // CRC-8 (poly 0x07, MSB first) of one byte
 
 static int g_code_ready = 0;
 static int g_K = 0;
@@ -558,8 +559,7 @@ __global__ void __launch_bounds__(128) scl_hard_kernel(const float* __restrict__
             const uint8_t byte = (uint8_t)(word >> (24 - 8 * bb));
             if (byte_idx < nbytes) {
                 if (lane == bb) out[byte_idx] = byte;
-#pragma unroll
-                for (int t = 7; t >= 0; --t) crcreg = crc8_step_bit(crcreg, (byte >> t) & 1u);
+                crcreg = c_crc8[crcreg ^ byte];                 // uniform index: one constant-cache broadcast
             } else if (byte_idx == nbytes) {
                 crcbits = byte;
             }
@@ -695,6 +695,15 @@ int es_polar_set_code(const uint8_t* frozen_host, int K)
     ES_CUDA_OK(cudaMemcpyToSymbol(c_frozen, words, sizeof(words)));
     ES_CUDA_OK(cudaMemcpyToSymbol(c_datapos, pos, sizeof(pos)));
     ES_CUDA_OK(cudaMemcpyToSymbol(c_K, &K, sizeof(int)));
+    {
+        uint8_t tab[256];
+        for (int v = 0; v < 256; ++v) {
+            uint8_t r = (uint8_t)v;
+            for (int t = 0; t < 8; ++t) r = (r & 0x80) ? (uint8_t)((r << 1) ^ 0x07) : (uint8_t)(r << 1);
+            tab[v] = r;
+        }
+        ES_CUDA_OK(cudaMemcpyToSymbol(c_crc8, tab, sizeof(tab)));
+    }
     { const int rc = tx_set_code(pos, K); if (rc != ES_OK) return rc; }
     g_code_ready = 1;
     g_K = K;
