@@ -177,6 +177,20 @@ def verify_batch(keys, audio, *, fs_target: int = 48_000, list_size: int = 8, mf
             return verdicts, results
         return verdicts
 
+    copy_stream = None if is_tensor else torch.cuda.Stream()
+    staged = {}
+
+    def stage_input(s0):
+        """host audio of clips [s0, s1): pinned -> device on a side stream, so the copy overlaps the kernels"""
+        if is_tensor or s0 in staged or s0 >= B:
+            return
+        host = torch.from_numpy(np.ascontiguousarray(audio[s0:min(B, s0 + sub_batch)], dtype=np.float32)).pin_memory()
+        with torch.cuda.stream(copy_stream):
+            x = host.to(dev, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(copy_stream)
+        staged[s0] = (x, ev, host)
+
     def scan(s0):
         """enqueue K1-K4 for clips [s0, s1) and the asynchronous read-back of peaks / header tuples"""
         sb = _Sub()
@@ -185,9 +199,11 @@ def verify_batch(keys, audio, *, fs_target: int = 48_000, list_size: int = 8, mf
         if is_tensor:
             x = audio[sb.s0:sb.s1].to(device=dev, dtype=torch.float32).contiguous()
         else:
-            host = torch.from_numpy(np.ascontiguousarray(audio[sb.s0:sb.s1], dtype=np.float32)).pin_memory()
-            sb._keep = host
-            x = host.to(dev, non_blocking=True)
+            stage_input(s0)
+            x, ev, sb._keep = staged.pop(s0)
+            torch.cuda.current_stream().wait_event(ev)
+            x.record_stream(torch.cuda.current_stream())
+            stage_input(s0 + sub_batch)                    # next sub-batch's copy runs under this one's kernels
         hdr_pn = torch.from_numpy(bank.hdr_pn(sb.kidx)).to(dev)
         y = rx_gpu.bandpass(x)
         corr = rx_gpu.ncc(y)
