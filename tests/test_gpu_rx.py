@@ -233,3 +233,34 @@ def test_long_recording_k3_equals_single_cta_k3(env):
         assert torch.equal(a, b)
     for a, b in zip(ref, got_nosil):
         assert torch.equal(a[:-1], b)
+
+
+def test_positive_path_matches_reference_golden(env):
+    """tests/golden/positive_golden.npz: the REFERENCE's own _try_decode_frame / _llr / _decode_header on
+    the identity-channel fixture (generated by tests/golden/make_positive_golden.py)."""
+    torch, rx_gpu, detector, clips, taps = env
+    from oracle import tx_oracle as txo
+    from echoseal_b200.utils import BAND_PLAN, choose_band
+    P = np.load(os.path.join(os.path.dirname(__file__), "golden", "positive_golden.npz"))
+    key = bytes([0x5A]) * 32
+    k = txo.Keys(key)
+    for ctr, sigma, seed in [(0, 0.0, 1), (5, 0.05, 2), (1234, 0.12, 3), (70001, 0.10, 4)]:
+        payload = txo.build_payload(k, ctr, b"NONCE123", bytes(11), bytes(range(12)))
+        sym = txo.frame_symbols(k, ctr, payload).astype(np.float64) + sigma * np.random.default_rng(seed).standard_normal(1215)
+        rx = detector.WatermarkDetector(key, list_size=8)
+        for lo, hi in BAND_PLAN:
+            rx._mf_cache[(lo, hi, 48000)] = np.array([1.0], np.float32)
+        ok = rx._try_decode_frame(sym, ctr)
+        nonce = rx.session_nonce
+        again = rx._try_decode_frame(sym, ctr)
+        wrong = rx._try_decode_frame(sym, ctr + 1)
+        rx.session_nonce = b"OTHERNON"
+        mism = rx._try_decode_frame(sym, ctr)
+        pre = f"c{ctr}/"
+        assert [ok, again, wrong, mism] == [bool(v) for v in P[pre + "verdicts"]]
+        assert nonce == P[pre + "nonce"].tobytes()
+        assert np.abs(rx._llr(sym, ctr, 0) - P[pre + "llr0"]).max() <= 1e-4 * 12.0
+        assert np.abs(rx._llr(sym, ctr, 1) - P[pre + "llr1"]).max() <= 1e-4 * 12.0
+        hok, hval, hscore = rx._decode_header(sym, choose_band(key, ctr))
+        assert (float(hok), float(hval)) == (P[pre + "hdr"][0], P[pre + "hdr"][1])
+        assert abs(hscore - P[pre + "hdr"][2]) <= 2e-3 * abs(P[pre + "hdr"][2])
