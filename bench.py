@@ -33,6 +33,39 @@ SCL_NODE_UPDATES_PER_CW = 81920            # N log2 N * L
 SCL_DRAM_BYTES_PER_CW = 708e3              # dram read+write per codeword, ncu --set full (profiles/r01_scl_list_ncu_full.txt: 6.70 GB / 9472 cw)
 
 
+def scl_phi_counts():
+    """phi() evaluations per codeword (8 paths): (reference leaf-by-leaf walk as the kernel would run it without
+    node shortcuts, executed by scl_list_kernel when codewords come as +/- pairs).  Mirrors scl.cu: levels 1..8
+    through f_loop (2 phi per f), 10 phi per ordinary quad, rate-0 nodes = one phi per node LLR (c_r0 map),
+    and the -row variant restarted at bit 512."""
+    from echoseal_b200.polar_tables import frozen_mask
+    fm = np.asarray(frozen_mask(1024, 448)).astype(bool)
+    r0 = [0] * 256
+    for v in range(8, 0, -1):
+        nq = 1 << (v - 1)
+        for q0 in range(nq, 256 - nq + 1, nq):
+            if all(r0[q] == 0 and fm[4 * q:4 * q + 4].all() for q in range(q0, q0 + nq)):
+                r0[q0] = v
+                for q in range(q0 + 1, q0 + nq):
+                    r0[q] = 255
+
+    def count(qlo, qhi, shortcuts):
+        phi = 0.0
+        for q in range(qlo, qhi):
+            node = r0[q] if shortcuts else 0
+            if node == 255:
+                continue
+            last = 8 if node == 0 else 9 - node
+            l0 = 0 if q == 0 else 11 - ((4 * q) & -(4 * q)).bit_length()
+            for lv in range(l0 + 1, last + 1):
+                phi += 2 * (1 << (10 - lv)) / (8 if q == 0 else 1)     # bit 0: one path, shared by the 8 lanes
+            phi += (4 << (node - 1)) if node else 10
+        return phi
+    walk = 8 * count(0, 256, False)
+    pair = 8 * (count(0, 128, True) + 2 * count(128, 256, True)) / 2
+    return walk, pair
+
+
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
@@ -461,6 +494,7 @@ def main():
     achieved_gbs = cw_per_launch * SCL_ALG_BYTES_PER_CW / (scl_avg_ms / 1e3) / 1e9
     sm_mhz = float(peaks.get("sm_max_mhz", 1965.0))
     fp64_lane_rate = 148 * 64 * sm_mhz * 1e6            # DFMA lanes/s
+    phi_walk, phi_exec = scl_phi_counts()
     kshare = {k: float(np.sum(v_)) for k, v_ in ktimes.items()}
     ksum = sum(kshare.values()) or 1.0
     scan_ms = sum(kshare.get(k, 0.0) for k in ("bandpass", "ncc", "peaks"))
@@ -495,9 +529,15 @@ def main():
         "roofline_issue": {"kernel": "scl_list_kernel", "bound": "fp64_issue", "achieved": scl_cw_s, "unit": "codewords/s",
                            "avg_launch_ms": scl_avg_ms, "codewords_per_launch": cw_per_launch,
                            "node_updates_per_s": scl_cw_s * SCL_NODE_UPDATES_PER_CW,
-                           "stated_bound_cw_s": fp64_lane_rate / (86016 * 29),
-                           "frac": scl_cw_s / (fp64_lane_rate / (86016 * 29)),
-                           "bound_def": "148 SM x 64 FP64 lanes x sm_max_mhz / (86016 phi evaluations x 29 FP64 instr)"},
+                           "stated_bound_cw_s": fp64_lane_rate / (phi_walk * 29),
+                           "frac": scl_cw_s / (fp64_lane_rate / (phi_walk * 29)),
+                           "bound_def": f"148 SM x 64 FP64 lanes x sm_max_mhz / ({phi_walk:.0f} phi evaluations of the "
+                                        "leaf-by-leaf walk x 29 FP64 instr)",
+                           "phi_executed_per_cw": phi_exec,
+                           "fp64_pipe_frac_executed": scl_cw_s * phi_exec * 29 / fp64_lane_rate,
+                           "note": "rate-0 node sums and the shared first half of each +/- pair cut the executed phi "
+                                   "count below the walk's; frac is against the walk (algorithmic work), "
+                                   "fp64_pipe_frac_executed against what the kernel really issues"},
         "roofline_scan": {"kernels": "bandpass+ncc+peaks", "bound": "hbm", "achieved": scan_gbs, "peak": hbm, "unit": "GB/s",
                           "frac": (scan_gbs / hbm) if scan_gbs else None,
                           "alg_bytes_per_audio_s": ALG_BYTES_PER_AUDIO_S},

@@ -32,6 +32,9 @@ namespace es {
 __constant__ uint32_t c_frozen[32];      // bit (i&31) of word (i>>5): 1 = frozen
 __constant__ uint16_t c_datapos[1024];   // ascending un-frozen positions (K entries used)
 __constant__ int c_K;                    // info + CRC bits
+// rate-0 node map per quad (bits 4q..4q+3): 0 = ordinary quad; v in 1..8 = first quad of a maximal aligned
+// all-frozen node of 4 << (v-1) bits; 255 = interior quad of such a node
+__constant__ uint8_t c_r0[256];
 __constant__ uint8_t c_crc8[256];        // CRC-8 (poly 0x07, MSB first) of one byte
 
 static int g_code_ready = 0;
@@ -77,6 +80,8 @@ struct SclParams {
     const int32_t* index;    // optional list of codeword ids to decode (nullptr = 0..ncw-1)
     int ncw;                 // number of codewords to decode (length of index if given)
     int neg_mode;            // 0: codeword w = +row w ; 1: codeword w = (w&1 ? - : +) row (w>>1)
+    int pair;                // neg_mode without index: one lane group decodes +row and -row (shared first half)
+    int nunits;              // work units: rows when pair, else codewords
     int list_size;           // 1..8
     double* scratch;         // global alpha scratch, per warp
     size_t scratch_stride;   // doubles per warp
@@ -99,6 +104,7 @@ struct Lane {
     uint32_t ptr, bptr, bs;
     int ord;
     bool active;
+    bool neg;            // decoding the sign-flipped variant: level 0 is negated when bit 512 is reached
 };
 
 struct LvlRef { double* base; int stride; };
@@ -191,6 +197,13 @@ __device__ __forceinline__ void g_level(Lane& L, int l0)
     L.ptr = (L.ptr & ~(7u << (3 * (l0 - 1)))) | ((uint32_t)L.p << (3 * (l0 - 1)));
 }
 
+// level-0 copy of one codeword, this lane's share (k = p, p+8, ...): x -> -x.  Out of line: runs once per decode.
+__device__ __noinline__ void negate_level0(double* l0)
+{
+#pragma unroll 4
+    for (int k = 0; k < 128; ++k) l0[k * 32] = -l0[k * 32];
+}
+
 // bit 0: only one path exists; the 8 lanes of the codeword share the work, everything goes to slot 0
 template <int S>
 __device__ __forceinline__ void spine(Lane& L)
@@ -212,12 +225,30 @@ __device__ __forceinline__ void spine(Lane& L)
 // levels 1..8 for the quad starting at bit i (i % 4 == 0, i > 0): one g node, then f nodes down to level 8.
 // Levels 9 and 10 never touch memory: the quad routine in the kernel keeps them in registers.
 template <int S>
-__device__ __forceinline__ void llr_update8(Lane& L, int i)
+__device__ __forceinline__ void llr_update8(Lane& L, int i, int last)   // last: deepest level wanted, l0 <= last <= 8
 {
     const int l0 = 11 - __ffs(i);    // <= 8
     g_level<S>(L, l0);
 #pragma unroll 1
-    for (int lv = l0 + 1; lv <= 8; ++lv) f_level<S>(L, lv);
+    for (int lv = l0 + 1; lv <= last; ++lv) f_level<S>(L, lv);
+}
+
+// Rate-0 node: all `count` (multiple of 4) bits below the node are frozen, so every path's decisions there
+// are zeros and its metric grows by -ln P(x = 0 | node LLRs) = sum_k ln(1 + exp(a_k)) -- the same quantity the
+// leaf-by-leaf walk (rtwm/fastpolar.py:305-312) accumulates, summed in another order (DESIGN.md section 4,
+// "tie contract").  Four interleaved partial sums, combined as (s0 + s1) + (s2 + s3).
+__device__ __noinline__ double r0_sum(const double* a, int stride, int count, uint32_t tab)
+{
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll 1
+    for (int k = 0; k < count; k += 4) {
+        const double a0 = a[k * stride], a1 = a[(k + 1) * stride], a2 = a[(k + 2) * stride], a3 = a[(k + 3) * stride];
+        s0 += phi_fast(fabs(a0), tab) + fmax(a0, 0.0);
+        s1 += phi_fast(fabs(a1), tab) + fmax(a1, 0.0);
+        s2 += phi_fast(fabs(a2), tab) + fmax(a2, 0.0);
+        s3 += phi_fast(fabs(a3), tab) + fmax(a3, 0.0);
+    }
+    return (s0 + s1) + (s2 + s3);
 }
 
 __device__ __forceinline__ int nth_set8(uint32_t mask, int n)
@@ -358,7 +389,8 @@ template <int S> struct SclLayout {
     static constexpr int AROWS = (1 << (11 - S)) - 4;                   // levels S..8 (9 and 10 live in registers)
     static constexpr int BROWS_S = 7;                                    // beta words of levels 3..5 in shared memory
     static constexpr int BROWS_G = 24;                                   // beta words of levels 1..2 in global memory
-    static constexpr int WARP_BYTES = AROWS * 256 + BROWS_S * 128;
+    static constexpr int SNAP_BYTES = 32 * 16;                           // per-lane (metric, bptr, ord|active) at bit 512
+    static constexpr int WARP_BYTES = AROWS * 256 + BROWS_S * 128 + SNAP_BYTES;
     static constexpr int TAB_BYTES = PHI_TAB_DOUBLES * 8;
     static constexpr size_t G_ROWS = 1024 - (1 << (11 - S));           // global alpha rows, levels 1..S-1
     static constexpr size_t G_DOUBLES = G_ROWS * 32 + 1024 * 4 + BROWS_G * 16;   // + level-0 copy [1024][4] + beta rows
@@ -395,34 +427,61 @@ __global__ void __launch_bounds__(W * 32, 4) scl_list_kernel(SclParams P)
     L.gb = reinterpret_cast<uint32_t*>(gscr + LY::G_ROWS * 32 + 1024 * 4);
     const int K = c_K;
     const int nbytes = (K - 8) >> 3;
-    const int ngroups = (P.ncw + 3) >> 2;
+    const int ngroups = (P.nunits + 3) >> 2;
     const int nwarps = gridDim.x * W;
+    uint4* snap = reinterpret_cast<uint4*>(wbase + (size_t)LY::AROWS * 256 + LY::BROWS_S * 128) + L.lane;
 
     for (int grp = gwarp; grp < ngroups; grp += nwarps) {
         const int j = grp * 4 + (L.lane >> 3);
-        const bool valid = j < P.ncw;
-        const int jj = valid ? j : (P.ncw - 1);
-        const int w = P.index ? P.index[jj] : jj;
-        {   // level 0: widen this warp's 4 codewords to double, [k][4]
+        const bool valid = j < P.nunits;
+        const int jj = valid ? j : (P.nunits - 1);
+        int w = P.pair ? 2 * jj : (P.index ? P.index[jj] : jj);
+        {   // level 0: widen this warp's 4 rows to double, [k][4].  Always +row: f(-a,-b) = f(a,b), so the first
+            // half of the tree of -row is that of +row; the copy is negated at bit 512 (below) for the second half.
             const int row = P.neg_mode ? (w >> 1) : w;
-            const float sgn = (P.neg_mode && (w & 1)) ? -1.0f : 1.0f;
             const float* src = P.llr + (size_t)row * 1024;
             double* dst = gscr + LY::G_ROWS * 32 + (L.lane >> 3);
 #pragma unroll 4
-            for (int k = L.p; k < 1024; k += 8) dst[k * 4] = (double)(sgn * __ldg(src + k));
+            for (int k = L.p; k < 1024; k += 8) dst[k * 4] = (double)__ldg(src + k);
         }
         L.m = 0.0; L.ptr = 0; L.bptr = 0; L.bs = 0; L.ord = 0;
         L.active = (L.p == 0);
+        L.neg = P.neg_mode && (w & 1);
         __syncwarp();
 
+        int qfirst = 0;
 #pragma unroll 1
-        for (int q = 0; q < 256; ++q) {
+        for (int pass = 0; ; ++pass) {
+#pragma unroll 1
+        for (int q = qfirst; q < 256; ++q) {
             const int i = q << 2;
-            if (q == 0) spine<S>(L);
-            else llr_update8<S>(L, i);
-            __syncwarp();
-            const uint32_t fz = (c_frozen[i >> 5] >> (i & 31)) & 15u;       // frozen flags of bits i..i+3
+            if (q == 128 && P.pair && pass == 0) {
+                // bit 512: everything the second half reads from the first half is the level-1 partial sums
+                // (global rows, never rewritten) plus these per-lane words
+                *snap = make_uint4((uint32_t)__double2loint(L.m), (uint32_t)__double2hiint(L.m), L.bptr,
+                                   ((uint32_t)L.ord << 1) | (L.active ? 1u : 0u));
+            }
+            if (q == 128) {
+                if (L.neg) negate_level0(gscr + LY::G_ROWS * 32 + (L.lane >> 3) + L.p * 4);
+                __syncwarp();
+            }
+            // rate-0 nodes: the first quad adds the whole node's penalty, every quad feeds zeros upward
+            const int r0 = c_r0[q];
+            const int last = (r0 == 0) ? 8 : (9 - r0);
+            if (r0 != 255) {
+                if (q == 0) spine<S>(L);
+                else llr_update8<S>(L, i, last);
+                __syncwarp();
+            }
             Carry cy; cy.qb = 0;
+            if (r0 != 0) {
+                if (r0 != 255) {
+                    const LvlRef nd = lvl_ref<S>(L, last, L.p);
+                    const double pen = r0_sum(nd.base, nd.stride, 4 << (r0 - 1), L.tab);
+                    if (L.active) L.m += pen;
+                }
+            } else {
+            const uint32_t fz = (c_frozen[i >> 5] >> (i & 31)) & 15u;       // frozen flags of bits i..i+3
             double fm = 0.0, fp = 0.0;
             int prev = 0;
 #pragma unroll 1
@@ -451,6 +510,7 @@ __global__ void __launch_bounds__(W * 32, 4) scl_list_kernel(SclParams P)
                 }
                 prev = decide(L, (fz >> t) & 1u, leaf, ph, P.list_size, cy);
                 cy.qb |= (uint32_t)prev << t;
+            }
             }
             uint32_t X = cy.qb;
             X ^= (X >> 1) & 0x5u;
@@ -507,6 +567,17 @@ __global__ void __launch_bounds__(W * 32, 4) scl_list_kernel(SclParams P)
         }
         if (valid && L.p == 0) P.npaths[w] = np;
         __syncwarp();
+        if (!P.pair || pass == 1) break;
+        // second pass: the sign-flipped variant of the same row, restarted at bit 512
+        const uint4 sn = *snap;
+        L.m = __hiloint2double((int)sn.y, (int)sn.x);
+        L.bptr = sn.z;
+        L.ord = (int)(sn.w >> 1);
+        L.active = (sn.w & 1u) != 0u;
+        L.neg = true;
+        w += 1;
+        qfirst = 128;
+        }
     }
 }
 
@@ -696,6 +767,22 @@ int es_polar_set_code(const uint8_t* frozen_host, int K)
     ES_CUDA_OK(cudaMemcpyToSymbol(c_datapos, pos, sizeof(pos)));
     ES_CUDA_OK(cudaMemcpyToSymbol(c_K, &K, sizeof(int)));
     {
+        // maximal aligned all-frozen nodes of >= 4 bits that do not start at bit 0 (bit 0 belongs to the spine)
+        uint8_t r0[256] = {0};
+        for (int v = 8; v >= 1; --v) {
+            const int nq = 1 << (v - 1);
+            for (int q0 = nq; q0 + nq <= 256; q0 += nq) {
+                bool all = true;
+                for (int q = q0; q < q0 + nq && all; ++q)
+                    all = (r0[q] == 0) && (((words[(4 * q) >> 5] >> ((4 * q) & 31)) & 15u) == 15u);
+                if (!all) continue;
+                r0[q0] = (uint8_t)v;
+                for (int q = q0 + 1; q < q0 + nq; ++q) r0[q] = 255;
+            }
+        }
+        ES_CUDA_OK(cudaMemcpyToSymbol(c_r0, r0, sizeof(r0)));
+    }
+    {
         uint8_t tab[256];
         for (int v = 0; v < 256; ++v) {
             uint8_t r = (uint8_t)v;
@@ -748,7 +835,9 @@ int es_scl_list(const float* llr, const int32_t* index, int ncw, int neg_mode, i
     if (ncw <= 0) return ES_OK;
     int rc = scl_configure();
     if (rc != ES_OK) return rc;
-    const int ngroups = (ncw + 3) / 4;
+    const int pair = (neg_mode && !index && (ncw % 2) == 0) ? 1 : 0;
+    const int nunits = pair ? ncw / 2 : ncw;
+    const int ngroups = (nunits + 3) / 4;
     int ctas = sm_count() * g_scl_ctas_per_sm;
     const int need_ctas = (ngroups + SCL_W - 1) / SCL_W;
     if (ctas > need_ctas) ctas = need_ctas;
@@ -756,6 +845,7 @@ int es_scl_list(const float* llr, const int32_t* index, int ncw, int neg_mode, i
     if (!scratch || scratch_bytes < need) { set_error("es_scl_list: scratch %zu < %zu bytes", scratch_bytes, need); return ES_EINVAL; }
     SclParams P;
     P.llr = llr; P.index = index; P.ncw = ncw; P.neg_mode = neg_mode; P.list_size = list_size;
+    P.pair = pair; P.nunits = nunits;
     P.scratch = (double*)scratch; P.scratch_stride = scl_scratch_doubles_per_warp();
     P.phi_tab = g_phi_tab_dev;
     P.path_payload = path_payload; P.path_crc = path_crc; P.path_metric = path_metric; P.npaths = npaths;

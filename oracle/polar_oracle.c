@@ -140,7 +140,14 @@ static int crc_ok_u(const uint8_t *frozen, int K, const uint8_t *u, uint8_t *inf
     return es_oracle_crc8(info_out, ninfo) == crcbits;
 }
 
-static void sc_step_llr(path_t *p, const double *llr0, int i)
+/* Device model only: the kernel decodes the detector's sign-flipped variant -llr (rtwm/detector.py:405-413)
+ * from +llr: f(-a,-b) = f(a,b), so the first half of the tree is that of +llr, and the level-1 g node of
+ * -llr is minus the one of +llr.  g_neg selects that form; the reference build negates the input instead. */
+static __thread int g_neg = 0;
+static void sc_step_llr_to(path_t *p, const double *llr0, int i, int last);
+static void sc_step_llr(path_t *p, const double *llr0, int i) { sc_step_llr_to(p, llr0, i, NLOG); }
+
+static void sc_step_llr_to(path_t *p, const double *llr0, int i, int last)
 {
     int l0;
     if (i == 0) l0 = 0;
@@ -152,8 +159,10 @@ static void sc_step_llr(path_t *p, const double *llr0, int i)
         const uint8_t *b = &p->bl[AOFF(l0)];
         for (int k = 0; k < s; k++)
             dst[k] = par[k + s] + (1.0 - 2.0 * (double)b[k]) * par[k];
+        if (l0 == 1 && g_neg)
+            for (int k = 0; k < s; k++) dst[k] = -dst[k];
     }
-    for (int l = l0 + 1; l <= NLOG; l++) {
+    for (int l = l0 + 1; l <= last; l++) {
         int s = 1 << (NLOG - l);
         const double *par = (l == 1) ? llr0 : &p->alpha[AOFF(l - 1)];
         double *dst = &p->alpha[AOFF(l)];
@@ -207,7 +216,7 @@ int es_oracle_scl_decode(const double *llr, const uint8_t *frozen, int K, int L,
     /* fast path candidate */
     {
         uint8_t h[NMAX];
-        for (int i = 0; i < NMAX; i++) h[i] = llr[i] > 0.0;
+        for (int i = 0; i < NMAX; i++) h[i] = (g_neg ? -llr[i] : llr[i]) > 0.0;
         es_oracle_polar_transform(h, NMAX);
         for (int i = 0; i < NMAX; i++) if (frozen[i]) h[i] = 0;
         *hard_crc = crc_ok_u(frozen, K, h, hard_info);
@@ -220,6 +229,34 @@ int es_oracle_scl_decode(const double *llr, const uint8_t *frozen, int K, int L,
     double min_gap = INFINITY, min_rel = INFINITY, nzero = 0, nties = 0;
     cand_t c[2 * LMAX], t;
     for (int i = 0; i < NMAX; i++) {
+#ifdef ORACLE_PHI_FAST
+        /* Device model only: the kernel's rate-0 node rule (echoseal_b200/csrc/scl.cu, r0_sum).  At a quad
+         * boundary i > 0 that starts an aligned all-frozen node of s >= 4 bits (s maximal), every path adds
+         * sum_k ln(1 + exp(a_k)) over the node's own LLRs -- mathematically the sum of the s leaf penalties
+         * the reference walk below accumulates -- in the kernel's summation order, and decides s zeros. */
+        if (i > 0 && (i & 3) == 0) {
+            int s = 0;
+            for (int c2 = 4; c2 <= NMAX / 2 && (i % c2) == 0 && i + c2 <= NMAX; c2 <<= 1) {
+                int all = 1;
+                for (int k = 0; k < c2 && all; k++) all = frozen[i + k] != 0;
+                if (!all) break;
+                s = c2;
+            }
+            if (s) {
+                int lv = NLOG - __builtin_ctz((unsigned)s);
+                for (int p = 0; p < np; p++) {
+                    sc_step_llr_to(&P[p], llr, i, lv);
+                    const double *a = &P[p].alpha[AOFF(lv)];
+                    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+                    for (int k = 0; k < s; k++) acc[k & 3] += phi(fabs(a[k])) + fmax(a[k], 0.0);
+                    P[p].metric += (acc[0] + acc[1]) + (acc[2] + acc[3]);
+                    for (int k = 0; k < s; k++) sc_extend(&P[p], i + k, 0);
+                }
+                i += s - 1;
+                continue;
+            }
+        }
+#endif
         for (int p = 0; p < np; p++) sc_step_llr(&P[p], llr, i);
         if (frozen[i]) {
             for (int p = 0; p < np; p++) {
@@ -293,16 +330,29 @@ static void batch_one(batch_t *b, int w)
 {
     int ninfo = b->K - 8, L = b->L;
     double d[NMAX];
-    for (int i = 0; i < NMAX; i++) d[i] = (double)b->llr[(size_t)w * NMAX + i];
+    if (b->flags & 2) {     /* detector pairing: codeword w = (w odd ? - : +) row w/2 */
+        const float *src = b->llr + (size_t)(w >> 1) * NMAX;
+#ifdef ORACLE_PHI_FAST
+        for (int i = 0; i < NMAX; i++) d[i] = (double)src[i];
+        g_neg = w & 1;
+#else
+        const float sg = (w & 1) ? -1.0f : 1.0f;
+        for (int i = 0; i < NMAX; i++) d[i] = (double)(sg * src[i]);
+#endif
+    } else {
+        g_neg = 0;
+        for (int i = 0; i < NMAX; i++) d[i] = (double)b->llr[(size_t)w * NMAX + i];
+    }
     if (b->flags & 1) {
         uint8_t h[NMAX];
-        for (int i = 0; i < NMAX; i++) h[i] = d[i] > 0.0;
+        for (int i = 0; i < NMAX; i++) h[i] = (g_neg ? -d[i] : d[i]) > 0.0;
         es_oracle_polar_transform(h, NMAX);
         for (int i = 0; i < NMAX; i++) if (b->frozen[i]) h[i] = 0;
         int ok = crc_ok_u(b->frozen, b->K, h, b->hard_info + (size_t)w * ninfo);
         if (ok) {
             b->hard_crc[w] = 1; b->npaths[w] = 0;
             if (b->stats) { double *s = b->stats + 4 * (size_t)w; s[0] = INFINITY; s[1] = INFINITY; s[2] = 0; s[3] = 0; }
+            g_neg = 0;
             return;
         }
     }
@@ -311,6 +361,7 @@ static void batch_one(batch_t *b, int w)
                                  b->path_info + (size_t)w * L * ninfo, b->path_metric + (size_t)w * L,
                                  b->path_crc + (size_t)w * L, b->npaths + w,
                                  b->stats ? b->stats + 4 * (size_t)w : NULL);
+    g_neg = 0;
     if (r) __atomic_store_n(&b->rc, r, __ATOMIC_RELAXED);
 }
 

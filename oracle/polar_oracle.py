@@ -59,10 +59,11 @@ def frozen_default(K: int = 448) -> np.ndarray:
 
 
 def scl_batch(llr: np.ndarray, L: int = 8, K: int = 448, frozen=None, skip_on_hard_crc: bool = False,
-              threads: int | None = None, device_arith: bool = False):
-    """llr float32[ncw,1024] -> dict(hard_info, hard_crc, path_info, path_metric, path_crc, npaths, stats)."""
+              threads: int | None = None, device_arith: bool = False, neg_mode: bool = False):
+    """llr float32[rows,1024] -> dict(hard_info, hard_crc, path_info, path_metric, path_crc, npaths, stats).
+    neg_mode: the detector's pairing (rtwm/detector.py:405-413): codeword 2r = +row r, codeword 2r+1 = -row r."""
     llr = np.ascontiguousarray(llr, dtype=np.float32).reshape(-1, 1024)
-    ncw = llr.shape[0]
+    ncw = llr.shape[0] * (2 if neg_mode else 1)
     fr = np.ascontiguousarray(frozen_default(K) if frozen is None else frozen, dtype=np.uint8)
     ninfo = K - 8
     out = dict(
@@ -72,7 +73,7 @@ def scl_batch(llr: np.ndarray, L: int = 8, K: int = 448, frozen=None, skip_on_ha
         stats=np.zeros((ncw, 4), np.float64),
     )
     rc = (lib_fastphi() if device_arith else lib()).es_oracle_scl_decode_batch(_p(llr), C.c_int(ncw), _p(fr), C.c_int(K), C.c_int(L),
-                                          C.c_int(1 if skip_on_hard_crc else 0), C.c_int(threads or (os.cpu_count() or 1)),
+                                          C.c_int((1 if skip_on_hard_crc else 0) | (2 if neg_mode else 0)), C.c_int(threads or (os.cpu_count() or 1)),
                                           _p(out["hard_info"]), _p(out["hard_crc"]), _p(out["path_info"]),
                                           _p(out["path_metric"]), _p(out["path_crc"]), _p(out["npaths"]),
                                           _p(out["stats"]))

@@ -87,17 +87,48 @@ def test_scl_matches_reference_golden(gpu):
 
 def test_scl_neg_mode_and_index(gpu):
     torch, polar_gpu = gpu
+    from oracle import polar_oracle as po
     llr, _ = awgn_llr_set(64, seed=21)
     out, ref = _cmp_with_oracle(torch, polar_gpu, llr, 8, neg_mode=1)
-    assert (out["payload"].cpu().numpy() == np.packbits(ref["path_info"], axis=2)).all()
+    pay = out["payload"].cpu().numpy()
+    near = ref["stats"][:, 1] < 1e-11
+    same = (pay == np.packbits(ref["path_info"], axis=2)).all(axis=(1, 2))
+    assert same[~near].all()
+    # the sign-flipped variant shares the first half of the tree with +row (scl.cu, "pair" mode): the device
+    # arithmetic model does the same, and the kernel must equal it bit for bit, metrics included
+    model = po.scl_batch(llr, L=8, device_arith=True, neg_mode=True)
+    assert (pay == np.packbits(model["path_info"], axis=2)).all()
+    assert (out["metric"].cpu().numpy() == model["path_metric"]).all()
+    assert (out["crc"].cpu().numpy() == model["path_crc"]).all()
     # index list: only odd codewords decoded
     d = torch.from_numpy(llr).cuda()
     idx = torch.arange(1, 64, 2, dtype=torch.int32, device="cuda")
     o2 = polar_gpu.list_decode(d, list_size=8, index=idx)
-    ref2 = np.packbits(__import__("oracle.polar_oracle", fromlist=["x"]).scl_batch(llr, L=8)["path_info"], axis=2)
+    ref2 = np.packbits(po.scl_batch(llr, L=8)["path_info"], axis=2)
     p2 = o2["payload"].cpu().numpy()
     assert (p2[1::2] == ref2[1::2]).all()
     assert (o2["npaths"].cpu().numpy()[0::2] == 0).all()
+    # index list in neg mode (unpaired decode of single variants) gives the same answers as the paired run
+    idx3 = torch.tensor([1, 2, 5, 7, 8, 127], dtype=torch.int32, device="cuda")
+    o3 = polar_gpu.list_decode(d, list_size=8, neg_mode=1, index=idx3)
+    sel = idx3.cpu().numpy()
+    assert (o3["payload"].cpu().numpy()[sel] == pay[sel]).all()
+    assert (o3["metric"].cpu().numpy()[sel] == out["metric"].cpu().numpy()[sel]).all()
+
+
+def test_scl_pair_mode_detector_like(gpu):
+    """Detector-like (tie-prone) LLR rows in the detector's +/- pairing: kernel == device arithmetic model."""
+    torch, polar_gpu = gpu
+    from oracle import polar_oracle as po
+    tl = detector_like_llr_set(130, seed=5)
+    d = torch.from_numpy(tl).cuda()
+    for L in (8, 3):
+        out = polar_gpu.list_decode(d, list_size=L, neg_mode=1)
+        model = po.scl_batch(tl, L=L, device_arith=True, neg_mode=True)
+        assert (out["payload"].cpu().numpy() == np.packbits(model["path_info"], axis=2)).all(), L
+        assert (out["crc"].cpu().numpy() == model["path_crc"]).all(), L
+        assert (out["metric"].cpu().numpy() == model["path_metric"]).all(), L
+        assert (out["npaths"].cpu().numpy() == model["npaths"]).all(), L
 
 
 def test_scl_tie_prone_verdicts(gpu):

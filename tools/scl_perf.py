@@ -21,6 +21,15 @@ def main():
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
         print(f"list_decode n={n} L={L}: {ms:.2f} ms  -> {n / ms * 1e3 / 1e6:.3f} M cw/s")
+    # the detector's pairing: n/2 rows -> n codewords (+row, -row), first half of the tree shared
+    half = llr[: n // 2]
+    for rep in range(2):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = polar_gpu.list_decode(half, list_size=L, neg_mode=1)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        print(f"pair_decode n={n} L={L}: {ms:.2f} ms  -> {n / ms * 1e3 / 1e6:.3f} M cw/s")
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); polar_gpu.hard_decide(llr); e1.record(); torch.cuda.synchronize()
     print(f"hard_decide n={n}: {e0.elapsed_time(e1):.3f} ms")
