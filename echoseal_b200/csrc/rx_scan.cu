@@ -101,40 +101,69 @@ __global__ void __launch_bounds__(BP_WARPS * 32) bandpass_kernel(const float* __
 }
 
 // ---------------------------------------------------------------------------------------------
-// K2: normalised cross-correlation, 1024 outputs per CTA from a shared y tile
+// K2: normalised cross-correlation (rtwm/detector.py:75-79).  2048 outputs per CTA from a shared y tile;
+// each thread owns 8 CONSECUTIVE outputs so that a loaded sample feeds 8 dot products from registers
+// (8.75 shared loads per output instead of 63: the kernel is FP64-issue bound, not shared-memory bound).
+// The 8 window energies share the 56 squares common to all of them and add their own 7 head/tail squares:
+// only additions of non-negative terms, no sliding subtraction.
 // ---------------------------------------------------------------------------------------------
-constexpr int NCC_TILE = 1024;
+constexpr int NCC_T = 8;
+constexpr int NCC_TILE = 256 * NCC_T;
+constexpr int NCC_IN = NCC_TILE + PRE_L - 1;
+// shared layout: sample j at j + (j >> 3), so that lanes reading j = 8*lane + m are 9 doubles apart (conflict-free)
+__device__ __forceinline__ constexpr int ncc_pad(int j) { return j + (j >> 3); }
+
 __global__ void __launch_bounds__(256) ncc_kernel(const double* __restrict__ y, int n, int nc,
                                                   double* __restrict__ corr)
 {
-    __shared__ double sy[NCC_TILE + PRE_L - 1];
+    __shared__ double sy[ncc_pad(NCC_IN) + 1];
     const int cb = blockIdx.y;                  // clip*4 + band
     const int band = cb & 3;
     const int i0 = blockIdx.x * NCC_TILE;
     const double* ys = y + (long long)cb * n;
-    for (int t = threadIdx.x; t < NCC_TILE + PRE_L - 1; t += 256) {
+    for (int t = threadIdx.x; t < NCC_IN; t += 256) {
         const int j = i0 + t;
-        sy[t] = (j < n) ? ys[j] : 0.0;
+        sy[ncc_pad(t)] = (j < n) ? ys[j] : 0.0;
     }
     __syncthreads();
-    double* cs = corr + (long long)cb * nc;
-    // four outputs per thread, interleaved: 8 independent fp64 accumulation chains hide the DFMA latency
-    const int t0 = threadIdx.x;
-    double e[4] = {0.0, 0.0, 0.0, 0.0}, d[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll 3
+    const double* sv = sy + 9 * threadIdx.x;    // ncc_pad(8*t + m) = 9*t + m + (m >> 3)
+#define NCC_V(m) sv[(m) + ((m) >> 3)]
+    double d[NCC_T], win[NCC_T];
+#pragma unroll
+    for (int q = 0; q < NCC_T; ++q) d[q] = 0.0;
+#pragma unroll
+    for (int q = 0; q < NCC_T - 1; ++q) win[q] = NCC_V(q);
+    double core = 0.0;                          // sum of v[m]^2, m = 7..62: common to the 8 windows
+#pragma unroll
     for (int k = 0; k < PRE_L; ++k) {
+        win[(k + NCC_T - 1) & (NCC_T - 1)] = NCC_V(k + NCC_T - 1);
         const double w = c_tpl[band][k];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const double v = sy[t0 + 256 * q + k];
-            e[q] = fma(v, v, e[q]);
-            d[q] = fma(v, w, d[q]);
-        }
+        for (int q = 0; q < NCC_T; ++q) d[q] = fma(win[(k + q) & (NCC_T - 1)], w, d[q]);
+        if (k >= NCC_T - 1) { const double v = win[k & (NCC_T - 1)]; core = fma(v, v, core); }
     }
+    // window q = samples q..q+62 = head (q..6) + core (7..62) + tail (63..62+q)
+    double head[NCC_T], tail[NCC_T];
+    head[NCC_T - 1] = 0.0;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const int i = i0 + t0 + 256 * q;
-        if (i < nc) cs[i] = d[q] / (sqrt(e[q]) + 1e-12);
+    for (int q = NCC_T - 2; q >= 0; --q) { const double v = NCC_V(q); head[q] = fma(v, v, head[q + 1]); }
+    tail[0] = 0.0;
+#pragma unroll
+    for (int q = 1; q < NCC_T; ++q) { const double v = NCC_V(PRE_L - 1 + q); tail[q] = fma(v, v, tail[q - 1]); }
+    double r[NCC_T];
+#pragma unroll
+    for (int q = 0; q < NCC_T; ++q) r[q] = d[q] / (sqrt((head[q] + core) + tail[q]) + 1e-12);
+#undef NCC_V
+    // stage the 8 results per thread through shared memory for coalesced stores
+    __syncthreads();
+    double* so = sy + 9 * threadIdx.x;
+#pragma unroll
+    for (int q = 0; q < NCC_T; ++q) so[q] = r[q];
+    __syncthreads();
+    double* cs = corr + (long long)cb * nc;
+    for (int t = threadIdx.x; t < NCC_TILE; t += 256) {
+        const int i = i0 + t;
+        if (i < nc) cs[i] = sy[ncc_pad(t)];
     }
 }
 
