@@ -453,7 +453,7 @@ def main():
     e2e_steps = max(1, min(args.steps, 2))
     host_clips = torch.empty((args.clips, N_SAMPLES), dtype=torch.float32, pin_memory=True)
     host_clips.copy_(clips)
-    host_np = host_clips.numpy()
+    host_np = host_clips                                    # pinned CPU tensor: verify_batch copies from it in place
     step(host_np)                                           # warm the pinned path
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

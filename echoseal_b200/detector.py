@@ -144,7 +144,13 @@ def verify_batch(keys, audio, *, fs_target: int = 48_000, list_size: int = 8, mf
         raise RuntimeError("echoseal_b200 needs a CUDA device (no CPU fallback)")
     if not (1 <= int(list_size) <= 8):
         raise ValueError("list_size must be in 1..8 on the B200 path (north_star: SCL-8)")
-    is_tensor = isinstance(audio, torch.Tensor)
+    is_tensor = isinstance(audio, torch.Tensor) and audio.is_cuda
+    host_audio = None
+    if not is_tensor:
+        # host input: a CPU torch tensor (used in place when it is pinned float32) or anything numpy understands
+        host_audio = audio if isinstance(audio, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(audio))
+        if host_audio.dtype != torch.float32:
+            host_audio = host_audio.to(torch.float32)
     B = int(audio.shape[0])
     n = int(audio.shape[1]) if audio.ndim == 2 else 0
     if bank is None:
@@ -184,7 +190,9 @@ def verify_batch(keys, audio, *, fs_target: int = 48_000, list_size: int = 8, mf
         """host audio of clips [s0, s1): pinned -> device on a side stream, so the copy overlaps the kernels"""
         if is_tensor or s0 in staged or s0 >= B:
             return
-        host = torch.from_numpy(np.ascontiguousarray(audio[s0:min(B, s0 + sub_batch)], dtype=np.float32)).pin_memory()
+        host = host_audio[s0:min(B, s0 + sub_batch)]
+        if not (host.is_pinned() and host.is_contiguous()):
+            host = host.contiguous().pin_memory()          # pageable input: one extra host copy into pinned memory
         with torch.cuda.stream(copy_stream):
             x = host.to(dev, non_blocking=True)
             ev = torch.cuda.Event()
