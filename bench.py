@@ -412,10 +412,10 @@ def main():
     key_idx = np.arange(args.clips, dtype=np.int32)
 
     def step(audio, want_details=False):
-        # a fresh key bank per step: key derivation and hop tables are part of verifying a clip
-        bank = KeyBank(keys, nthreads=host_threads)
-        return detector.verify_batch(None, audio, list_size=8, mf_taps=taps, sub_batch=args.sub_batch,
-                                     bank=bank, key_idx=key_idx, details=want_details)
+        # keys, not a prebuilt bank: key derivation and hop tables are part of verifying a clip (built per
+        # sub-batch inside verify_batch's pipeline)
+        return detector.verify_batch(keys, audio, list_size=8, mf_taps=taps, sub_batch=args.sub_batch,
+                                     details=want_details, host_threads=host_threads)
 
     def barrier():
         torch.cuda.synchronize()

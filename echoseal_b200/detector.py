@@ -39,7 +39,7 @@ class RxResult:
     __slots__ = ("verdict", "peaks", "npeaks", "stats", "hdr", "attempts", "payload", "nonce", "n_scl")
 
 
-def _bank_for(keys):
+def _bank_for(keys, nthreads=None):
     """KeyBank over the distinct keys + key index per clip."""
     from .host_feeder import KeyBank
     uniq, idx = {}, np.empty(len(keys), np.int32)
@@ -49,7 +49,7 @@ def _bank_for(keys):
         if j is None:
             j = uniq[k] = len(uniq)
         idx[i] = j
-    return KeyBank(list(uniq)), idx
+    return (KeyBank(list(uniq), nthreads=nthreads) if nthreads else KeyBank(list(uniq))), idx
 
 
 def _pinned_like(t: torch.Tensor) -> torch.Tensor:
@@ -126,10 +126,12 @@ class _Sub:
 
 
 def verify_batch(keys, audio, *, fs_target: int = 48_000, list_size: int = 8, mf_taps=None,
-                 session_nonces=None, sub_batch: int = 512, details: bool = False, bank=None, key_idx=None):
+                 session_nonces=None, sub_batch: int = 512, details: bool = False, bank=None, key_idx=None,
+                 host_threads: int | None = None):
     """Verify B clips (already at fs_target) in one pass.
 
-    keys   : list of B 32-byte keys (or one key for all clips); or pass a prebuilt (bank, key_idx)
+    keys   : list of B 32-byte keys (or one key for all clips); or pass a prebuilt (bank, key_idx).  With a
+             key list the key banks (HKDF, PN sub-keys, hop tables) are built per sub-batch, inside the pipeline
     audio  : float32 [B, n] numpy array (host; copied through pinned memory) or CUDA tensor
     returns: bool[B] (and a list of RxResult when details=True)
     The per-clip semantics are exactly those of WatermarkDetector.verify (rtwm/detector.py:44-152):
@@ -158,8 +160,11 @@ def verify_batch(keys, audio, *, fs_target: int = 48_000, list_size: int = 8, mf
             keys = [bytes(keys)] * B
         if len(keys) != B:
             raise ValueError("need one key per clip")
-        bank, key_idx = _bank_for(keys)
-    key_idx = np.ascontiguousarray(key_idx, np.int32)
+        keys = [bytes(k) for k in keys]
+        if len(set(keys)) == 1:
+            bank, key_idx = _bank_for(keys[:1], host_threads)[0], np.zeros(B, np.int32)
+    if bank is not None:
+        key_idx = np.ascontiguousarray(key_idx, np.int32)
     if mf_taps is None:
         mf_taps = [rx_gpu.matched_filter_taps(b, fs_target) for b in BAND_PLAN]
     rx_gpu.set_filters(fs_target, mf_taps)
@@ -173,6 +178,8 @@ def verify_batch(keys, audio, *, fs_target: int = 48_000, list_size: int = 8, mf
                 nonce_state[i, 1:] = np.frombuffer(sn, np.uint8)
     dev = torch.device("cuda", torch.cuda.current_device())
 
+    if B == 0:
+        return (verdicts, results) if details else verdicts
     if n < PRE_L:          # rtwm/detector.py:72-73: shorter than the template -> False for every band
         if details:
             for i in range(B):
@@ -203,7 +210,10 @@ def verify_batch(keys, audio, *, fs_target: int = 48_000, list_size: int = 8, mf
         """enqueue K1-K4 for clips [s0, s1) and the asynchronous read-back of peaks / header tuples"""
         sb = _Sub()
         sb.s0, sb.s1 = s0, min(B, s0 + sub_batch)
-        sb.kidx = key_idx[sb.s0:sb.s1]
+        if bank is not None:
+            sb.bank, sb.kidx = bank, key_idx[sb.s0:sb.s1]
+        else:
+            sb.bank, sb.kidx = _bank_for(keys[sb.s0:sb.s1], host_threads)
         if is_tensor:
             x = audio[sb.s0:sb.s1].to(device=dev, dtype=torch.float32).contiguous()
         else:
@@ -212,7 +222,7 @@ def verify_batch(keys, audio, *, fs_target: int = 48_000, list_size: int = 8, mf
             torch.cuda.current_stream().wait_event(ev)
             x.record_stream(torch.cuda.current_stream())
             stage_input(s0 + sub_batch)                    # next sub-batch's copy runs under this one's kernels
-        hdr_pn = torch.from_numpy(bank.hdr_pn(sb.kidx)).to(dev)
+        hdr_pn = torch.from_numpy(sb.bank.hdr_pn(sb.kidx)).to(dev)
         y = rx_gpu.bandpass(x)
         corr = rx_gpu.ncc(y)
         sb.pk, sb.npk, sb.st = rx_gpu.peaks(corr)
@@ -229,8 +239,8 @@ def verify_batch(keys, audio, *, fs_target: int = 48_000, list_size: int = 8, mf
     def enumerate_(sb):
         """host: candidate counters, 400-try budget, PN bits (native, threaded)"""
         sb.ev.synchronize()
-        sb.enum = bank.rx_enumerate(sb.kidx, n, sb.pk_h.numpy(), sb.npk_h.numpy(), sb.hdr_h.numpy())
-        sb.dec = _Decode(bank, sb.kidx, sb.enum, sb.fr["mf_aligned"], list_size, dev)
+        sb.enum = sb.bank.rx_enumerate(sb.kidx, n, sb.pk_h.numpy(), sb.npk_h.numpy(), sb.hdr_h.numpy())
+        sb.dec = _Decode(sb.bank, sb.kidx, sb.enum, sb.fr["mf_aligned"], list_size, dev)
 
     def finish(sb):
         ns = np.ascontiguousarray(nonce_state[sb.s0:sb.s1])
@@ -257,7 +267,7 @@ def verify_batch(keys, audio, *, fs_target: int = 48_000, list_size: int = 8, mf
                 r.nonce = ns[ci, 1:].tobytes() if ns[ci, 0] else None
                 r.n_scl = 4 * int(enum["band_count"][ci].sum())
                 results[sb.s0 + ci] = r
-        sb.fr = None; sb.dec = None
+        sb.fr = None; sb.dec = None; sb.bank = None
 
     starts = list(range(0, B, sub_batch))
     cur = scan(starts[0])
