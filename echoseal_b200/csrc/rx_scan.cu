@@ -33,70 +33,104 @@ __constant__ int c_mf_len[NBANDS];
 static int g_rx_ready = 0;
 
 // ---------------------------------------------------------------------------------------------
-// K1: band-pass.  One LANE per (clip, band, 2048-sample chunk): direct-form II transposed, the operation
-// order of scipy's lfilter, states in registers; chunks other than the first start from zero state
-// BP_WARM samples early (the filter's impulse response has decayed below 1e-12 by then; samples before
-// the clip start are zeros, which keep the zero state exactly).  A warp owns 32 consecutive chunks and
-// moves data through shared-memory tiles so that every global access is a full 128-byte (input) or
-// 256-byte (output) row: the per-lane streams themselves would touch 32 different lines per instruction.
+// K1: band-pass.  One LANE per (clip, chunk), all four bands: direct-form II transposed, the operation order
+// of scipy's lfilter, the 4 x 8 states in registers (four independent recurrences per lane hide the DFMA
+// latency); chunks other than the first start from zero state BP_WARM samples early (the filter's impulse
+// response has decayed below 1e-12 by then; samples before the clip start are zeros, which keep the zero state
+// exactly).  The chunk length is chosen per call so that a (clip) fills whole warps (144 000 samples -> 64
+// chunks of 2250).  A warp owns 32 consecutive chunks and moves data through shared-memory tiles so that every
+// global access is a full row (128-byte input, 256-byte output); the input tile of the next step is in flight
+// (cp.async into the other half of a double buffer) while the current one is filtered, and it is read from HBM
+// once for the four bands.
+// ODDZ: the odd numerator taps of a Butterworth band-pass are exactly 0.0; fma(0, x, z) == z, so they are skipped.
 // ---------------------------------------------------------------------------------------------
-constexpr int BP_WARPS = 3;
+constexpr int BP_WARPS = 1;
+constexpr int BP_STEP = 16;                 // samples per lane per pipeline step
+constexpr int BP_MIN_CTAS = 14;             // 146 registers, 13.6 KB shared memory per warp
 struct BpWarpShared {
-    float xin[32][33];
-    double yout[32][33];
+    float xin[2][32][BP_STEP + 1];
+    double yout[NBANDS][32][9];             // half a step (8 samples) of the four bands
 };
+static bool g_bp_oddz = false;
 
-__global__ void __launch_bounds__(BP_WARPS * 32) bandpass_kernel(const float* __restrict__ x, int nclips, int n,
-                                                                 long long x_stride, double* __restrict__ y)
+template <bool ODDZ>
+__global__ void __launch_bounds__(BP_WARPS * 32, BP_MIN_CTAS) bandpass_kernel(const float* __restrict__ x, int nclips, int n,
+                                                                 long long x_stride, double* __restrict__ y,
+                                                                 int ch, int groups)
 {
     __shared__ BpWarpShared SH[BP_WARPS];
     const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
     BpWarpShared& S = SH[wl];
-    const int nchunks = (n + BP_CHUNK - 1) / BP_CHUNK;
-    const int groups = (nchunks + 31) / 32;                       // warps per (clip, band)
     const long long wid = (long long)blockIdx.x * BP_WARPS + wl;
-    if (wid >= (long long)nclips * NBANDS * groups) return;
+    if (wid >= (long long)nclips * groups) return;
     const int grp = (int)(wid % groups);
-    const int band = (int)((wid / groups) % NBANDS);
-    const int clip = (int)(wid / ((long long)groups * NBANDS));
-    const float* xs = x + (long long)clip * x_stride;
-    double* ys = y + ((long long)clip * NBANDS + band) * n;
-    double b[9], a[9], z[8];
+    const long long clip = wid / groups;
+    const float* xs = x + clip * x_stride;
+    double* ys = y + clip * NBANDS * (long long)n;
+    double z[NBANDS][8];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) { b[i] = c_bp_b[band][i]; a[i] = c_bp_a[band][i]; }
+    for (int bd = 0; bd < NBANDS; ++bd)
 #pragma unroll
-    for (int i = 0; i < 8; ++i) z[i] = 0.0;
+        for (int i = 0; i < 8; ++i) z[bd][i] = 0.0;
     const int chunk0 = grp * 32;
-    // step s covers samples [out0 - BP_WARM + 32 s, +32) of every lane's chunk
-    const int nsteps = (BP_WARM + BP_CHUNK) / 32;
+    // step st covers samples [first - BP_WARM + BP_STEP st, +BP_STEP) of every lane's chunk
+    static_assert(BP_WARM % BP_STEP == 0 && BP_STEP == 16, "fetch() maps a warp onto two 16-sample rows");
+    const int nsteps = (BP_WARM + ch + BP_STEP - 1) / BP_STEP;
+    auto fetch = [&](int st) {          // row r = chunk chunk0 + r, BP_STEP consecutive samples; 2 rows per instruction
+        const int rel = -BP_WARM + st * BP_STEP + (lane & 15);
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&S.xin[st & 1][lane >> 4][lane & 15]);
+#pragma unroll 8
+        for (int i = 0; i < 16; ++i) {
+            const long long j = (long long)(chunk0 + 2 * i + (lane >> 4)) * ch + rel;
+            const bool in = (j >= 0 && j < n);
+            // 4-byte asynchronous copy; src-size 0 zero-fills (samples outside the clip)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + i * 2 * (BP_STEP + 1) * 4),
+                         "l"(xs + (in ? j : 0)), "r"(in ? 4 : 0));
+        }
+        asm volatile("cp.async.commit_group;");
+    };
+    fetch(0);
 #pragma unroll 1
     for (int st = 0; st < nsteps; ++st) {
-        const int rel = -BP_WARM + st * 32;                        // offset from each chunk's first output
-        // cooperative load: row r = chunk chunk0+r, 32 consecutive samples
-#pragma unroll 4
-        for (int r = 0; r < 32; ++r) {
-            const long long j = (long long)(chunk0 + r) * BP_CHUNK + rel + lane;
-            S.xin[r][lane] = (j >= 0 && j < n && chunk0 + r < nchunks) ? __ldg(xs + j) : 0.0f;
-        }
+        const int rel = -BP_WARM + st * BP_STEP;                   // offset from each chunk's first output
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();
-#pragma unroll 4
-        for (int t = 0; t < 32; ++t) {
-            const double xn = (double)S.xin[lane][t];
-            const double yn = fma(b[0], xn, z[0]);
+        if (st + 1 < nsteps) fetch(st + 1);
+        const float(*xin)[BP_STEP + 1] = S.xin[st & 1];
+#pragma unroll 1
+        for (int q8 = 0; q8 < BP_STEP / 8; ++q8) {
+            // 8 samples, the four band recurrences interleaved: one shared load + conversion feeds 4 independent chains
+#pragma unroll 2
+            for (int t = 0; t < 8; ++t) {
+                const double xn = (double)xin[lane][q8 * 8 + t];
 #pragma unroll
-            for (int i = 0; i < 7; ++i) z[i] = fma(-a[i + 1], yn, fma(b[i + 1], xn, z[i + 1]));
-            z[7] = fma(-a[8], yn, b[8] * xn);
-            S.yout[lane][t] = yn;
-        }
-        __syncwarp();
-        if (rel >= 0) {
-#pragma unroll 4
-            for (int r = 0; r < 32; ++r) {
-                const long long j = (long long)(chunk0 + r) * BP_CHUNK + rel + lane;
-                if (chunk0 + r < nchunks && j < n) ys[j] = S.yout[r][lane];
+                for (int bd = 0; bd < NBANDS; ++bd) {
+                    const double yn = fma(c_bp_b[bd][0], xn, z[bd][0]);
+#pragma unroll
+                    for (int i = 0; i < 7; ++i) {
+                        const double zi = (ODDZ && !(i & 1)) ? z[bd][i + 1] : fma(c_bp_b[bd][i + 1], xn, z[bd][i + 1]);
+                        z[bd][i] = fma(-c_bp_a[bd][i + 1], yn, zi);
+                    }
+                    z[bd][7] = fma(-c_bp_a[bd][8], yn, c_bp_b[bd][8] * xn);
+                    S.yout[bd][lane][t] = yn;
+                }
             }
+            __syncwarp();
+            const int o0 = rel + q8 * 8;
+            if (o0 + 7 >= 0) {
+                const int o = o0 + (lane & 7);                     // four 64-byte row segments per instruction
+#pragma unroll
+                for (int bd = 0; bd < NBANDS; ++bd) {
+                    double* yb = ys + (long long)bd * n;
+#pragma unroll 4
+                    for (int r = lane >> 3; r < 32; r += 4) {
+                        const long long j = (long long)(chunk0 + r) * ch + o;
+                        if (o >= 0 && o < ch && j < n) yb[j] = S.yout[bd][r][lane & 7];
+                    }
+                }
+            }
+            __syncwarp();
         }
-        __syncwarp();
     }
 }
 
@@ -1047,6 +1081,9 @@ int es_rx_set_filters(const double* bp_b /*[4][9]*/, const double* bp_a /*[4][9]
     ES_CUDA_OK(cudaMemcpyToSymbol(c_tpl, tpl, sizeof(double) * NBANDS * PRE_L));
     ES_CUDA_OK(cudaMemcpyToSymbol(c_mf, mf, sizeof(float) * NBANDS * MAXH));
     ES_CUDA_OK(cudaMemcpyToSymbol(c_mf_len, mf_len, sizeof(int) * NBANDS));
+    g_bp_oddz = true;
+    for (int b = 0; b < NBANDS; ++b)
+        for (int i = 1; i < 8; i += 2) g_bp_oddz = g_bp_oddz && (bp_b[b * 9 + i] == 0.0);
     g_rx_ready = 1;
     return ES_OK;
 }
@@ -1055,9 +1092,29 @@ int es_rx_bandpass(const float* x, int nclips, int n, long long x_stride, double
 {
     if (!g_rx_ready) { set_error("es_rx_bandpass: call es_rx_set_filters first"); return ES_ENOTREADY; }
     if (nclips <= 0 || n <= 0) return ES_OK;
-    const long long nchunks = (n + BP_CHUNK - 1) / BP_CHUNK;
-    const long long warps = (long long)nclips * NBANDS * ((nchunks + 31) / 32);
-    bandpass_kernel<<<(unsigned)((warps + BP_WARPS - 1) / BP_WARPS), BP_WARPS * 32, 0, (cudaStream_t)stream>>>(x, nclips, n, x_stride, y);
+    // chunk length: about BP_CHUNK, such that a clip is a whole number of 32-chunk warps; among 1x..3x that many
+    // warps per clip pick the split with the least (waves over the resident warp slots) x (steps per warp)
+    static int slots = 0;
+    if (!slots) {
+        int per_sm = 0;
+        ES_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bandpass_kernel<true>, BP_WARPS * 32, 0));
+        slots = sm_count() * (per_sm > 0 ? per_sm : 1) * BP_WARPS;
+    }
+    int g0 = (int)(((long long)n + 16LL * BP_CHUNK) / (32LL * BP_CHUNK));
+    if (g0 < 1) g0 = 1;
+    int groups = g0, ch = 0;
+    double best = 0.0;
+    for (int g = g0; g <= 3 * g0; ++g) {
+        int c = (int)(((long long)n + 32LL * g - 1) / (32LL * g));
+        c = (c + 15) & ~15;                                // rows of y start on 128-byte lines
+        const long long units = (long long)nclips * g;
+        const double cost = (double)((units + slots - 1) / slots) * (double)(BP_WARM + c);
+        if (g == g0 || cost < best) { best = cost; groups = g; ch = c; }
+    }
+    const long long warps = (long long)nclips * groups;
+    const unsigned grid = (unsigned)((warps + BP_WARPS - 1) / BP_WARPS);
+    if (g_bp_oddz) bandpass_kernel<true><<<grid, BP_WARPS * 32, 0, (cudaStream_t)stream>>>(x, nclips, n, x_stride, y, ch, groups);
+    else bandpass_kernel<false><<<grid, BP_WARPS * 32, 0, (cudaStream_t)stream>>>(x, nclips, n, x_stride, y, ch, groups);
     ES_CUDA_OK(cudaGetLastError());
     return ES_OK;
 }

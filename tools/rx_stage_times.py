@@ -17,8 +17,10 @@ def main():
     def T(label, fn):
         torch.cuda.synchronize(); t0 = time.perf_counter(); r = fn(); torch.cuda.synchronize()
         print(f"{label:28s} {1e3 * (time.perf_counter() - t0):8.2f} ms"); return r
+    from echoseal_b200 import _native as N
     for rep in range(2):
         print("--- rep", rep)
+        N.KERNEL_TIMES = {}
         bank = T("KeyBank(keys)", lambda: KeyBank(keys))
         hdr_pn = T("hdr_pn->dev", lambda: torch.from_numpy(bank.hdr_pn(kidx)).to(dev))
         y = T("bandpass", lambda: rx_gpu.bandpass(clips))
@@ -42,6 +44,9 @@ def main():
         ih, hp = T("collect hits", collect)
         ns = np.zeros((nb, 9), np.uint8)
         T(f"rx_validate ({len(ih)} hits)", lambda: bank.rx_validate(kidx, enum, ih[:, 0].astype(np.int64), ih[:, 1].astype(np.int32), hp, ns))
+        torch.cuda.synchronize()
+        print("kernel-only (CUDA events):", {k: round(sum(a.elapsed_time(b) for a, b in v), 3) for k, v in N.KERNEL_TIMES.items()})
+        N.KERNEL_TIMES = None
 
 if __name__ == "__main__":
     main()
