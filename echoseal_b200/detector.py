@@ -190,6 +190,18 @@ def verify_batch(keys, audio, *, fs_target: int = 48_000, list_size: int = 8, mf
             return verdicts, results
         return verdicts
 
+    # sub-batch boundaries: full-size in the middle, tapered (1/4, 1/2) at both ends so that the pipeline's
+    # fill (first scan + enumeration before any SCL kernel runs) and drain (last validation) are short
+    sizes = []
+    if B >= 4 * sub_batch and sub_batch >= 8:
+        head = [sub_batch // 4, sub_batch // 2]
+        tail = [sub_batch // 2, sub_batch // 4]
+        mid = B - sum(head) - sum(tail)
+        sizes = head + [sub_batch] * (mid // sub_batch) + ([mid % sub_batch] if mid % sub_batch else []) + tail
+    else:
+        sizes = [min(sub_batch, B - s) for s in range(0, B, sub_batch)]
+    bounds = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    end_of = {int(bounds[i]): int(bounds[i + 1]) for i in range(len(sizes))}
     copy_stream = None if is_tensor else torch.cuda.Stream()
     staged = {}
 
@@ -197,7 +209,7 @@ def verify_batch(keys, audio, *, fs_target: int = 48_000, list_size: int = 8, mf
         """host audio of clips [s0, s1): pinned -> device on a side stream, so the copy overlaps the kernels"""
         if is_tensor or s0 in staged or s0 >= B:
             return
-        host = host_audio[s0:min(B, s0 + sub_batch)]
+        host = host_audio[s0:end_of[s0]]
         if not (host.is_pinned() and host.is_contiguous()):
             host = host.contiguous().pin_memory()          # pageable input: one extra host copy into pinned memory
         with torch.cuda.stream(copy_stream):
@@ -209,7 +221,7 @@ def verify_batch(keys, audio, *, fs_target: int = 48_000, list_size: int = 8, mf
     def scan(s0):
         """enqueue K1-K4 for clips [s0, s1) and the asynchronous read-back of peaks / header tuples"""
         sb = _Sub()
-        sb.s0, sb.s1 = s0, min(B, s0 + sub_batch)
+        sb.s0, sb.s1 = s0, end_of[s0]
         if bank is not None:
             sb.bank, sb.kidx = bank, key_idx[sb.s0:sb.s1]
         else:
@@ -221,7 +233,7 @@ def verify_batch(keys, audio, *, fs_target: int = 48_000, list_size: int = 8, mf
             x, ev, sb._keep = staged.pop(s0)
             torch.cuda.current_stream().wait_event(ev)
             x.record_stream(torch.cuda.current_stream())
-            stage_input(s0 + sub_batch)                    # next sub-batch's copy runs under this one's kernels
+            stage_input(end_of[s0])                        # next sub-batch's copy runs under this one's kernels
         hdr_pn = torch.from_numpy(sb.bank.hdr_pn(sb.kidx)).to(dev)
         y = rx_gpu.bandpass(x)
         corr = rx_gpu.ncc(y)
@@ -269,7 +281,7 @@ def verify_batch(keys, audio, *, fs_target: int = 48_000, list_size: int = 8, mf
                 results[sb.s0 + ci] = r
         sb.fr = None; sb.dec = None; sb.bank = None
 
-    starts = list(range(0, B, sub_batch))
+    starts = [int(b) for b in bounds[:-1]]
     cur = scan(starts[0])
     enumerate_(cur)
     prev = None

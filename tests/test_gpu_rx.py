@@ -176,6 +176,25 @@ def test_batch_matches_single_and_details(env):
             assert [c for _, c in r.attempts[bi]] == list(G[f"{n}/b{bi}/att_ctr"])
 
 
+def test_batch_schedules_agree(env):
+    """The tapered multi-sub-batch schedule, per-sub-batch key banks and the pinned-host input path give the
+    same sync offsets, attempt lists and verdicts as one big sub-batch of device-resident clips."""
+    torch, rx_gpu, detector, clips, taps = env
+    names = ["chirp_aa", "noise_44", "bench_17", "plain_noise"]
+    reps = 9                                               # 36 clips, sub_batch 8 -> sizes 2,4,8,8,6,4,2... tapered
+    audio = np.stack([clips[n][0] for n in names] * reps)
+    keys = [clips[n][1] for n in names] * reps
+    v1, r1 = detector.verify_batch(keys, torch.from_numpy(audio).cuda(), details=True, sub_batch=64)
+    host = torch.from_numpy(audio).pin_memory()
+    v2, r2 = detector.verify_batch(keys, host, details=True, sub_batch=8)
+    v3, r3 = detector.verify_batch(keys, audio, details=True, sub_batch=8)      # pageable numpy input
+    assert (v1 == v2).all() and (v1 == v3).all()
+    for a, b, c in zip(r1, r2, r3):
+        assert (a.peaks == b.peaks).all() and (a.peaks == c.peaks).all()
+        assert a.attempts == b.attempts == c.attempts
+        assert a.n_scl == b.n_scl == c.n_scl
+
+
 def test_verdicts_match_unmodified_reference(env):
     """tests/golden/rx_verdicts.json: verdicts of the reference's own verify() (list_size=8, real
     fastpolar decoder, 2-7 CPU-minutes per clip)."""
