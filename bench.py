@@ -30,7 +30,7 @@ N_SAMPLES = int(FS * SECS)
 ALG_BYTES_PER_AUDIO_S = 4 * FS             # RX reads each float32 input sample once
 SCL_ALG_BYTES_PER_CW = 4096 + 55           # fp32 LLR in + payload out
 SCL_NODE_UPDATES_PER_CW = 81920            # N log2 N * L
-SCL_DRAM_BYTES_PER_CW = 708e3              # dram read+write per codeword, ncu --set full (profiles/r01_scl_list_ncu_full.txt: 6.70 GB / 9472 cw)
+SCL_DRAM_BYTES_PER_CW = 555e3              # dram read+write per codeword, ncu --set full (profiles/r01_scl_list_ncu_full.txt: 10.51 GB / 18944 cw, +/- pairs)
 
 
 def scl_phi_counts():
