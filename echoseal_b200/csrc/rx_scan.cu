@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(256) ncc_kernel(const double* __restrict__ y, 
 // ---------------------------------------------------------------------------------------------
 // K3: exact order statistics + NMS.  One CTA of 1024 threads per (clip, band).
 // ---------------------------------------------------------------------------------------------
-constexpr int PK_THREADS = 1024;
+constexpr int PK_THREADS = 512;        // two CTAs (rows) per SM: one row's serial decisions overlap the other's streaming passes
 constexpr int SEL_BINS = 2048;
 constexpr int SEL_CAP = 4096;       // values gathered from the selected bin (shared memory)
 constexpr int NMS_BLOCK = 4096;
@@ -366,17 +366,14 @@ struct PeakShared {
     int top_i[32];
 };
 
-__global__ void __launch_bounds__(PK_THREADS) peaks_kernel(const double* __restrict__ corr, int nc,
-                                                           int32_t* __restrict__ peaks, int32_t* __restrict__ npeaks,
-                                                           double* __restrict__ stats)
+// One (clip, band) row, general form: every order statistic by histogram + gather (+ radix select), NMS by
+// 4096-index blocks.  ~6 passes over the row.  peaks2_kernel below answers the common case in 2 passes and
+// calls this for everything else, so it is also the definition the fast path is tested against.
+__device__ void peaks_row_general(const double* __restrict__ c, int nc, int cb, int32_t* __restrict__ pk,
+                                  int32_t* __restrict__ npeaks, double* __restrict__ stats, PeakShared& S)
 {
-    extern __shared__ __align__(16) unsigned char pk_raw[];
-    PeakShared& S = *reinterpret_cast<PeakShared*>(pk_raw);
-    const int cb = blockIdx.x;
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
-    const double* c = corr + (long long)cb * nc;
-    int32_t* pk = peaks + (long long)cb * PEAK_LIMIT;
     for (int t = tid; t < PEAK_LIMIT; t += PK_THREADS) pk[t] = -1;
     if (nc <= 0) {
         if (tid == 0) { npeaks[cb] = 0; stats[cb * 4 + 0] = 0; stats[cb * 4 + 1] = 0; stats[cb * 4 + 2] = 0; stats[cb * 4 + 3] = 0; }
@@ -475,6 +472,320 @@ __global__ void __launch_bounds__(PK_THREADS) peaks_kernel(const double* __restr
             }
             __syncthreads();
         }
+        }
+        np = kf;
+    }
+    if (tid == 0) {
+        npeaks[cb] = np < PEAK_LIMIT ? np : PEAK_LIMIT;
+        stats[cb * 4 + 0] = med; stats[cb * 4 + 1] = mad; stats[cb * 4 + 2] = thr; stats[cb * 4 + 3] = (double)fallback;
+    }
+}
+
+__global__ void __launch_bounds__(PK_THREADS) peaks_kernel(const double* __restrict__ corr, int nc,
+                                                           int32_t* __restrict__ peaks, int32_t* __restrict__ npeaks,
+                                                           double* __restrict__ stats)
+{
+    extern __shared__ __align__(16) unsigned char pk_raw[];
+    PeakShared& S = *reinterpret_cast<PeakShared*>(pk_raw);
+    const int cb = blockIdx.x;
+    peaks_row_general(corr + (long long)cb * nc, nc, cb, peaks + (long long)cb * PEAK_LIMIT, npeaks, stats, S);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3, two-pass form.  The general form above re-reads the 1.15 MB row about six times from DRAM (the rows of
+// all resident CTAs do not fit L2).  Here:
+//  pass A  histogram of corr + speculative gather of the six central bins (|corr| < 3/1024): the median of a
+//          correlation row sits there, so the gather of the general form is already done;
+//  then    from the SAME histogram and the exact median, a bracket r_lo < MAD <= r_hi in whole bin widths with a
+//          one-bin safety margin on each side;
+//  pass B  exact count of |corr - med| <= r_lo, gather of the values inside the bracket, indices of everything
+//          above the conservative threshold med + 6.67 r_lo, indices of the top histogram bins (top-5 fallback);
+//  then    exact MAD by rank inside the bracket, exact threshold, NMS on the few candidates in index order.
+// Same results as the general form (tests/test_gpu_rx.py compares them on adversarial rows); whenever a buffer
+// would overflow or the speculation misses, the row is redone by peaks_row_general.
+// ---------------------------------------------------------------------------------------------
+constexpr int PK2_CAP = 6144;          // gathered values per stage (about 2700 / 4200 expected for sigma = 1/sqrt(63))
+constexpr int PK2_SUB = 2048;          // values of the (sub-)bins holding the two middle ranks
+constexpr int PK2_NCAND = 2048;        // threshold candidates / top-bin candidates
+constexpr int PK2_SPEC_LO = 1021, PK2_SPEC_HI = 1027;   // speculative median bins
+constexpr int PK2_UNROLL = 8;          // loads in flight per thread in the streaming passes
+constexpr int PK2_MIN_NC = 8192;       // shorter rows go to the general form directly
+
+struct Pk2Shared {
+    unsigned int hist[SEL_BINS];
+    unsigned int pref[SEL_BINS + 1];   // pref[b] = number of values in bins < b
+    double buf[PK2_CAP];
+    double sub[PK2_SUB];
+    int cand[PK2_NCAND];
+    int top[PK2_NCAND];
+    int sorted[PK2_NCAND];
+    unsigned int nbuf, nsub, ncand, ntop, nkeep, below_cnt, topcount;
+    int topbin, b1, b2, ok, npeaks, pass[32];
+    unsigned int below1;
+    double r1, r2, r_lo, r_hi, thr_lo;
+};
+union PkUnion { PeakShared g; Pk2Shared f; };
+
+// ranks ra <= rb (0-based) among S.sub[0..ms): the v with #less <= r < #less + #equal.  Results in S.r1 / S.r2.
+__device__ __forceinline__ void pk2_select2(Pk2Shared& S, int ms, int ra, int rb)
+{
+    for (int i = threadIdx.x; i < ms; i += PK_THREADS) {
+        const double v = S.sub[i];
+        int less = 0, eq = 0;
+        for (int j = 0; j < ms; ++j) {
+            const double w = S.sub[j];
+            less += (w < v); eq += (w == v);
+        }
+        if (less <= ra && ra < less + eq) S.r1 = v;        // all writers write the same value
+        if (less <= rb && rb < less + eq) S.r2 = v;
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(PK_THREADS) peaks2_kernel(const double* __restrict__ corr, int nc,
+                                                            int32_t* __restrict__ peaks, int32_t* __restrict__ npeaks,
+                                                            double* __restrict__ stats)
+{
+    extern __shared__ __align__(16) unsigned char pk_raw[];
+    PkUnion& U = *reinterpret_cast<PkUnion*>(pk_raw);
+    Pk2Shared& S = U.f;
+    const int cb = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const double* c = corr + (long long)cb * nc;
+    int32_t* pk = peaks + (long long)cb * PEAK_LIMIT;
+    if (nc < PK2_MIN_NC) { peaks_row_general(c, nc, cb, pk, npeaks, stats, U.g); return; }
+    const int k2 = nc >> 1, k1 = (nc - 1) >> 1;
+
+    // ---- pass A: histogram + speculative gather
+    for (int b = tid; b < SEL_BINS; b += PK_THREADS) S.hist[b] = 0;
+    if (tid == 0) { S.nbuf = 0; S.nsub = 0; S.ncand = 0; S.ntop = 0; S.nkeep = 0; S.below_cnt = 0; S.npeaks = 0; }
+    __syncthreads();
+    // PK2_UNROLL loads in flight per thread: with 1024 threads per SM the streaming passes need that to reach HBM speed
+    for (int i0 = tid; i0 < nc; i0 += PK_THREADS * PK2_UNROLL) {
+        double vv[PK2_UNROLL];
+#pragma unroll
+        for (int u = 0; u < PK2_UNROLL; ++u) { const int i = i0 + u * PK_THREADS; vv[u] = (i < nc) ? __ldg(c + i) : 0.0; }
+#pragma unroll
+        for (int u = 0; u < PK2_UNROLL; ++u) {
+            const int i = i0 + u * PK_THREADS;
+            if (i >= nc) break;
+            const double v = vv[u];
+            const int b = sel_bin<0>(v);
+            atomicAdd(&S.hist[b], 1u);
+            if (b >= PK2_SPEC_LO && b < PK2_SPEC_HI) {
+                const unsigned int p = atomicAdd(&S.nbuf, 1u);
+                if (p < (unsigned)PK2_CAP) S.buf[p] = v;
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {            // exclusive prefix over the 2048 bins: 64 bins per lane
+        unsigned int loc = 0;
+        for (int b = lane * 64; b < lane * 64 + 64; ++b) loc += S.hist[b];
+        unsigned int inc = loc;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        unsigned int run = inc - loc;
+        for (int b = lane * 64; b < lane * 64 + 64; ++b) { S.pref[b] = run; run += S.hist[b]; }
+        if (lane == 31) S.pref[SEL_BINS] = run;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        // bins of ranks k1, k2 (binary search on the prefix: largest b with pref[b] <= k)
+        int lo = 0, hi = SEL_BINS - 1;
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (S.pref[mid] <= (unsigned)k1) lo = mid; else hi = mid - 1; }
+        S.b1 = lo; S.below1 = S.pref[lo];
+        lo = S.b1; hi = SEL_BINS - 1;
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (S.pref[mid] <= (unsigned)k2) lo = mid; else hi = mid - 1; }
+        S.b2 = lo;
+        // smallest bin tb with count(bins >= tb) >= min(5, nc): as in median_of<0>
+        const unsigned int want = 5u;
+        int tb = SEL_BINS - 1;
+        for (; tb > 0; --tb) if ((unsigned)nc - S.pref[tb] >= want) break;
+        S.topbin = tb; S.topcount = (unsigned)nc - S.pref[tb];
+        const unsigned int inbins = S.hist[S.b1] + ((S.b2 != S.b1) ? S.hist[S.b2] : 0u);
+        S.ok = (S.b1 >= PK2_SPEC_LO && S.b2 < PK2_SPEC_HI && S.nbuf <= (unsigned)PK2_CAP && inbins <= (unsigned)PK2_SUB) ? 1 : 0;
+    }
+    __syncthreads();
+    if (!S.ok) { __syncthreads(); peaks_row_general(c, nc, cb, pk, npeaks, stats, U.g); return; }
+    {
+        const int b1 = S.b1, b2 = S.b2;
+        const int m = (int)S.nbuf;
+        for (int i = tid; i < m; i += PK_THREADS) {
+            const double v = S.buf[i];
+            const int bb = sel_bin<0>(v);
+            if (bb == b1 || bb == b2) S.sub[atomicAdd(&S.nsub, 1u)] = v;
+        }
+        __syncthreads();
+        pk2_select2(S, (int)S.nsub, k1 - (int)S.below1, k2 - (int)S.below1);
+    }
+    const double med = (S.r1 + S.r2) * 0.5;
+    const int topbin = S.topbin;
+    const bool want_top = S.topcount <= (unsigned)PK2_NCAND;
+
+    // ---- MAD bracket from the corr histogram: |v - med| <= m/1024 certainly holds inside bins (bl+2 .. bh-2) and
+    //      certainly fails outside bins (bl-1 .. bh+1), bl/bh = bins of med -+ m/1024
+    if (tid == 0) {
+        const double smed = (med + 1.0) * 1024.0;
+        auto P = [&](int b) -> unsigned int { return S.pref[b < 0 ? 0 : (b > SEL_BINS ? SEL_BINS : b)]; };
+        auto upper = [&](int m) -> unsigned int {
+            const int bl = (int)floor(smed - (double)m), bh = (int)floor(smed + (double)m);
+            return P(bh + 2) - P(bl - 1);
+        };
+        auto lower = [&](int m) -> unsigned int {
+            const int bl = (int)floor(smed - (double)m), bh = (int)floor(smed + (double)m);
+            return (bh - 1 > bl + 2) ? (P(bh - 1) - P(bl + 2)) : 0u;
+        };
+        int mlo = -1;
+        if (upper(0) <= (unsigned)k1) {
+            int lo = 0, hi = 2 * SEL_BINS;
+            while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (upper(mid) <= (unsigned)k1) lo = mid; else hi = mid - 1; }
+            mlo = lo;
+        }
+        int lo = 0, hi = 2 * SEL_BINS + 4;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (lower(mid) >= (unsigned)k2 + 1u) hi = mid; else lo = mid + 1; }
+        S.r_lo = (mlo < 0) ? -1.0 : (double)mlo / 1024.0;
+        S.r_hi = (double)lo / 1024.0;
+        const double t0 = med + (4.5 * 1.4826) * (((mlo < 0) ? 0.0 : S.r_lo) + 1e-12);
+        S.thr_lo = (t0 < 0.95 ? t0 : 0.95) - 1e-9;
+        S.nbuf = 0; S.nsub = 0;
+    }
+    __syncthreads();
+    const double r_lo = S.r_lo, r_hi = S.r_hi, thr_lo = S.thr_lo;
+
+    // ---- pass B
+    {
+        unsigned int mine = 0;
+        for (int i0 = tid; i0 < nc; i0 += PK_THREADS * PK2_UNROLL) {
+          double vv[PK2_UNROLL];
+#pragma unroll
+          for (int u = 0; u < PK2_UNROLL; ++u) { const int i = i0 + u * PK_THREADS; vv[u] = (i < nc) ? __ldg(c + i) : 0.0; }
+#pragma unroll
+          for (int u = 0; u < PK2_UNROLL; ++u) {
+            const int i = i0 + u * PK_THREADS;
+            if (i >= nc) break;
+            const double v = vv[u];
+            const double d = sel_value<1>(v, med);
+            if (d <= r_lo) ++mine;
+            else if (d <= r_hi) {
+                const unsigned int p = atomicAdd(&S.nbuf, 1u);
+                if (p < (unsigned)PK2_CAP) S.buf[p] = d;
+            }
+            if (v >= thr_lo) {
+                const unsigned int p = atomicAdd(&S.ncand, 1u);
+                if (p < (unsigned)PK2_NCAND) S.cand[p] = i;
+            }
+            if (want_top && sel_bin<0>(v) >= topbin) {
+                const unsigned int p = atomicAdd(&S.ntop, 1u);
+                if (p < (unsigned)PK2_NCAND) S.top[p] = i;
+            }
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+        if (lane == 0 && mine) atomicAdd(&S.below_cnt, mine);
+    }
+    for (int b = tid; b < 256; b += PK_THREADS) S.hist[b] = 0;
+    __syncthreads();
+    const int mb = (int)S.nbuf;
+    const int ra0 = k1 - (int)S.below_cnt, rb0 = k2 - (int)S.below_cnt;
+    if (mb > PK2_CAP || S.ncand > (unsigned)PK2_NCAND || ra0 < 0 || rb0 >= mb) {
+        __syncthreads(); peaks_row_general(c, nc, cb, pk, npeaks, stats, U.g); return;
+    }
+    // refine inside the bracket: 256 monotone sub-bins over (base, r_hi]
+    const double base = r_lo < 0.0 ? 0.0 : r_lo;
+    const double scale = 256.0 / (r_hi - base);
+    auto subbin = [&](double d) -> int { const double t = (d - base) * scale; return t >= 255.0 ? 255 : (t <= 0.0 ? 0 : (int)t); };
+    for (int i = tid; i < mb; i += PK_THREADS) atomicAdd(&S.hist[subbin(S.buf[i])], 1u);
+    __syncthreads();
+    if (tid == 0) {
+        unsigned int acc = 0;
+        int b = 0;
+        for (; b < 256; ++b) { if (acc + S.hist[b] > (unsigned)ra0) break; acc += S.hist[b]; }
+        S.b1 = b; S.below1 = acc;
+        int b2 = b;
+        unsigned int acc2 = acc;
+        for (; b2 < 256; ++b2) { if (acc2 + S.hist[b2] > (unsigned)rb0) break; acc2 += S.hist[b2]; }
+        S.b2 = b2;
+        const unsigned int inbins = S.hist[b] + ((b2 != b) ? S.hist[b2] : 0u);
+        S.ok = (inbins <= (unsigned)PK2_SUB) ? 1 : 0;
+    }
+    __syncthreads();
+    if (!S.ok) { __syncthreads(); peaks_row_general(c, nc, cb, pk, npeaks, stats, U.g); return; }
+    {
+        const int b1 = S.b1, b2 = S.b2;
+        for (int i = tid; i < mb; i += PK_THREADS) {
+            const double d = S.buf[i];
+            const int bb = subbin(d);
+            if (bb == b1 || bb == b2) S.sub[atomicAdd(&S.nsub, 1u)] = d;
+        }
+        __syncthreads();
+        pk2_select2(S, (int)S.nsub, ra0 - (int)S.below1, rb0 - (int)S.below1);
+    }
+    const double mad = (S.r1 + S.r2) * 0.5 + 1e-12;
+    double thr = med + (4.5 * 1.4826) * mad;
+    thr = thr < 0.95 ? thr : 0.95;
+
+    // ---- candidates >= thr, ascending index order, NMS until 25 peaks (rtwm/detector.py:87-97, 108-110)
+    for (int t = tid; t < PEAK_LIMIT; t += PK_THREADS) pk[t] = -1;
+    const int ncand = (int)S.ncand;
+    for (int q = tid; q < ncand; q += PK_THREADS) {
+        const int i = S.cand[q];
+        if (c[i] >= thr) S.sorted[atomicAdd(&S.nkeep, 1u)] = i;
+    }
+    __syncthreads();
+    const int nk = (int)S.nkeep;
+    for (int q = tid; q < nk; q += PK_THREADS) {          // rank by counting -> cand[] ascending
+        const int i = S.sorted[q];
+        int r = 0;
+        for (int j = 0; j < nk; ++j) r += (S.sorted[j] < i);
+        S.cand[r] = i;
+    }
+    __syncthreads();
+    for (int q0 = 0; q0 < nk; q0 += PK_THREADS / 32) {
+        const int q = q0 + warp;
+        bool pass = false;
+        if (q < nk) {
+            const int i = S.cand[q];
+            const double v = c[i];
+            const int lo = max(0, i - NMS_HALF), hi = min(nc, i + NMS_HALF + 1);
+            bool bigger = false;
+            for (int j = lo + lane; j < hi; j += 32) bigger |= (c[j] > v);
+            pass = !__any_sync(0xffffffffu, bigger);
+        }
+        if (lane == 0) S.pass[warp] = pass ? 1 : 0;
+        __syncthreads();
+        if (tid == 0) {
+            int np0 = S.npeaks;
+            for (int w = 0; w < PK_THREADS / 32 && q0 + w < nk; ++w)
+                if (S.pass[w]) { if (np0 < PEAK_LIMIT) pk[np0] = S.cand[q0 + w]; ++np0; }
+            S.npeaks = np0;
+        }
+        __syncthreads();
+        if (S.npeaks >= PEAK_LIMIT) break;
+    }
+    int np = S.npeaks;
+    int fallback = 0;
+    if (np == 0) {
+        // ---- top-k fallback, k = min(5, nc): descending value (ties: larger index first)
+        if (!want_top || S.ntop > (unsigned)PK2_NCAND) { __syncthreads(); peaks_row_general(c, nc, cb, pk, npeaks, stats, U.g); return; }
+        fallback = 1;
+        const int kf = nc < 5 ? nc : 5;
+        const int m = (int)S.ntop;
+        for (int q = tid; q < m; q += PK_THREADS) {
+            const int i = S.top[q];
+            const double v = c[i];
+            int r = 0;
+            for (int j = 0; j < m; ++j) {
+                const int ij = S.top[j];
+                const double w = c[ij];
+                r += (w > v) || (w == v && ij > i);
+            }
+            if (r < kf) pk[r] = i;
         }
         np = kf;
     }
@@ -1130,15 +1441,22 @@ int es_rx_ncc(const double* y, int nclips, int n, double* corr, void* stream)
     return ES_OK;
 }
 
+static int g_peaks_general = 0;
+void es_rx_peaks_force_general(int on) { g_peaks_general = on ? 1 : 0; }
+
 int es_rx_peaks(const double* corr, int nclips, int nc, int32_t* peaks, int32_t* npeaks, double* stats, void* stream)
 {
     if (nclips <= 0) return ES_OK;
     static int configured = 0;
     if (!configured) {
         ES_CUDA_OK(cudaFuncSetAttribute(peaks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PeakShared)));
+        ES_CUDA_OK(cudaFuncSetAttribute(peaks2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PkUnion)));
         configured = 1;
     }
-    peaks_kernel<<<nclips * NBANDS, PK_THREADS, sizeof(PeakShared), (cudaStream_t)stream>>>(corr, nc, peaks, npeaks, stats);
+    if (g_peaks_general)
+        peaks_kernel<<<nclips * NBANDS, PK_THREADS, sizeof(PeakShared), (cudaStream_t)stream>>>(corr, nc, peaks, npeaks, stats);
+    else
+        peaks2_kernel<<<nclips * NBANDS, PK_THREADS, sizeof(PkUnion), (cudaStream_t)stream>>>(corr, nc, peaks, npeaks, stats);
     ES_CUDA_OK(cudaGetLastError());
     return ES_OK;
 }

@@ -90,6 +90,11 @@ def ncc(y: torch.Tensor) -> torch.Tensor:
 K3_LONG_MIN = 1 << 21      # correlation length from which the multi-CTA form of K3 is used
 
 
+def peaks_force_general(on: bool):
+    """Test hook: route every row of K3 through the general multi-pass form (same results as the two-pass form)."""
+    N.lib().es_rx_peaks_force_general(C.c_int(1 if on else 0))
+
+
 def peaks(corr: torch.Tensor):
     """corr float64[B,4,nc] -> (peaks i32[B,4,25] (-1 padded), npeaks i32[B,4], stats f64[B,4,4] =
     med, mad, thr, used_fallback) (K3).  Long recordings (nc >= 2^21) take the multi-CTA form."""

@@ -67,6 +67,9 @@ int es_rx_ncc(const double* y, int nclips, int n, double* corr /*[clips][4][n-62
  * stats = med, mad, thr, used_fallback */
 int es_rx_peaks(const double* corr, int nclips, int nc, int32_t* peaks /*[clips][4][25]*/,
                 int32_t* npeaks /*[clips][4]*/, double* stats /*[clips][4][4]*/, void* stream);
+/* test hook: on != 0 makes es_rx_peaks run every row through the general multi-pass form instead of the two-pass
+ * form (the two give identical results; tests compare them) */
+void es_rx_peaks_force_general(int on);
 /* K3 for one LONG recording: same outputs, every pass spread over many CTAs; *overflow_dev != 0 means a
  * gather buffer overflowed (degenerate data) and the caller must fall back to es_rx_peaks */
 size_t es_rx_peaks_long_scratch_bytes(int nclips, int nc);

@@ -176,6 +176,51 @@ def test_batch_matches_single_and_details(env):
             assert [c for _, c in r.attempts[bi]] == list(G[f"{n}/b{bi}/att_ctr"])
 
 
+def test_peaks_two_pass_equals_general_form(env):
+    """K3's two-pass form (histogram + speculative gather, bracketed MAD, candidate NMS) against the general
+    multi-pass form on ordinary and adversarial correlation rows: identical peaks, counts and statistics."""
+    torch, rx_gpu, detector, clips, taps = env
+    rng = np.random.default_rng(123)
+    nc = 143938
+    rows = []
+    rows.append(rng.normal(0, 0.126, nc))                                  # plain noise row (fallback top-5 likely)
+    r = rng.normal(0, 0.126, nc); r[5000::1215] = 0.8; rows.append(r)      # 115 strong peaks -> 25 kept
+    r = rng.normal(0, 0.05, nc); r[[100, 700, 1300, 90000]] = [0.6, 0.7, 0.65, 0.9]; rows.append(r)   # NMS interplay
+    r = rng.normal(0.002, 0.126, nc); rows.append(r)                       # median off-centre but inside the spec bins
+    r = rng.normal(0.2, 0.1, nc); rows.append(r)                           # median outside the spec bins -> general
+    rows.append(np.zeros(nc))                                              # silence: every value equal
+    r = np.zeros(nc); r[::2] = 1e-3; rows.append(r)                        # two-valued
+    r = rng.normal(0, 1e-5, nc); rows.append(r)                            # very narrow: bracket collapses
+    r = rng.normal(0, 0.126, nc); r[1000:1040] = 0.97; rows.append(r)      # plateau above the 0.95 cap
+    r = rng.uniform(-1, 1, nc); rows.append(r)                             # flat distribution
+    r = np.round(rng.normal(0, 0.126, nc), 3); rows.append(r)              # heavy ties
+    r = rng.normal(0, 0.126, nc); r[0:nc - 1:2] = r[1:nc:2]; rows.append(r)      # every value twice
+    while len(rows) % 4:
+        rows.append(rng.normal(0, 0.1, nc))
+    corr = torch.from_numpy(np.clip(np.stack(rows), -1, 1).reshape(-1, 4, nc)).cuda()
+    try:
+        rx_gpu.peaks_force_general(True)
+        pk0, np0, st0 = (t.cpu().numpy() for t in rx_gpu.peaks(corr))
+    finally:
+        rx_gpu.peaks_force_general(False)
+    pk1, np1, st1 = (t.cpu().numpy() for t in rx_gpu.peaks(corr))
+    assert (np0 == np1).all()
+    assert (pk0 == pk1).all()
+    assert (st0 == st1).all()          # med, mad, thr, fallback flag: bit-identical
+    # and a whole batch of detector-produced rows
+    names = ["chirp_aa", "noise_44", "bench_17", "plain_noise"]
+    x = torch.from_numpy(np.stack([clips[n][0] for n in names])).cuda()
+    cr = rx_gpu.ncc(rx_gpu.bandpass(x))
+    try:
+        rx_gpu.peaks_force_general(True)
+        a = [t.cpu().numpy() for t in rx_gpu.peaks(cr)]
+    finally:
+        rx_gpu.peaks_force_general(False)
+    b = [t.cpu().numpy() for t in rx_gpu.peaks(cr)]
+    for u, w in zip(a, b):
+        assert (u == w).all()
+
+
 def test_batch_schedules_agree(env):
     """The tapered multi-sub-batch schedule, per-sub-batch key banks and the pinned-host input path give the
     same sync offsets, attempt lists and verdicts as one big sub-batch of device-resident clips."""
