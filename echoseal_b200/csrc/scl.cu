@@ -32,6 +32,7 @@ namespace es {
 __constant__ uint32_t c_frozen[32];      // bit (i&31) of word (i>>5): 1 = frozen
 __constant__ uint16_t c_datapos[1024];   // ascending un-frozen positions (K entries used)
 __constant__ int c_K;                    // info + CRC bits
+__device__ uint16_t d_datapos[1024];     // the same positions in global memory, for lane-indexed (divergent) reads
 // rate-0 node map per quad (bits 4q..4q+3): 0 = ordinary quad; v in 1..8 = first quad of a maximal aligned
 // all-frozen node of 4 << (v-1) bits; 255 = interior quad of such a node
 __constant__ uint8_t c_r0[256];
@@ -595,48 +596,57 @@ __device__ __forceinline__ uint32_t warp_transform(uint32_t x, int lane)
     return x;
 }
 
-__global__ void __launch_bounds__(128) scl_hard_kernel(const float* __restrict__ llr, int ncw, int neg_mode,
+// One warp per LLR row.  In neg_mode the row yields two codewords (+row: bit = llr > 0, -row: bit = llr < 0) from
+// one set of loads; all 32 coalesced row loads are issued before the first ballot.
+__global__ void __launch_bounds__(128) scl_hard_kernel(const float* __restrict__ llr, int nrows, int neg_mode,
                                                        uint8_t* __restrict__ hard_payload,
                                                        uint8_t* __restrict__ hard_crc)
 {
     const unsigned full = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (w >= ncw) return;
-    const int row = neg_mode ? (w >> 1) : w;
-    const float sgn = (neg_mode && (w & 1)) ? -1.0f : 1.0f;
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= nrows) return;
     const float* src = llr + (size_t)row * 1024;
     const int K = c_K;
     const int nbytes = (K - 8) >> 3;
-    uint32_t x = 0;
-#pragma unroll 4
-    for (int it = 0; it < 32; ++it) {
-        const uint32_t bal = __ballot_sync(full, sgn * __ldg(src + it * 32 + lane) > 0.0f);
-        if (lane == it) x = bal;
-    }
-    x = warp_transform(x, lane);
-    uint8_t* out = hard_payload + (size_t)w * nbytes;
-    uint8_t crcreg = 0, crcbits = 0;
-    const int nchunk = (K + 31) >> 5;
-    for (int c = 0; c < nchunk; ++c) {
-        const int q = c * 32 + lane;
-        const int pos = (q < K) ? c_datapos[q] : 0;
-        const uint32_t wv = __shfl_sync(full, x, pos >> 5);
-        const uint32_t b = (q < K) ? ((wv >> (pos & 31)) & 1u) : 0u;
-        const uint32_t word = __brev(__ballot_sync(full, b));   // bit q -> MSB-first
+    float v[32];
 #pragma unroll
-        for (int bb = 0; bb < 4; ++bb) {
-            const int byte_idx = c * 4 + bb;
-            const uint8_t byte = (uint8_t)(word >> (24 - 8 * bb));
-            if (byte_idx < nbytes) {
-                if (lane == bb) out[byte_idx] = byte;
-                crcreg = c_crc8[crcreg ^ byte];                 // uniform index: one constant-cache broadcast
-            } else if (byte_idx == nbytes) {
-                crcbits = byte;
+    for (int it = 0; it < 32; ++it) v[it] = __ldg(src + it * 32 + lane);
+    uint32_t xp = 0, xn = 0;
+#pragma unroll
+    for (int it = 0; it < 32; ++it) {
+        const uint32_t bp = __ballot_sync(full, v[it] > 0.0f);
+        const uint32_t bn = __ballot_sync(full, v[it] < 0.0f);      // -llr > 0
+        if (lane == it) { xp = bp; xn = bn; }
+    }
+    const int nvar = neg_mode ? 2 : 1;
+#pragma unroll 1
+    for (int var = 0; var < nvar; ++var) {
+        const int w = neg_mode ? (2 * row + var) : row;
+        const uint32_t x = warp_transform(var ? xn : xp, lane);
+        uint8_t* out = hard_payload + (size_t)w * nbytes;
+        uint8_t crcreg = 0, crcbits = 0;
+        const int nchunk = (K + 31) >> 5;
+        for (int c = 0; c < nchunk; ++c) {
+            const int q = c * 32 + lane;
+            const int pos = (q < K) ? d_datapos[q] : 0;             // per-lane index: a constant-bank read would serialise
+            const uint32_t wv = __shfl_sync(full, x, pos >> 5);
+            const uint32_t b = (q < K) ? ((wv >> (pos & 31)) & 1u) : 0u;
+            const uint32_t word = __brev(__ballot_sync(full, b));   // bit q -> MSB-first
+#pragma unroll
+            for (int bb = 0; bb < 4; ++bb) {
+                const int byte_idx = c * 4 + bb;
+                const uint8_t byte = (uint8_t)(word >> (24 - 8 * bb));
+                if (byte_idx < nbytes) {
+                    if (lane == bb) out[byte_idx] = byte;
+                    crcreg = c_crc8[crcreg ^ byte];                 // uniform index: one constant-cache broadcast
+                } else if (byte_idx == nbytes) {
+                    crcbits = byte;
+                }
             }
         }
+        if (lane == 0) hard_crc[w] = (crcreg == crcbits) ? 1 : 0;
     }
-    if (lane == 0) hard_crc[w] = (crcreg == crcbits) ? 1 : 0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -696,7 +706,7 @@ __global__ void __launch_bounds__(128) polar_encode_kernel(const uint8_t* __rest
         const int byte_idx = q >> 3;
         const uint8_t byte = (byte_idx < nbytes) ? __ldg(src + byte_idx) : crc;
         const uint32_t b = (byte >> (7 - (q & 7))) & 1u;
-        const int pos = c_datapos[q];
+        const int pos = d_datapos[q];
         if (b) atomicOr(&su[wl][pos >> 5], 1u << (pos & 31));
     }
     __syncwarp();
@@ -765,6 +775,7 @@ int es_polar_set_code(const uint8_t* frozen_host, int K)
     if (n != K) { set_error("es_polar_set_code: %d unfrozen positions != K=%d", n, K); return ES_EINVAL; }
     ES_CUDA_OK(cudaMemcpyToSymbol(c_frozen, words, sizeof(words)));
     ES_CUDA_OK(cudaMemcpyToSymbol(c_datapos, pos, sizeof(pos)));
+    ES_CUDA_OK(cudaMemcpyToSymbol(d_datapos, pos, sizeof(pos)));
     ES_CUDA_OK(cudaMemcpyToSymbol(c_K, &K, sizeof(int)));
     {
         // maximal aligned all-frozen nodes of >= 4 bits that do not start at bit 0 (bit 0 belongs to the spine)
@@ -820,8 +831,10 @@ int es_scl_hard(const float* llr, int ncw, int neg_mode, uint8_t* hard_payload, 
 {
     if (!g_code_ready) { set_error("es_scl_hard: call es_polar_set_code first"); return ES_ENOTREADY; }
     if (ncw <= 0) return ES_OK;
+    if (neg_mode && (ncw & 1)) { set_error("es_scl_hard: neg_mode takes 2 codewords per row, got ncw=%d", ncw); return ES_EINVAL; }
+    const int nrows = neg_mode ? ncw / 2 : ncw;
     const int wpb = 4;
-    scl_hard_kernel<<<(ncw + wpb - 1) / wpb, wpb * 32, 0, (cudaStream_t)stream>>>(llr, ncw, neg_mode, hard_payload, hard_crc);
+    scl_hard_kernel<<<(nrows + wpb - 1) / wpb, wpb * 32, 0, (cudaStream_t)stream>>>(llr, nrows, neg_mode, hard_payload, hard_crc);
     ES_CUDA_OK(cudaGetLastError());
     return ES_OK;
 }

@@ -13,13 +13,13 @@ constexpr int TX_FRAME = 1215, TX_PRE = 63, TX_HDR = 128;
 constexpr int TX_SYM_WORDS = 38;          // 1216 sign bits per frame
 
 // this translation unit's copy of the polar code layout (filled by es_polar_set_code via tx_set_code)
-__constant__ uint16_t c_datapos[1024];
+__device__ uint16_t d_datapos[1024];     // global memory: read with per-lane indices (a constant-bank read would serialise)
 __constant__ int c_K;
 static int g_tx_code_ready = 0;
 
 int tx_set_code(const uint16_t* pos, int K)
 {
-    ES_CUDA_OK(cudaMemcpyToSymbol(c_datapos, pos, sizeof(uint16_t) * 1024));
+    ES_CUDA_OK(cudaMemcpyToSymbol(d_datapos, pos, sizeof(uint16_t) * 1024));
     ES_CUDA_OK(cudaMemcpyToSymbol(c_K, &K, sizeof(int)));
     g_tx_code_ready = 1;
     return ES_OK;
@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(128) tx_frames_kernel(const uint8_t* __restric
         for (int q = lane; q < K; q += 32) {
             const int bi = q >> 3;
             const uint8_t byte = (bi < nbytes) ? __ldg(pay + bi) : crc;
-            if ((byte >> (7 - (q & 7))) & 1u) { const int pos = c_datapos[q]; atomicOr(&S.u[pos >> 5], 1u << (pos & 31)); }
+            if ((byte >> (7 - (q & 7))) & 1u) { const int pos = d_datapos[q]; atomicOr(&S.u[pos >> 5], 1u << (pos & 31)); }
         }
         __syncwarp();
         uint32_t x = tx_xform_word(S.u[lane]);
