@@ -1,6 +1,13 @@
 """Multi-GPU sharding of the path: clips / codewords / streams are independent, so the
 units are block-partitioned across ranks with NO collective on the data path; the only exchange is the
-final verdict gather.  Works with any torch.distributed backend (NCCL on the GPUs, gloo in the CPU tests)."""
+final verdict gather.  Works with any torch.distributed backend (NCCL on the GPUs, gloo in the CPU tests).
+
+One LONG recording (config 3) shards by BAND: the reference scans the four bands independently
+(rtwm/detector.py:44-53: one `_scan_band_multi_frame` per band, each with its own median / MAD threshold, NMS,
+25-peak limit and 400-try budget), so band i of the reference's order goes to rank i mod world and again the
+only exchange is the gather of the (verdict, latched nonce) records.  Splitting one band in TIME across GPUs
+(halo + all-reduced histograms for the global order statistics) is not built: a whole hour of
+audio is one 0.13 s pass on one GPU, less than the exchanges would cost."""
 from __future__ import annotations
 import numpy as np
 import torch
@@ -42,3 +49,51 @@ def verify_sharded(keys, audio, verify_fn, device=None) -> np.ndarray:
     lo, hi = shard_range(n, rank, world)
     local = verify_fn(keys[lo:hi], audio[lo:hi]) if hi > lo else np.zeros(0, bool)
     return gather_verdicts(local, n, device)
+
+
+def band_order(band_key: bytes):
+    """The reference's scan order: the hop-0 band first, then the rest in BAND_PLAN order (rtwm/detector.py:46-52)."""
+    from .utils import BAND_PLAN, choose_band
+    hop0 = tuple(choose_band(band_key, 0))
+    return [hop0] + [tuple(b) for b in BAND_PLAN if tuple(b) != hop0]
+
+
+def verify_recording_sharded(det, audio, fs_in: int, device=None) -> bool:
+    """`det.verify(audio, fs_in)` for ONE recording with its four band scans spread over the ranks.
+    `det` is a WatermarkDetector (same key on every rank); every rank passes the same audio.  Returns the same
+    verdict on every rank and latches `det.session_nonce` exactly as the sequential scan would: from the first
+    band, in the reference's order, that accepted a frame."""
+    rank = dist.get_rank() if (dist.is_available() and dist.is_initialized()) else 0
+    world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+    order = band_order(det._band_key)
+    signal = det._resample(np.asarray(audio), fs_in)
+    if isinstance(signal, torch.Tensor):
+        signal = signal.detach().cpu().numpy()
+    signal = np.asarray(signal, dtype=np.float32).reshape(-1)
+    rec = np.zeros((len(order), 10), np.uint8)           # per band: verdict, has_nonce, nonce[8]
+    entry_nonce = det.session_nonce
+    for i, band in enumerate(order):
+        if i % world != rank:
+            continue
+        det.session_nonce = entry_nonce                  # every band scan starts from the caller's latch state
+        ok = bool(det._scan_band_multi_frame(signal, band))
+        rec[i, 0] = 1 if ok else 0
+        if ok and det.session_nonce:
+            rec[i, 1] = 1
+            rec[i, 2:] = np.frombuffer(det.session_nonce, np.uint8)
+    det.session_nonce = entry_nonce
+    if world > 1:
+        dev = device if device is not None else torch.device("cpu")
+        mine = torch.from_numpy(rec).to(dev)
+        out = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(out, mine)
+        rec = np.zeros_like(rec)
+        for r in range(world):
+            part = out[r].cpu().numpy()
+            rec[r::world] = part[r::world]               # rank r filled rows r, r + world, ...
+    for i in range(len(order)):                          # first accepting band in the reference's order wins
+        if rec[i, 0]:
+            if rec[i, 1]:
+                det.session_nonce = rec[i, 2:].tobytes()
+            return True
+    return False

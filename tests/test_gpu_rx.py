@@ -221,6 +221,18 @@ def test_peaks_two_pass_equals_general_form(env):
         assert (u == w).all()
 
 
+def test_band_sharded_recording_equals_verify(env):
+    """sharding.verify_recording_sharded at world size 1 (no process group): same verdict and nonce latch as
+    WatermarkDetector.verify; the rank / gather logic itself is covered by the gloo tests."""
+    torch, rx_gpu, detector, clips, taps = env
+    from echoseal_b200.sharding import verify_recording_sharded
+    for n in ("chirp_aa", "plain_noise", "short_1s"):
+        audio, key = clips[n]
+        a, b = detector.WatermarkDetector(key), detector.WatermarkDetector(key)
+        assert verify_recording_sharded(a, audio, 48000) == b.verify(audio, 48000)
+        assert a.session_nonce == b.session_nonce
+
+
 def test_batch_schedules_agree(env):
     """The tapered multi-sub-batch schedule, per-sub-batch key banks and the pinned-host input path give the
     same sync offsets, attempt lists and verdicts as one big sub-batch of device-resident clips."""

@@ -61,3 +61,68 @@ def test_shard_range_properties():
             assert all(ends[i][1] == ends[i + 1][0] for i in range(w - 1))
             sizes = [b - a for a, b in ends]
             assert max(sizes) - min(sizes) <= 1
+
+
+class _FakeDetector:
+    """Duck-typed WatermarkDetector for the band-sharding logic: band scans are table look-ups."""
+    def __init__(self, band_key, accept, nonces):
+        self._band_key, self._accept, self._nonces = band_key, accept, nonces
+        self.session_nonce = None
+        self.scanned = []
+    def _resample(self, audio, fs_in):
+        return np.asarray(audio, np.float32)
+    def _scan_band_multi_frame(self, signal, band):
+        self.scanned.append(tuple(band))
+        assert self.session_nonce is None                 # each band scan starts from the entry latch state
+        if tuple(band) in self._accept:
+            self.session_nonce = self._nonces[tuple(band)]
+            return True
+        return False
+
+
+def _band_worker(rank, world, port, accept_idx, q):
+    sys.path.insert(0, ROOT)
+    from echoseal_b200.sharding import band_order, verify_recording_sharded
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    key = bytes(range(32))
+    order = band_order(key)
+    nonces = {b: bytes([65 + i]) * 8 for i, b in enumerate(order)}
+    det = _FakeDetector(key, {order[i] for i in accept_idx}, nonces)
+    v = verify_recording_sharded(det, np.zeros(100, np.float32), 48000)
+    q.put((rank, v, det.session_nonce, [order.index(b) for b in det.scanned]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,accept_idx", [(2, ()), (2, (3,)), (2, (1, 2)), (3, (2,)), (4, (0, 3))])
+def test_long_recording_band_sharding_gloo(world, accept_idx):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() + world * 17 + sum(accept_idx) * 7 + len(accept_idx)) % 2000
+    procs = [ctx.Process(target=_band_worker, args=(r, world, port, accept_idx, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    scanned = []
+    for rank, v, nonce, idx in sorted(res):
+        assert v == (len(accept_idx) > 0)                 # same verdict on every rank
+        want = bytes([65 + min(accept_idx)]) * 8 if accept_idx else None
+        assert nonce == want                              # latch = first accepting band in the reference order
+        assert idx == [i for i in range(4) if i % world == rank]
+        scanned += idx
+    assert sorted(scanned) == [0, 1, 2, 3]                # every band scanned exactly once
+
+
+def test_band_order_is_reference_order():
+    sys.path.insert(0, ROOT)
+    from echoseal_b200.sharding import band_order
+    from echoseal_b200.utils import BAND_PLAN, choose_band
+    for k in (bytes(32), bytes(range(32)), b"\xaa" * 32):
+        o = band_order(k)
+        assert o[0] == tuple(choose_band(k, 0)) and sorted(o) == sorted(tuple(b) for b in BAND_PLAN)
+        assert o[1:] == [tuple(b) for b in BAND_PLAN if tuple(b) != o[0]]

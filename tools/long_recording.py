@@ -1,5 +1,7 @@
 """configs[2]: one 1-hour 44.1 kHz synthetic recording with +-5 % time-scale and -15 dB SNR noise through
-WatermarkDetector.verify (full +-200 counter fallback search, 400-try budget per band).  Prints one JSON line."""
+WatermarkDetector.verify (full +-200 counter fallback search, 400-try budget per band).  Prints one JSON line.
+Under torchrun (WORLD_SIZE > 1) the four band scans are spread over the ranks
+(echoseal_b200.sharding.verify_recording_sharded) and rank 0 prints the line, with the sequential verdict beside it."""
 import json, os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -9,7 +11,14 @@ from echoseal_b200 import rx_gpu, embedder, detector, _native as N
 def main():
     hours = float(sys.argv[1]) if len(sys.argv) > 1 else 1.0
     scale = float(sys.argv[2]) if len(sys.argv) > 2 else 1.05
-    dev = torch.device("cuda", 0)
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
     n48 = int(hours * 3600 * 48000)
     key = bench.bench_key(2024)
     g = torch.Generator(device=dev).manual_seed(2024)
@@ -36,11 +45,25 @@ def main():
     torch.cuda.synchronize(); dt = time.perf_counter() - t1
     kt = {k: float(sum(a.elapsed_time(b) for a, b in v)) for k, v in N.KERNEL_TIMES.items()}
     r = rx.last_result
+    sharded = None
+    if world > 1:
+        from echoseal_b200.sharding import verify_recording_sharded
+        rx2 = detector.WatermarkDetector(key, list_size=8)
+        dist.barrier(); torch.cuda.synchronize(); t2 = time.perf_counter()
+        ok2 = verify_recording_sharded(rx2, audio, 44100, device=dev)
+        torch.cuda.synchronize(); dist.barrier(); dt2 = time.perf_counter() - t2
+        sharded = {"world": world, "verdict": bool(ok2), "verify_seconds": dt2, "equals_sequential": bool(ok2) == bool(ok)}
+        if rank != 0:
+            dist.destroy_process_group()
+            return
     print(json.dumps({"workload": f"configs[2]: {hours} h 44.1 kHz recording, time-scale x{num}/{den}, -15 dB SNR",
                       "samples_44k1": int(audio.size), "verdict": bool(ok), "verify_seconds": dt,
                       "audio_seconds_per_second": audio.size / 44100 / dt, "scl_decodes": int(r.n_scl),
                       "attempts_per_band": [len(a) for a in r.attempts], "npeaks": [int(v) for v in r.npeaks],
-                      "thr": [float(v) for v in r.stats[:, 2]], "kernel_ms": kt, "generate_seconds": t_gen}))
+                      "thr": [float(v) for v in r.stats[:, 2]], "kernel_ms": kt, "generate_seconds": t_gen,
+                      "band_sharded": sharded}))
+    if world > 1:
+        dist.destroy_process_group()
 
 if __name__ == "__main__":
     main()
