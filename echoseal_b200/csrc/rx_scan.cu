@@ -37,7 +37,7 @@ static int g_rx_ready = 0;
 // of scipy's lfilter, the 4 x 8 states in registers (four independent recurrences per lane hide the DFMA
 // latency); chunks other than the first start from zero state BP_WARM samples early (the filter's impulse
 // response has decayed below 1e-12 by then; samples before the clip start are zeros, which keep the zero state
-// exactly).  The chunk length is chosen per call so that a (clip) fills whole warps (144 000 samples -> 64
+// exactly).  The chunk length depends on n only and is chosen so that a clip fills whole warps (144 000 samples -> 64
 // chunks of 2250).  A warp owns 32 consecutive chunks and moves data through shared-memory tiles so that every
 // global access is a full row (128-byte input, 256-byte output); the input tile of the next step is in flight
 // (cp.async into the other half of a double buffer) while the current one is filtered, and it is read from HBM
@@ -1403,25 +1403,13 @@ int es_rx_bandpass(const float* x, int nclips, int n, long long x_stride, double
 {
     if (!g_rx_ready) { set_error("es_rx_bandpass: call es_rx_set_filters first"); return ES_ENOTREADY; }
     if (nclips <= 0 || n <= 0) return ES_OK;
-    // chunk length: about BP_CHUNK, such that a clip is a whole number of 32-chunk warps; among 1x..3x that many
-    // warps per clip pick the split with the least (waves over the resident warp slots) x (steps per warp)
-    static int slots = 0;
-    if (!slots) {
-        int per_sm = 0;
-        ES_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, bandpass_kernel<true>, BP_WARPS * 32, 0));
-        slots = sm_count() * (per_sm > 0 ? per_sm : 1) * BP_WARPS;
-    }
-    int g0 = (int)(((long long)n + 16LL * BP_CHUNK) / (32LL * BP_CHUNK));
-    if (g0 < 1) g0 = 1;
-    int groups = g0, ch = 0;
-    double best = 0.0;
-    for (int g = g0; g <= 3 * g0; ++g) {
-        int c = (int)(((long long)n + 32LL * g - 1) / (32LL * g));
-        c = (c + 15) & ~15;                                // rows of y start on 128-byte lines
-        const long long units = (long long)nclips * g;
-        const double cost = (double)((units + slots - 1) / slots) * (double)(BP_WARM + c);
-        if (g == g0 || cost < best) { best = cost; groups = g; ch = c; }
-    }
+    // chunk length: about BP_CHUNK, such that a clip is a whole number of 32-chunk warps.  A function of n ONLY:
+    // the chunk boundaries decide where the (4e-13) warm-up truncation falls, so a clip's filtered samples -- and
+    // everything downstream -- are bit-identical whatever batch it is verified in.
+    int groups = (int)(((long long)n + 16LL * BP_CHUNK) / (32LL * BP_CHUNK));
+    if (groups < 1) groups = 1;
+    int ch = (int)(((long long)n + 32LL * groups - 1) / (32LL * groups));
+    ch = (ch + 15) & ~15;                                  // rows of y start on 128-byte lines
     const long long warps = (long long)nclips * groups;
     const unsigned grid = (unsigned)((warps + BP_WARPS - 1) / BP_WARPS);
     if (g_bp_oddz) bandpass_kernel<true><<<grid, BP_WARPS * 32, 0, (cudaStream_t)stream>>>(x, nclips, n, x_stride, y, ch, groups);

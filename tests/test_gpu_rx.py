@@ -1,6 +1,7 @@
 """GPU parity of the RX scan path (K1-K5 + host orchestration) through the C-ABI against the
 oracle (oracle/detector_oracle.py) and the reference-generated golden vectors."""
 import os
+import sys
 import numpy as np
 import pytest
 
@@ -340,3 +341,36 @@ def test_positive_path_matches_reference_golden(env):
         hok, hval, hscore = rx._decode_header(sym, choose_band(key, ctr))
         assert (float(hok), float(hval)) == (P[pre + "hdr"][0], P[pre + "hdr"][1])
         assert abs(hscore - P[pre + "hdr"][2]) <= 2e-3 * abs(P[pre + "hdr"][2])
+
+
+def test_full_size_batch_properties(env):
+    """BASELINE configs[1] at full size (10 000 x 3 s clips, one key per clip): size-independent properties of
+    the whole RX path.  (i) permutation equivariance: verifying the batch in another clip order and with another
+    sub-batch schedule gives the permuted sync offsets, thresholds, attempt lists and verdicts; (ii) the
+    un-watermarked clips (every 5th) and the watermarked ones all end False (the reference
+    does not decode its own embedder) with the 400-try budget respected per band; (iii) spot parity: 6 clips
+    of the batch against the CPU oracle (sync offsets, attempted counters)."""
+    torch, rx_gpu, detector, clips, taps = env
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    from oracle import detector_oracle as do
+    dev = torch.device("cuda", 0)
+    B = 10_000
+    keys, _, audio = bench.make_clips_gpu(0, B, dev)
+    v1, r1 = detector.verify_batch(keys, audio, details=True, sub_batch=1000)
+    perm = torch.from_numpy(np.random.default_rng(5).permutation(B)).to(dev)
+    pk = perm.cpu().numpy()
+    v2, r2 = detector.verify_batch([keys[i] for i in pk], audio[perm], details=True, sub_batch=1700)
+    assert not v1.any() and not v2.any()
+    for j in range(B):
+        a, b = r1[pk[j]], r2[j]
+        assert (a.peaks == b.peaks).all() and (a.npeaks == b.npeaks).all()
+        assert (a.stats == b.stats).all()
+        assert a.attempts == b.attempts
+    per_band = np.array([[len(x) for x in r.attempts] for r in r1])
+    assert per_band.max() <= 400 and per_band.sum() * 4 == sum(r.n_scl for r in r1)
+    for i in (0, 3, 4, 4999, 7777, 9999):
+        ok, det = do.verify(audio[i].cpu().numpy(), keys[i], list_size=8, return_details=True)
+        assert ok == bool(v1[i]) and det["n_scl"] == r1[i].n_scl
+        for bi in range(4):
+            assert [(int(s), int(c)) for s, c in det["attempts"].get(bi, [])] == r1[i].attempts[bi]
