@@ -1063,8 +1063,8 @@ constexpr int FR_THREADS = 256;
 constexpr int MF_MAX = NPAY + 2 * MAXH;      // upper bound of conv length we keep
 
 struct FrameShared {
-    float hs[MAXH];
-    float frame[FRAME_LEN];
+    double hs[MAXH + 8];             // taps (zero-padded by 4 on both sides) and frame widened once: float->double
+    double frame[FRAME_LEN];         // conversions run on the quarter-rate unit, two per DFMA would bound the kernel
     float mf[MF_MAX];
     double pre[MF_MAX + 1];
     float score[2 * MAXH + 64];
@@ -1073,13 +1073,29 @@ struct FrameShared {
     int best;
 };
 
-__device__ __forceinline__ float conv_at(const float* __restrict__ sig, int nsig, const float* __restrict__ h, int nh, int t)
+// out[t - tbase] = np.convolve(sig, h, 'full')[t] = sum_k sig[k] * h[t-k] for t in [tbase, tbase + nout), fp64
+// accumulation in ascending k (sig, h hold float32 values; h is zero outside [0, nh), 4 zeros readable on
+// each side).  Four consecutive outputs per thread: one sample load and one tap load feed four DFMAs; the
+// zero taps only add exact zeros, so every output equals its own k-ascending sum.
+__device__ __forceinline__ void conv_block(const double* __restrict__ sig, int nsig, const double* __restrict__ h, int nh,
+                                           int tbase, int nout, float* __restrict__ out)
 {
-    // np.convolve(sig, h, 'full')[t] = sum_k sig[k] * h[t-k]
-    const int k0 = max(0, t - (nh - 1)), k1 = min(nsig - 1, t);
-    double acc = 0.0;
-    for (int k = k0; k <= k1; ++k) acc = fma((double)sig[k], (double)h[t - k], acc);
-    return (float)acc;
+    for (int o = 4 * threadIdx.x; o < nout; o += 4 * FR_THREADS) {
+        const int t0 = tbase + o;
+        const int k0 = max(0, t0 - (nh - 1)), k1 = min(nsig - 1, t0 + 3);
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        double h0 = h[t0 - k0], h1 = h[t0 + 1 - k0], h2 = h[t0 + 2 - k0], h3 = h[t0 + 3 - k0];
+#pragma unroll 4
+        for (int k = k0; k <= k1; ++k) {
+            const double sk = sig[k];
+            a0 = fma(sk, h0, a0); a1 = fma(sk, h1, a1); a2 = fma(sk, h2, a2); a3 = fma(sk, h3, a3);
+            h3 = h2; h2 = h1; h1 = h0; h0 = h[t0 - k - 1];
+        }
+        out[o] = (float)a0;
+        if (o + 1 < nout) out[o + 1] = (float)a1;
+        if (o + 2 < nout) out[o + 2] = (float)a2;
+        if (o + 3 < nout) out[o + 3] = (float)a3;
+    }
 }
 
 __global__ void __launch_bounds__(FR_THREADS) frames_kernel(const double* __restrict__ y, int n,
@@ -1101,20 +1117,21 @@ __global__ void __launch_bounds__(FR_THREADS) frames_kernel(const double* __rest
         return;
     }
     const double* ys = y + (long long)cb * n + start;
-    for (int t = tid; t < FRAME_LEN; t += FR_THREADS) S.frame[t] = (float)ys[t];
+    for (int t = tid; t < FRAME_LEN; t += FR_THREADS) S.frame[t] = (double)(float)ys[t];   // frame.astype(float32)
     __syncthreads();
     const int nh = c_mf_len[band];
     const int mem = nh - 1;
-    for (int t = tid; t < nh; t += FR_THREADS) S.hs[t] = c_mf[band][t];   // divergent indices below: keep taps in smem
+    for (int t = tid; t < nh + 8; t += FR_THREADS)                       // divergent indices below: keep taps in smem
+        S.hs[t] = (t >= 4 && t < nh + 4) ? (double)c_mf[band][t - 4] : 0.0;
     __syncthreads();
-    const float* h = S.hs;
+    const double* h = S.hs + 4;
     // ======== header (rtwm/detector.py:452-515) ========
     {
         const int prefix = min(mem, PRE_L);
-        const float* sig = S.frame + PRE_L - prefix;
+        const double* sig = S.frame + PRE_L - prefix;
         const int nsig = prefix + HDR_L;
         const int nmf = nsig + nh - 1;
-        for (int t = tid; t < nmf; t += FR_THREADS) S.mf[t] = conv_at(sig, nsig, h, nh, t);
+        conv_block(sig, nsig, h, nh, 0, nmf, S.mf);
         __syncthreads();
         const int offset = mem + prefix;
         int maxs = min(HDR_L / 2 + prefix, 4 * nh);
@@ -1186,7 +1203,7 @@ __global__ void __launch_bounds__(FR_THREADS) frames_kernel(const double* __rest
     {
         const int pstart = PRE_L + HDR_L;
         const int prefix = min(mem, pstart);
-        const float* sig = S.frame + pstart - prefix;
+        const double* sig = S.frame + pstart - prefix;
         const int nsig = prefix + NPAY;
         const int nmf = nsig + nh - 1;
         const int offset = prefix + mem;
@@ -1196,7 +1213,7 @@ __global__ void __launch_bounds__(FR_THREADS) frames_kernel(const double* __rest
         const int wlen = wstop - wstart;
         const int base = offset - wstart;
         int guard = min(NPAY / 4, max(nh / 2, 24));
-        for (int t = tid; t < wlen; t += FR_THREADS) S.mf[t] = conv_at(sig, nsig, h, nh, wstart + t);
+        conv_block(sig, nsig, h, nh, wstart, wlen, S.mf);
         __syncthreads();
         // prefix sums of |mf| (fp64) -> score(s) = mean |mf_win[i0+guard : i0+n]|  (PN cancels under |.|, quirk 3)
         if (tid < 32) {
