@@ -827,18 +827,20 @@ template <int MODE> __device__ __forceinline__ int k3_sub(double val, int bin)
 
 // LEVEL 1: hist[cb][2048] over all values.  LEVEL 2: hist2[cb][2][2048] over the values of bins b[0] / b[1].
 template <int MODE, int LEVEL>
-__global__ void __launch_bounds__(1024) k3_hist_kernel(const double* __restrict__ corr, int nc, const K3Meta* __restrict__ meta,
-                                                       unsigned int* __restrict__ hist)
+// All streaming K3 kernels take the row stride and an index range [lo, hi) of the row: the whole row on one GPU,
+// the rank's own part of it (inside a local array that also holds the halos) when one recording is split in time.
+__global__ void __launch_bounds__(1024) k3_hist_kernel(const double* __restrict__ corr, long long stride, int lo, int hi,
+                                                       const K3Meta* __restrict__ meta, unsigned int* __restrict__ hist)
 {
     __shared__ unsigned int sh[2][2048];
     const int cb = blockIdx.y;
-    const double* c = corr + (long long)cb * nc;
+    const double* c = corr + (long long)cb * stride;
     const K3Meta M = meta[cb];
     const double center = MODE ? M.med : 0.0;
     for (int b = threadIdx.x; b < 2048; b += 1024) { sh[0][b] = 0; sh[1][b] = 0; }
     __syncthreads();
-    const long long i0 = (long long)blockIdx.x * K3_CHUNK;
-    const long long i1 = min((long long)nc, i0 + K3_CHUNK);
+    const long long i0 = lo + (long long)blockIdx.x * K3_CHUNK;
+    const long long i1 = min((long long)hi, i0 + K3_CHUNK);
     for (long long i = i0 + threadIdx.x; i < i1; i += 1024) {
         const double v = sel_value<MODE>(c[i], center);
         const int bin = sel_bin<MODE>(v);
@@ -893,17 +895,17 @@ __global__ void k3_locate_kernel(const unsigned int* __restrict__ hist, int nc, 
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(1024) k3_gather_kernel(const double* __restrict__ corr, int nc, K3Meta* __restrict__ meta,
-                                                         double* __restrict__ buf)
+__global__ void __launch_bounds__(1024) k3_gather_kernel(const double* __restrict__ corr, long long stride, int lo, int hi,
+                                                         K3Meta* __restrict__ meta, double* __restrict__ buf)
 {
     const int cb = blockIdx.y;
-    const double* c = corr + (long long)cb * nc;
+    const double* c = corr + (long long)cb * stride;
     K3Meta& M = meta[cb];
     const int b0 = M.b[0], b1 = M.b[1], s0 = M.sb[0], s1 = M.sb[1];
     const double center = MODE ? M.med : 0.0;
     double* out = buf + (long long)cb * K3_CAP;
-    const long long i0 = (long long)blockIdx.x * K3_CHUNK;
-    const long long i1 = min((long long)nc, i0 + K3_CHUNK);
+    const long long i0 = lo + (long long)blockIdx.x * K3_CHUNK;
+    const long long i1 = min((long long)hi, i0 + K3_CHUNK);
     for (long long i = i0 + threadIdx.x; i < i1; i += 1024) {
         const double v = sel_value<MODE>(c[i], center);
         const int bin = sel_bin<MODE>(v);
@@ -949,7 +951,9 @@ __global__ void __launch_bounds__(1024) k3_finish_kernel(const double* __restric
 }
 
 // NMS per 4096-index block: up to 25 peaks of the block in index order + their count
-__global__ void __launch_bounds__(1024) k3_nms_kernel(const double* __restrict__ corr, int nc, const K3Meta* __restrict__ meta,
+// (nc = length of the row as stored: the +-607 windows clamp there; candidates come from [lo, hi) only)
+__global__ void __launch_bounds__(1024) k3_nms_kernel(const double* __restrict__ corr, int nc, int lo, int hi,
+                                                      const K3Meta* __restrict__ meta,
                                                       int nblk, int32_t* __restrict__ blk_peaks, int32_t* __restrict__ blk_count)
 {
     __shared__ int cand[NMS_BLOCK];
@@ -961,8 +965,8 @@ __global__ void __launch_bounds__(1024) k3_nms_kernel(const double* __restrict__
     const double thr = meta[cb].thr;
     if (tid == 0) { ncand = 0; nfound = 0; }
     __syncthreads();
-    const int blk0 = blk * NMS_BLOCK;
-    for (int i = blk0 + tid; i < min(nc, blk0 + NMS_BLOCK); i += 1024)
+    const int blk0 = lo + blk * NMS_BLOCK;
+    for (int i = blk0 + tid; i < min(hi, blk0 + NMS_BLOCK); i += 1024)
         if (c[i] >= thr) cand[atomicAdd(&ncand, 1u)] = i;
     __syncthreads();
     const int nca = (int)ncand;
@@ -987,13 +991,14 @@ __global__ void __launch_bounds__(1024) k3_nms_kernel(const double* __restrict__
 }
 
 // first 25 peaks in index order; top-5 fallback from the top histogram bins (gathered by k3_top_kernel)
-__global__ void __launch_bounds__(1024) k3_collect_kernel(const double* __restrict__ corr, int nc, K3Meta* __restrict__ meta, int nblk,
+// (nc = number of values of the WHOLE row: k of the top-k fallback)
+__global__ void __launch_bounds__(1024) k3_collect_kernel(const double* __restrict__ corr, long long stride, int nc, K3Meta* __restrict__ meta, int nblk,
                                                           const int32_t* __restrict__ blk_peaks, const int32_t* __restrict__ blk_count,
                                                           const int32_t* __restrict__ top_idx,
                                                           int32_t* __restrict__ peaks, int32_t* __restrict__ npeaks, double* __restrict__ stats)
 {
     const int cb = blockIdx.x, tid = threadIdx.x;
-    const double* c = corr + (long long)cb * nc;
+    const double* c = corr + (long long)cb * stride;
     K3Meta& M = meta[cb];
     int32_t* pk = peaks + (long long)cb * PEAK_LIMIT;
     __shared__ int np_s;
@@ -1032,16 +1037,16 @@ __global__ void __launch_bounds__(1024) k3_collect_kernel(const double* __restri
 }
 
 // indices of all values in bins >= topbin (the top-5 live there)
-__global__ void __launch_bounds__(1024) k3_top_kernel(const double* __restrict__ corr, int nc, K3Meta* __restrict__ meta,
-                                                      int32_t* __restrict__ top_idx)
+__global__ void __launch_bounds__(1024) k3_top_kernel(const double* __restrict__ corr, long long stride, int lo, int hi,
+                                                      K3Meta* __restrict__ meta, int32_t* __restrict__ top_idx)
 {
     const int cb = blockIdx.y;
-    const double* c = corr + (long long)cb * nc;
+    const double* c = corr + (long long)cb * stride;
     K3Meta& M = meta[cb];
     const int topbin = M.topbin;
     int32_t* out = top_idx + (long long)cb * K3_CAP;
-    const long long i0 = (long long)blockIdx.x * K3_CHUNK;
-    const long long i1 = min((long long)nc, i0 + K3_CHUNK);
+    const long long i0 = lo + (long long)blockIdx.x * K3_CHUNK;
+    const long long i1 = min((long long)hi, i0 + K3_CHUNK);
     for (long long i = i0 + threadIdx.x; i < i1; i += 1024) {
         if (sel_bin<0>(c[i]) >= topbin) {
             const unsigned int q = atomicAdd(&M.topcnt, 1u);
@@ -1473,52 +1478,124 @@ size_t es_rx_peaks_long_scratch_bytes(int nclips, int nc)
     return ncb * (sizeof(K3Meta) + 2048 * 4 + 4096 * 4 + (size_t)K3_CAP * 8 + (size_t)K3_CAP * 4 + nblk * (PEAK_LIMIT + 1) * 4) + 256;
 }
 
+struct K3Scratch {
+    K3Meta* meta; unsigned int* hist1; unsigned int* hist2; double* buf; int32_t* top_idx; int32_t* blk_peaks; int32_t* blk_count;
+    size_t off[7];
+};
+static K3Scratch k3_carve(void* scratch, int ncb, int nblk)
+{
+    K3Scratch k;
+    unsigned char* p0 = (unsigned char*)scratch;
+    unsigned char* p = p0;
+    k.meta = (K3Meta*)p; k.off[0] = 0; p += ((size_t)ncb * sizeof(K3Meta) + 255) / 256 * 256;
+    k.hist1 = (unsigned int*)p; k.off[1] = (size_t)(p - p0); p += (size_t)ncb * 2048 * 4;
+    k.hist2 = (unsigned int*)p; k.off[2] = (size_t)(p - p0); p += (size_t)ncb * 4096 * 4;
+    k.buf = (double*)p; k.off[3] = (size_t)(p - p0); p += (size_t)ncb * K3_CAP * 8;
+    k.top_idx = (int32_t*)p; k.off[4] = (size_t)(p - p0); p += (size_t)ncb * K3_CAP * 4;
+    k.blk_peaks = (int32_t*)p; k.off[5] = (size_t)(p - p0); p += (size_t)ncb * nblk * PEAK_LIMIT * 4;
+    k.blk_count = (int32_t*)p; k.off[6] = (size_t)(p - p0);
+    return k;
+}
+
+// Byte offsets inside the scratch of es_rx_peaks_long(_phase) and the layout of its per-row record, for callers that
+// exchange the histograms / gathered values between GPUs (echoseal_b200/long_sharded.py):
+// out = off(meta), off(hist1 u32[rows][2048]), off(hist2 u32[rows][4096]), off(buf f64[rows][cap]), off(top_idx),
+//       sizeof(meta record), offsetof cnt, topcnt, overflow, topbin, med, mad, thr, cap
+int es_rx_peaks_long_layout(int nclips, int n_range, long long* out)
+{
+    const int ncb = nclips * NBANDS;
+    const int nblk = (n_range + NMS_BLOCK - 1) / NMS_BLOCK;
+    const K3Scratch k = k3_carve(nullptr, ncb, nblk);
+    out[0] = (long long)k.off[0]; out[1] = (long long)k.off[1]; out[2] = (long long)k.off[2]; out[3] = (long long)k.off[3];
+    out[4] = (long long)k.off[4];
+    out[5] = (long long)sizeof(K3Meta);
+    out[6] = (long long)offsetof(K3Meta, cnt); out[7] = (long long)offsetof(K3Meta, topcnt);
+    out[8] = (long long)offsetof(K3Meta, overflow); out[9] = (long long)offsetof(K3Meta, topbin);
+    out[10] = (long long)offsetof(K3Meta, med); out[11] = (long long)offsetof(K3Meta, mad); out[12] = (long long)offsetof(K3Meta, thr);
+    out[13] = (long long)K3_CAP;
+    return ES_OK;
+}
+
+// One phase of the long-recording K3 on the index range [lo, hi) of rows stored with `nloc` values each; `nc_total`
+// is the number of values of the WHOLE row (all ranks), which the rank arithmetic uses.  Between phases the caller
+// may sum hist1 / hist2 over ranks (after phases 0, 1, 3, 4) and merge the gathered values + counts (after 2, 5):
+//   0 clear, corr histogram            1 locate bins, sub-histogram          2 locate sub-bins, gather
+//   3 median, top-bin indices, |corr-med| histogram   4 locate, sub-histogram   5 locate, gather
+//   6 MAD + threshold, NMS per block, first 25 peaks of the range (+ local top-k candidates), overflow flag
+int es_rx_peaks_long_phase(int phase, const double* corr, int nclips, int nloc, int lo, int hi, int nc_total,
+                           void* scratch, size_t scratch_bytes,
+                           int32_t* peaks, int32_t* npeaks, double* stats, int32_t* overflow_dev, void* stream)
+{
+    if (nclips <= 0 || hi <= lo) return ES_OK;
+    if (lo < 0 || hi > nloc || nc_total < hi - lo) { set_error("es_rx_peaks_long_phase: bad range [%d,%d) of %d (total %d)", lo, hi, nloc, nc_total); return ES_EINVAL; }
+    if (!scratch || scratch_bytes < es_rx_peaks_long_scratch_bytes(nclips, hi - lo)) { set_error("es_rx_peaks_long: scratch too small"); return ES_EINVAL; }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int ncb = nclips * NBANDS;
+    const int nr = hi - lo;
+    const int nblk = (nr + NMS_BLOCK - 1) / NMS_BLOCK;
+    const K3Scratch k = k3_carve(scratch, ncb, nblk);
+    K3Meta* meta = k.meta;
+    const long long stride = nloc;
+    dim3 grid((unsigned)(((long long)nr + K3_CHUNK - 1) / K3_CHUNK), ncb);
+    switch (phase) {
+    case 0:     // ---- median of corr (rtwm/detector.py:83)
+        ES_CUDA_OK(cudaMemsetAsync(meta, 0, (size_t)ncb * sizeof(K3Meta), st));
+        ES_CUDA_OK(cudaMemsetAsync(overflow_dev, 0, sizeof(int32_t), st));
+        ES_CUDA_OK(cudaMemsetAsync(k.hist1, 0, (size_t)ncb * 2048 * 4, st));
+        k3_hist_kernel<0, 1><<<grid, 1024, 0, st>>>(corr, stride, lo, hi, meta, k.hist1);
+        break;
+    case 1:
+        k3_locate_kernel<1><<<ncb, 32, 0, st>>>(k.hist1, nc_total, meta, 1);
+        ES_CUDA_OK(cudaMemsetAsync(k.hist2, 0, (size_t)ncb * 4096 * 4, st));
+        k3_hist_kernel<0, 2><<<grid, 1024, 0, st>>>(corr, stride, lo, hi, meta, k.hist2);
+        break;
+    case 2:
+        k3_locate_kernel<2><<<ncb, 32, 0, st>>>(k.hist2, nc_total, meta, 0);
+        k3_gather_kernel<0><<<grid, 1024, 0, st>>>(corr, stride, lo, hi, meta, k.buf);
+        break;
+    case 3:
+        k3_finish_kernel<0><<<ncb, 1024, 0, st>>>(k.buf, nc_total, meta);
+        // candidates of the top-5 fallback (unconditional: no host round trip)
+        k3_top_kernel<<<grid, 1024, 0, st>>>(corr, stride, lo, hi, meta, k.top_idx);
+        // ---- MAD of |corr - med| and the threshold (rtwm/detector.py:84-86)
+        ES_CUDA_OK(cudaMemsetAsync(k.hist1, 0, (size_t)ncb * 2048 * 4, st));
+        k3_hist_kernel<1, 1><<<grid, 1024, 0, st>>>(corr, stride, lo, hi, meta, k.hist1);
+        break;
+    case 4:
+        k3_locate_kernel<1><<<ncb, 32, 0, st>>>(k.hist1, nc_total, meta, 0);
+        ES_CUDA_OK(cudaMemsetAsync(k.hist2, 0, (size_t)ncb * 4096 * 4, st));
+        k3_hist_kernel<1, 2><<<grid, 1024, 0, st>>>(corr, stride, lo, hi, meta, k.hist2);
+        break;
+    case 5:
+        k3_locate_kernel<2><<<ncb, 32, 0, st>>>(k.hist2, nc_total, meta, 0);
+        k3_gather_kernel<1><<<grid, 1024, 0, st>>>(corr, stride, lo, hi, meta, k.buf);
+        break;
+    case 6:
+        k3_finish_kernel<1><<<ncb, 1024, 0, st>>>(k.buf, nc_total, meta);
+        // ---- NMS per index block, then the first 25 peaks / the fallback (rtwm/detector.py:87-99, 108-110)
+        k3_nms_kernel<<<dim3(nblk, ncb), 1024, 0, st>>>(corr, nloc, lo, hi, meta, nblk, k.blk_peaks, k.blk_count);
+        k3_collect_kernel<<<ncb, 1024, 0, st>>>(corr, stride, nc_total, meta, nblk, k.blk_peaks, k.blk_count, k.top_idx, peaks, npeaks, stats);
+        k3_flag_kernel<<<(ncb + 255) / 256, 256, 0, st>>>(meta, ncb, overflow_dev);
+        break;
+    default:
+        set_error("es_rx_peaks_long_phase: phase %d not in 0..6", phase);
+        return ES_EINVAL;
+    }
+    ES_CUDA_OK(cudaGetLastError());
+    return ES_OK;
+}
+
 // long-recording form of es_rx_peaks (same outputs).  *overflow_dev (int32, device) is set non-zero when a gather
 // buffer overflowed (degenerate data): the caller then falls back to es_rx_peaks.
 int es_rx_peaks_long(const double* corr, int nclips, int nc, void* scratch, size_t scratch_bytes,
                      int32_t* peaks, int32_t* npeaks, double* stats, int32_t* overflow_dev, void* stream)
 {
     if (nclips <= 0 || nc <= 0) return ES_OK;
-    if (!scratch || scratch_bytes < es_rx_peaks_long_scratch_bytes(nclips, nc)) { set_error("es_rx_peaks_long: scratch too small"); return ES_EINVAL; }
-    cudaStream_t st = (cudaStream_t)stream;
-    const int ncb = nclips * NBANDS;
-    const int nblk = (nc + NMS_BLOCK - 1) / NMS_BLOCK;
-    unsigned char* p = (unsigned char*)scratch;
-    K3Meta* meta = (K3Meta*)p; p += ((size_t)ncb * sizeof(K3Meta) + 255) / 256 * 256;
-    unsigned int* hist1 = (unsigned int*)p; p += (size_t)ncb * 2048 * 4;
-    unsigned int* hist2 = (unsigned int*)p; p += (size_t)ncb * 4096 * 4;
-    double* buf = (double*)p; p += (size_t)ncb * K3_CAP * 8;
-    int32_t* top_idx = (int32_t*)p; p += (size_t)ncb * K3_CAP * 4;
-    int32_t* blk_peaks = (int32_t*)p; p += (size_t)ncb * nblk * PEAK_LIMIT * 4;
-    int32_t* blk_count = (int32_t*)p;
-    ES_CUDA_OK(cudaMemsetAsync(meta, 0, (size_t)ncb * sizeof(K3Meta), st));
-    ES_CUDA_OK(cudaMemsetAsync(overflow_dev, 0, sizeof(int32_t), st));
-    dim3 grid((unsigned)(((long long)nc + K3_CHUNK - 1) / K3_CHUNK), ncb);
-    // ---- median of corr (rtwm/detector.py:83)
-    ES_CUDA_OK(cudaMemsetAsync(hist1, 0, (size_t)ncb * 2048 * 4, st));
-    k3_hist_kernel<0, 1><<<grid, 1024, 0, st>>>(corr, nc, meta, hist1);
-    k3_locate_kernel<1><<<ncb, 32, 0, st>>>(hist1, nc, meta, 1);
-    ES_CUDA_OK(cudaMemsetAsync(hist2, 0, (size_t)ncb * 4096 * 4, st));
-    k3_hist_kernel<0, 2><<<grid, 1024, 0, st>>>(corr, nc, meta, hist2);
-    k3_locate_kernel<2><<<ncb, 32, 0, st>>>(hist2, nc, meta, 0);
-    k3_gather_kernel<0><<<grid, 1024, 0, st>>>(corr, nc, meta, buf);
-    k3_finish_kernel<0><<<ncb, 1024, 0, st>>>(buf, nc, meta);
-    // ---- candidates of the top-5 fallback (unconditional: no host round trip)
-    k3_top_kernel<<<grid, 1024, 0, st>>>(corr, nc, meta, top_idx);
-    // ---- MAD of |corr - med| and the threshold (rtwm/detector.py:84-86)
-    ES_CUDA_OK(cudaMemsetAsync(hist1, 0, (size_t)ncb * 2048 * 4, st));
-    k3_hist_kernel<1, 1><<<grid, 1024, 0, st>>>(corr, nc, meta, hist1);
-    k3_locate_kernel<1><<<ncb, 32, 0, st>>>(hist1, nc, meta, 0);
-    ES_CUDA_OK(cudaMemsetAsync(hist2, 0, (size_t)ncb * 4096 * 4, st));
-    k3_hist_kernel<1, 2><<<grid, 1024, 0, st>>>(corr, nc, meta, hist2);
-    k3_locate_kernel<2><<<ncb, 32, 0, st>>>(hist2, nc, meta, 0);
-    k3_gather_kernel<1><<<grid, 1024, 0, st>>>(corr, nc, meta, buf);
-    k3_finish_kernel<1><<<ncb, 1024, 0, st>>>(buf, nc, meta);
-    // ---- NMS per index block, then the first 25 peaks / the fallback (rtwm/detector.py:87-99, 108-110)
-    k3_nms_kernel<<<dim3(nblk, ncb), 1024, 0, st>>>(corr, nc, meta, nblk, blk_peaks, blk_count);
-    k3_collect_kernel<<<ncb, 1024, 0, st>>>(corr, nc, meta, nblk, blk_peaks, blk_count, top_idx, peaks, npeaks, stats);
-    k3_flag_kernel<<<(ncb + 255) / 256, 256, 0, st>>>(meta, ncb, overflow_dev);
-    ES_CUDA_OK(cudaGetLastError());
+    for (int phase = 0; phase <= 6; ++phase) {
+        const int rc = es_rx_peaks_long_phase(phase, corr, nclips, nc, 0, nc, nc, scratch, scratch_bytes, peaks, npeaks, stats,
+                                              overflow_dev, stream);
+        if (rc != ES_OK) return rc;
+    }
     return ES_OK;
 }
 

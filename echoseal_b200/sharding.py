@@ -5,9 +5,8 @@ final verdict gather.  Works with any torch.distributed backend (NCCL on the GPU
 One LONG recording (config 3) shards by BAND: the reference scans the four bands independently
 (rtwm/detector.py:44-53: one `_scan_band_multi_frame` per band, each with its own median / MAD threshold, NMS,
 25-peak limit and 400-try budget), so band i of the reference's order goes to rank i mod world and again the
-only exchange is the gather of the (verdict, latched nonce) records.  Splitting one band in TIME across GPUs
-(halo + all-reduced histograms for the global order statistics) is not built: a whole hour of
-audio is one 0.13 s pass on one GPU, less than the exchanges would cost."""
+only exchange is the gather of the (verdict, latched nonce) records.  Splitting the recording in TIME across
+GPUs (halos + all-reduced histograms for the global order statistics) lives in long_sharded.py."""
 from __future__ import annotations
 import numpy as np
 import torch

@@ -75,6 +75,15 @@ void es_rx_peaks_force_general(int on);
 size_t es_rx_peaks_long_scratch_bytes(int nclips, int nc);
 int es_rx_peaks_long(const double* corr, int nclips, int nc, void* scratch, size_t scratch_bytes,
                      int32_t* peaks, int32_t* npeaks, double* stats, int32_t* overflow_dev, void* stream);
+/* The same, one phase (0..6) at a time and on the index range [lo, hi) of rows stored with nloc values each;
+ * nc_total = number of values of the WHOLE row over all ranks.  For ONE recording split in time over several GPUs
+ * (SURVEY 8e): between phases the caller sums the histograms over the ranks (after phases 0, 1, 3, 4) and merges the
+ * gathered values and their counts (after 2, 5); es_rx_peaks_long_layout gives the byte offsets of those buffers and
+ * of the per-row record inside the scratch.  peaks are indices into the local rows. */
+int es_rx_peaks_long_phase(int phase, const double* corr, int nclips, int nloc, int lo, int hi, int nc_total,
+                           void* scratch, size_t scratch_bytes,
+                           int32_t* peaks, int32_t* npeaks, double* stats, int32_t* overflow_dev, void* stream);
+int es_rx_peaks_long_layout(int nclips, int n_range, long long* out /*[14]*/);
 /* K4: per peak header decode (rtwm/detector.py:452-515) + matched filter / shift search of _llr
  * (rtwm/detector.py:322-383). hdr_out = ok (-1: no frame), val, score, margin */
 int es_rx_frames(const double* y, int nclips, int n, const int32_t* peaks, const int32_t* npeaks,

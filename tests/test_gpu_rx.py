@@ -374,3 +374,41 @@ def test_full_size_batch_properties(env):
         assert ok == bool(v1[i]) and det["n_scl"] == r1[i].n_scl
         for bi in range(4):
             assert [(int(s), int(c)) for s, c in det["attempts"].get(bi, [])] == r1[i].attempts[bi]
+
+
+def test_time_sharded_recording_equals_single_gpu(env):
+    """long_sharded: one recording split in time over W virtual ranks (histogram / value / peak exchanges
+    simulated in-process) against the single-GPU path: same sync offsets, statistics to 1e-9, same attempt
+    count and verdict -- for a watermarked recording (many peaks), plain noise (top-5 fallback) and a recording
+    whose energy sits at the end (peaks owned by the last rank, frames cut by the end of the array)."""
+    torch, rx_gpu, detector, clips, taps = env
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    from echoseal_b200 import long_sharded
+    dev = torch.device("cuda", 0)
+    keys, _, audio = bench.make_clips_gpu(0, 8, dev)
+    a = audio.cpu().numpy()
+    rng = np.random.default_rng(77)
+    recs = {
+        "watermarked": (np.concatenate([a[0], a[5], a[6]]), keys[0]),      # no repeats: exact value ties would be decided by 1e-13 effects
+        "noise": ((0.05 * rng.standard_normal(400_000)).astype(np.float32), keys[1]),
+        "late": (np.concatenate([(1e-3 * rng.standard_normal(300_000)).astype(np.float32), a[2][:100_500]]), keys[2]),
+    }
+    for name, (sig, key) in recs.items():
+        ref = detector.WatermarkDetector(key, list_size=8)
+        v_ref = ref.verify(sig, 48000)
+        r = ref.last_result
+        for world in (1, 2, 3):
+            det = detector.WatermarkDetector(key, list_size=8)
+            v, outs = long_sharded.run_simulated(det, sig, world)
+            o = outs[0]
+            assert v == v_ref, (name, world)
+            for bi in range(4):
+                npk = int(r.npeaks[bi])
+                assert int(o["npeaks"][bi]) == npk, (name, world, bi)
+                assert list(o["peaks"][bi][:npk]) == [int(p) for p in r.peaks[bi][:npk]], (name, world, bi)
+                assert int(o["fallback"][bi]) == int(r.stats[bi, 3])
+                np.testing.assert_allclose([o["med"][bi], o["mad"][bi], o["thr"][bi]], r.stats[bi, :3], rtol=1e-9, atol=1e-12)
+            assert o["n_scl"] == r.n_scl, (name, world)
+            for other in outs[1:]:
+                assert (other["peaks"] == o["peaks"]).all() and torch.equal(other["frames"], o["frames"])

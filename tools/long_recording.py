@@ -34,6 +34,8 @@ def main():
     del stretched
     p = float((a441.double() ** 2).mean())
     a441 = a441 + torch.randn(a441.shape, device=dev, generator=g) * np.sqrt(p * 10 ** 1.5)   # -15 dB SNR
+    if world > 1:
+        dist.broadcast(a441, src=0)              # the embedder draws fresh payload nonces: every rank must see rank 0's audio
     audio = a441[0].cpu().numpy()
     del a441
     torch.cuda.synchronize()
@@ -53,6 +55,20 @@ def main():
         ok2 = verify_recording_sharded(rx2, audio, 44100, device=dev)
         torch.cuda.synchronize(); dist.barrier(); dt2 = time.perf_counter() - t2
         sharded = {"world": world, "verdict": bool(ok2), "verify_seconds": dt2, "equals_sequential": bool(ok2) == bool(ok)}
+        # the same recording split in TIME (global median / MAD through NCCL all-reduces of the histograms)
+        from echoseal_b200.long_sharded import verify_recording_time_sharded
+        rx3 = detector.WatermarkDetector(key, list_size=8)
+        verify_recording_time_sharded(rx3, audio, 44100, device=dev)            # warm-up (allocations, NCCL)
+        rx3 = detector.WatermarkDetector(key, list_size=8)
+        dist.barrier(); torch.cuda.synchronize(); t3 = time.perf_counter()
+        ok3 = verify_recording_time_sharded(rx3, audio, 44100, device=dev)
+        torch.cuda.synchronize(); dist.barrier(); dt3 = time.perf_counter() - t3
+        o = rx3.last_sharded
+        same_peaks = all(list(o["peaks"][bi][:int(r.npeaks[bi])]) == [int(p) for p in r.peaks[bi][:int(r.npeaks[bi])]]
+                         and int(o["npeaks"][bi]) == int(r.npeaks[bi]) for bi in range(4))
+        sharded["time_sharded"] = {"verdict": bool(ok3), "verify_seconds": dt3, "equals_sequential": bool(ok3) == bool(ok),
+                                   "sync_offsets_equal": bool(same_peaks), "scl_decodes": int(o["n_scl"]),
+                                   "thr": [float(v) for v in o["thr"]]}
         if rank != 0:
             dist.destroy_process_group()
             return
