@@ -127,7 +127,10 @@ class EmbedderBank:
     (rtwm/embedder.py:44-75): frames are generated on demand, the mix level is computed per block.
     The host side (payload sealing, PN bits, hop bands) runs in the native threaded feeder."""
 
-    def __init__(self, keys: list[bytes], params: TxParams | None = None, rand=None):
+    def __init__(self, keys: list[bytes], params: TxParams | None = None, rand=None, prefetch: bool = False):
+        """prefetch=True: the host side of the NEXT frames (payload sealing, PN, hop band: tx_prepare) runs in a
+        background thread as soon as a block leaves fewer chips in the FIFO than one more block needs, so the
+        block that does need them only launches the frame kernel (live use, TxService below)."""
         from .host_feeder import KeyBank
         import os
         self.p = params or TxParams()
@@ -140,20 +143,50 @@ class EmbedderBank:
         self.session_nonce = np.frombuffer(self._rand(8 * self.S), np.uint8).reshape(self.S, 8).copy()
         self._fifo = None          # device tensor [S, avail]
         self._kidx = np.arange(self.S, dtype=np.int32)
+        self._prefetch = bool(prefetch)
+        self._pending = None       # (nframes, thread, result holder) of a running host preparation
 
     def make_frames(self, nframes: int) -> torch.Tensor:
         """Next `nframes` frames of every stream -> device float32 [S, nframes*1215]; advances frame_ctr."""
         dev = _dev()
         tx_gpu.set_filters(self.p.fs, self.p.preamble)
-        S, F = self.S, self.S * nframes
-        ctr = (self.frame_ctr[:, None].astype(np.uint64) + np.arange(nframes, dtype=np.uint64)[None, :]) % (2 ** 32)
-        rnd = np.frombuffer(self._rand(23 * F), np.uint8).reshape(F, 23)
-        prep = self.bank.tx_prepare(np.repeat(self._kidx, nframes), ctr.reshape(-1).astype(np.uint32),
-                                    np.repeat(self.session_nonce, nframes, axis=0), rnd)
+        S = self.S
+        prep = None
+        if self._pending is not None:
+            pn, th, holder = self._pending
+            th.join()
+            self._pending = None
+            if pn == nframes and "prep" in holder:
+                prep = holder["prep"]
+            elif "err" in holder:
+                raise holder["err"]
+        if prep is None:
+            prep = self._prepare_host(nframes)
         chips = tx_gpu.frames(*(torch.from_numpy(prep[k]).to(dev, non_blocking=True)
                                 for k in ("payload", "pn", "hdr_pn", "band", "ctr_lo16")), K=self.p.K)
         self.frame_ctr = ((self.frame_ctr.astype(np.uint64) + nframes) % (2 ** 32)).astype(np.uint32)
         return chips.view(S, nframes * FRAME_LEN)
+
+    def _prepare_host(self, nframes: int):
+        """host inputs of the next `nframes` frames of every stream (does not advance frame_ctr)"""
+        F = self.S * nframes
+        ctr = (self.frame_ctr[:, None].astype(np.uint64) + np.arange(nframes, dtype=np.uint64)[None, :]) % (2 ** 32)
+        rnd = np.frombuffer(self._rand(23 * F), np.uint8).reshape(F, 23)
+        return self.bank.tx_prepare(np.repeat(self._kidx, nframes), ctr.reshape(-1).astype(np.uint32),
+                                    np.repeat(self.session_nonce, nframes, axis=0), rnd)
+
+    def _start_prefetch(self, nframes: int):
+        import threading
+        holder = {}
+
+        def work():
+            try:
+                holder["prep"] = self._prepare_host(nframes)
+            except Exception as e:           # surfaced by the next make_frames
+                holder["err"] = e
+        th = threading.Thread(target=work, daemon=True)
+        th.start()
+        self._pending = (nframes, th, holder)
 
     def process(self, x):
         """x float32 [S, B] (numpy -> numpy, CUDA tensor -> CUDA tensor): one block of every stream."""
@@ -170,5 +203,42 @@ class EmbedderBank:
             self._fifo = new if self._fifo is None else torch.cat([self._fifo, new], dim=1)
         chips = self._fifo[:, :B].contiguous()
         self._fifo = self._fifo[:, B:]
+        if self._prefetch and self._pending is None and int(self._fifo.shape[1]) < B:
+            self._start_prefetch((B - int(self._fifo.shape[1]) + FRAME_LEN - 1) // FRAME_LEN)
         out, _ = tx_gpu.mix(xd, chips, db_to_lin(self.p.target_rel_db), db_to_lin(self.p.floor_rel_dbfs))
         return out.cpu().numpy() if is_np else out
+
+
+class TxService:
+    """Live multi-stream embed service (rtwm/audioio.py:52-63 feeds WatermarkEmbedder.process one 1024-sample block
+    per PortAudio callback; README: loop latency < 50 ms).  S streams advance in lock-step: `process_block` takes the
+    next block of every stream in host memory and returns the watermarked block, through pinned staging buffers
+    (double-buffered, so the returned array stays valid until the call after next) and one CUDA stream; the host
+    crypto of upcoming frames runs in the background (EmbedderBank(prefetch=True)).  `latency_ms` holds the wall time
+    of every call."""
+
+    def __init__(self, keys: list[bytes], block: int = 1024, params: TxParams | None = None, rand=None):
+        self.bank = EmbedderBank(keys, params, rand=rand, prefetch=True)
+        self.S, self.B = len(keys), int(block)
+        self._in = [torch.empty((self.S, self.B), dtype=torch.float32, pin_memory=True) for _ in range(2)]
+        self._out = [torch.empty((self.S, self.B), dtype=torch.float32, pin_memory=True) for _ in range(2)]
+        self._k = 0
+        self._stream = torch.cuda.Stream()
+        self.latency_ms: list[float] = []
+
+    def process_block(self, x) -> np.ndarray:
+        import time
+        t0 = time.perf_counter()
+        x = np.asarray(x, np.float32)
+        if x.shape != (self.S, self.B):
+            raise ValueError(f"block must be [S={self.S}, B={self.B}]")
+        hin, hout = self._in[self._k], self._out[self._k]
+        self._k ^= 1
+        hin.numpy()[...] = x
+        with torch.cuda.stream(self._stream):
+            xd = hin.to(_dev(), non_blocking=True)
+            y = self.bank.process(xd)
+            hout.copy_(y, non_blocking=True)
+        self._stream.synchronize()
+        self.latency_ms.append(1e3 * (time.perf_counter() - t0))
+        return hout.numpy()

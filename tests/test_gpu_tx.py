@@ -105,3 +105,35 @@ def test_embedder_bank_matches_single_stream_semantics():
     # second block continues from the FIFO remainder
     out2 = bank.process(x[:, :500])
     assert out2.shape == (5, 500) and list(bank.frame_ctr) == [3, 10, 1003, 65538, 2]
+
+
+def test_live_service_equals_bank_and_reports_latency():
+    """TxService (pinned double-buffered staging, one CUDA stream, host crypto of the next frames prefetched in the
+    background) gives block for block what the synchronous EmbedderBank gives with the same randomness."""
+    from echoseal_b200 import embedder
+    keys = [bytes([i + 3]) * 32 for i in range(7)]
+    stream = np.random.default_rng(5).integers(0, 256, 1 << 18, dtype=np.uint8).tobytes()
+
+    def make_rand():
+        pos = [0]
+        def rand(n):
+            b = stream[pos[0]:pos[0] + n]; pos[0] += n
+            return b
+        return rand
+    bank = embedder.EmbedderBank(keys, rand=make_rand())
+    svc = embedder.TxService(keys, block=1024, rand=make_rand())
+    rng = np.random.default_rng(2)
+    prev = None
+    for blk in range(9):                                   # crosses several frame boundaries (1215-sample frames)
+        x = (0.1 * rng.standard_normal((7, 1024))).astype(np.float32)
+        a = bank.process(x)
+        b = svc.process_block(x)
+        assert a.shape == b.shape == (7, 1024)
+        assert (a == b).all(), blk
+        if prev is not None:
+            assert (prev[0] == prev[1]).all()              # the previous output buffer is still intact
+        prev = (a, b.copy() if blk % 2 else b)
+    assert (bank.frame_ctr == svc.bank.frame_ctr).all()
+    assert len(svc.latency_ms) == 9 and all(t > 0 for t in svc.latency_ms)
+    with pytest.raises(ValueError):
+        svc.process_block(np.zeros((7, 512), np.float32))
