@@ -416,10 +416,8 @@ def main():
 
     t0 = time.perf_counter()
     keys, _, clips = make_clips_gpu(rank * args.clips, args.clips, dev)
-    from echoseal_b200.host_feeder import KeyBank
     log(f"[rank {rank}] generated {args.clips} clips in {time.perf_counter() - t0:.1f}s; host threads {host_threads}")
     taps = [rx_gpu.matched_filter_taps(b, FS) for b in BAND_PLAN]
-    key_idx = np.arange(args.clips, dtype=np.int32)
 
     def step(audio, want_details=False):
         # keys, not a prebuilt bank: key derivation and hop tables are part of verifying a clip (built per

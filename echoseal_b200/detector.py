@@ -18,7 +18,7 @@ import torch
 
 from . import polar_gpu, rx_gpu
 from .crypto import SecureChannel
-from .utils import BAND_PLAN, choose_band, mseq_63, resample_ratio
+from .utils import BAND_PLAN, choose_band, mseq_63
 
 PRE_BITS = mseq_63()
 PRE_L = len(PRE_BITS)

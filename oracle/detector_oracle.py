@@ -10,7 +10,6 @@ Parity status: PINNED against outputs of the reference itself run in the build c
 (tests/golden/rx_golden.npz, made by tests/golden/make_rx_golden.py)."""
 from __future__ import annotations
 import ctypes as C
-import hashlib
 import hmac
 import struct
 import numpy as np

@@ -1,6 +1,8 @@
-import sys, os, time
-sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
-import numpy as np, torch
+"""Step-time probe: device-resident vs pinned-host input of the 10k-clip RX batch, three steps each, and raw H2D bandwidth."""
+import os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import torch
 import bench
 from echoseal_b200 import detector, rx_gpu
 from echoseal_b200.utils import BAND_PLAN

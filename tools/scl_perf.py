@@ -1,5 +1,5 @@
 """Quick SCL-8 throughput probe (CUDA events, L2-exceeding input set)."""
-import sys, os, time
+import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from echoseal_b200 import polar_gpu
