@@ -111,13 +111,26 @@ template <class F> static void parallel_for(int n, int nthreads, F fn)
     for (auto& t : th) t.join();
 }
 
+// OpenSSL 3: EVP_aes_128_ecb() / EVP_chacha20_poly1305() make every *Init_ex do an implicit algorithm fetch under a
+// library-wide lock, which serialises the feeder's threads.  Fetch both once and hand the fetched objects out.
+static const EVP_CIPHER* cipher_aes_ecb()
+{
+    static EVP_CIPHER* c = EVP_CIPHER_fetch(nullptr, "AES-128-ECB", nullptr);
+    return c ? c : EVP_aes_128_ecb();
+}
+static const EVP_CIPHER* cipher_chacha()
+{
+    static EVP_CIPHER* c = EVP_CIPHER_fetch(nullptr, "ChaCha20-Poly1305", nullptr);
+    return c ? c : EVP_chacha20_poly1305();
+}
+
 // AES-128-ECB over counter blocks (ctr << 64 | blk), big-endian (rtwm/utils.py:115-124)
 struct AesEcb {
     EVP_CIPHER_CTX* ctx;
     explicit AesEcb(const uint8_t key[16])
     {
         ctx = EVP_CIPHER_CTX_new();
-        EVP_EncryptInit_ex(ctx, EVP_aes_128_ecb(), nullptr, key, nullptr);
+        EVP_EncryptInit_ex(ctx, cipher_aes_ecb(), nullptr, key, nullptr);
         EVP_CIPHER_CTX_set_padding(ctx, 0);
     }
     ~AesEcb() { EVP_CIPHER_CTX_free(ctx); }
@@ -176,7 +189,7 @@ static void grow_hop(KeyCtx& k, size_t hi)
 static bool aead_open(EVP_CIPHER_CTX* ctx, const uint8_t key[32], const uint8_t blob[55], uint8_t pt[27])
 {
     int ol = 0, fl = 0;
-    if (EVP_DecryptInit_ex(ctx, EVP_chacha20_poly1305(), nullptr, nullptr, nullptr) != 1) return false;
+    if (EVP_DecryptInit_ex(ctx, cipher_chacha(), nullptr, nullptr, nullptr) != 1) return false;
     EVP_CIPHER_CTX_ctrl(ctx, EVP_CTRL_AEAD_SET_IVLEN, 12, nullptr);
     if (EVP_DecryptInit_ex(ctx, nullptr, nullptr, key, blob) != 1) return false;
     if (EVP_DecryptUpdate(ctx, pt, &ol, blob + 12, 27) != 1) return false;
@@ -187,7 +200,7 @@ static bool aead_open(EVP_CIPHER_CTX* ctx, const uint8_t key[32], const uint8_t 
 static bool aead_seal(EVP_CIPHER_CTX* ctx, const uint8_t key[32], const uint8_t nonce[12], const uint8_t pt[27], uint8_t blob[55])
 {
     int ol = 0, fl = 0;
-    if (EVP_EncryptInit_ex(ctx, EVP_chacha20_poly1305(), nullptr, nullptr, nullptr) != 1) return false;
+    if (EVP_EncryptInit_ex(ctx, cipher_chacha(), nullptr, nullptr, nullptr) != 1) return false;
     EVP_CIPHER_CTX_ctrl(ctx, EVP_CTRL_AEAD_SET_IVLEN, 12, nullptr);
     if (EVP_EncryptInit_ex(ctx, nullptr, nullptr, key, nonce) != 1) return false;
     memcpy(blob, nonce, 12);
