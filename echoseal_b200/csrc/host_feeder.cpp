@@ -153,12 +153,14 @@ static void derive_key(const uint8_t key32[32], KeyCtx& k)
     static const uint8_t info[] = "EchoSeal:KDF:v1";
     const size_t ilen = sizeof(info) - 1;
     uint8_t salt[32] = {0}, prk[32], t1[32], t2[32], buf[32 + 32];
-    unsigned int l = 0;
-    HMAC(EVP_sha256(), salt, 32, key32, 32, prk, &l);
+    HmacKey ext, exp;                       // (the one-shot HMAC() fetches SHA-256 under a library lock per call)
+    ext.init(salt, 32);
+    ext.mac(key32, 32, prk);
+    exp.init(prk, 32);
     memcpy(buf, info, ilen); buf[ilen] = 1;
-    HMAC(EVP_sha256(), prk, 32, buf, ilen + 1, t1, &l);
+    exp.mac(buf, ilen + 1, t1);
     memcpy(buf, t1, 32); memcpy(buf + 32, info, ilen); buf[32 + ilen] = 2;
-    HMAC(EVP_sha256(), prk, 32, buf, 32 + ilen + 1, t2, &l);
+    exp.mac(buf, 32 + ilen + 1, t2);
     memcpy(k.aead_key, t1, 32);
     // StreamPRNG sub-key: BLAKE2s-128(prng_key, person="EchoSeal") (rtwm/utils.py:94)
     static const uint8_t person[8] = {'E', 'c', 'h', 'o', 'S', 'e', 'a', 'l'};
