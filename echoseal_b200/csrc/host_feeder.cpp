@@ -15,6 +15,9 @@
 #include <math.h>
 #include <atomic>
 #include <thread>
+#include <functional>
+#include <mutex>
+#include <condition_variable>
 #include <vector>
 #include <algorithm>
 
@@ -99,16 +102,62 @@ struct Feeder {
     int nthreads;
 };
 
+// Process-wide worker pool: the feeder is called a few times per sub-batch (and once per block by the live TX
+// service), so spawning threads per call costs more than the work of a small call.  Workers are created on demand,
+// detached and never torn down (no static-destruction order to get wrong); one parallel region runs at a time.
+class WorkPool {
+public:
+    static WorkPool& get() { static WorkPool* p = new WorkPool(); return *p; }
+    void run(int n, int nthreads, const std::function<void(int)>& fn)
+    {
+        std::lock_guard<std::mutex> region(region_mu_);
+        const int helpers = nthreads - 1;
+        while ((int)nworkers_ < helpers) {
+            const int id = nworkers_++;
+            std::thread([this, id]() { worker(id); }).detach();
+        }
+        fn_ = &fn; n_ = n; next_.store(0);
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            want_ = helpers; active_ = helpers; ++gen_;
+        }
+        cv_start_.notify_all();
+        work();
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_done_.wait(lk, [&] { return active_ == 0; });
+    }
+private:
+    void work() { for (;;) { const int i = next_.fetch_add(1); if (i >= n_) break; (*fn_)(i); } }
+    void worker(int id)
+    {
+        unsigned long long seen = 0;
+        for (;;) {
+            std::unique_lock<std::mutex> lk(mu_);
+            cv_start_.wait(lk, [&] { return gen_ != seen; });
+            seen = gen_;
+            const bool part = id < want_;
+            lk.unlock();
+            if (!part) continue;
+            work();
+            lk.lock();
+            if (--active_ == 0) cv_done_.notify_one();
+        }
+    }
+    std::mutex region_mu_, mu_;
+    std::condition_variable cv_start_, cv_done_;
+    const std::function<void(int)>* fn_ = nullptr;
+    int n_ = 0, want_ = 0, active_ = 0, nworkers_ = 0;
+    unsigned long long gen_ = 0;
+    std::atomic<int> next_{0};
+};
+
 template <class F> static void parallel_for(int n, int nthreads, F fn)
 {
     if (n <= 0) return;
     nthreads = std::max(1, std::min(nthreads, n));
     if (nthreads == 1) { for (int i = 0; i < n; ++i) fn(i); return; }
-    std::atomic<int> next(0);
-    std::vector<std::thread> th;
-    for (int t = 0; t < nthreads; ++t)
-        th.emplace_back([&]() { for (;;) { const int i = next.fetch_add(1); if (i >= n) break; fn(i); } });
-    for (auto& t : th) t.join();
+    const std::function<void(int)> f = [&](int i) { fn(i); };
+    WorkPool::get().run(n, nthreads, f);
 }
 
 // OpenSSL 3: EVP_aes_128_ecb() / EVP_chacha20_poly1305() make every *Init_ex do an implicit algorithm fetch under a
