@@ -1277,9 +1277,12 @@ __device__ __forceinline__ float key_f32(uint32_t k)
 }
 
 // kth smallest (0-based) of the 32x32 keys held by the warp (invalid entries carry key 0xffffffff)
+// MSB-first: after bit b the answer lies in the bucket [prefix, prefix + 2^b), whose population is tracked; as soon
+// as it holds one key that key is the answer (the smallest key >= prefix), typically after ~20 of the 32 bits.
 __device__ __forceinline__ uint32_t warp_select(const uint32_t (&key)[32], int kth)
 {
     uint32_t prefix = 0;
+    int below = 0, inb = 1024;              // keys < prefix ; keys inside the current bucket
 #pragma unroll 1
     for (int b = 31; b >= 0; --b) {
         const uint32_t cand = prefix | (1u << b);
@@ -1287,7 +1290,14 @@ __device__ __forceinline__ uint32_t warp_select(const uint32_t (&key)[32], int k
 #pragma unroll
         for (int j = 0; j < 32; ++j) cnt += (key[j] < cand) ? 1 : 0;
         cnt = __reduce_add_sync(0xffffffffu, cnt);
-        if (cnt <= kth) prefix = cand;
+        if (cnt <= kth) { inb -= cnt - below; below = cnt; prefix = cand; }
+        else inb = cnt - below;
+        if (inb == 1) {
+            uint32_t m = 0xffffffffu;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) m = (key[j] >= prefix) ? min(m, key[j]) : m;
+            return __reduce_min_sync(0xffffffffu, m);
+        }
     }
     return prefix;
 }
