@@ -145,59 +145,82 @@ constexpr int NCC_T = 8;
 constexpr int NCC_TILE = 256 * NCC_T;
 constexpr int NCC_IN = NCC_TILE + PRE_L - 1;
 // shared layout: sample j at j + (j >> 3), so that lanes reading j = 8*lane + m are 9 doubles apart (conflict-free)
-__device__ __forceinline__ constexpr int ncc_pad(int j) { return j + (j >> 3); }
+__host__ __device__ __forceinline__ constexpr int ncc_pad(int j) { return j + (j >> 3); }
 
-__global__ void __launch_bounds__(256) ncc_kernel(const double* __restrict__ y, int n, int nc,
-                                                  double* __restrict__ corr)
+constexpr int NCC_SPAN = 12;                    // consecutive tiles per CTA (input tiles double-buffered with cp.async)
+
+__global__ void __launch_bounds__(256, 4) ncc_kernel(const double* __restrict__ y, int n, int nc,
+                                                     double* __restrict__ corr)
 {
-    __shared__ double sy[ncc_pad(NCC_IN) + 1];
+    extern __shared__ __align__(16) double ncc_sm[];
+    constexpr int BUF = ncc_pad(NCC_IN) + 1;
     const int cb = blockIdx.y;                  // clip*4 + band
     const int band = cb & 3;
-    const int i0 = blockIdx.x * NCC_TILE;
     const double* ys = y + (long long)cb * n;
-    for (int t = threadIdx.x; t < NCC_IN; t += 256) {
-        const int j = i0 + t;
-        sy[ncc_pad(t)] = (j < n) ? ys[j] : 0.0;
-    }
-    __syncthreads();
-    const double* sv = sy + 9 * threadIdx.x;    // ncc_pad(8*t + m) = 9*t + m + (m >> 3)
-#define NCC_V(m) sv[(m) + ((m) >> 3)]
-    double d[NCC_T], win[NCC_T];
-#pragma unroll
-    for (int q = 0; q < NCC_T; ++q) d[q] = 0.0;
-#pragma unroll
-    for (int q = 0; q < NCC_T - 1; ++q) win[q] = NCC_V(q);
-    double core = 0.0;                          // sum of v[m]^2, m = 7..62: common to the 8 windows
-#pragma unroll
-    for (int k = 0; k < PRE_L; ++k) {
-        win[(k + NCC_T - 1) & (NCC_T - 1)] = NCC_V(k + NCC_T - 1);
-        const double w = c_tpl[band][k];
-#pragma unroll
-        for (int q = 0; q < NCC_T; ++q) d[q] = fma(win[(k + q) & (NCC_T - 1)], w, d[q]);
-        if (k >= NCC_T - 1) { const double v = win[k & (NCC_T - 1)]; core = fma(v, v, core); }
-    }
-    // window q = samples q..q+62 = head (q..6) + core (7..62) + tail (63..62+q)
-    double head[NCC_T], tail[NCC_T];
-    head[NCC_T - 1] = 0.0;
-#pragma unroll
-    for (int q = NCC_T - 2; q >= 0; --q) { const double v = NCC_V(q); head[q] = fma(v, v, head[q + 1]); }
-    tail[0] = 0.0;
-#pragma unroll
-    for (int q = 1; q < NCC_T; ++q) { const double v = NCC_V(PRE_L - 1 + q); tail[q] = fma(v, v, tail[q - 1]); }
-    double r[NCC_T];
-#pragma unroll
-    for (int q = 0; q < NCC_T; ++q) r[q] = d[q] / (sqrt((head[q] + core) + tail[q]) + 1e-12);
-#undef NCC_V
-    // stage the 8 results per thread through shared memory for coalesced stores
-    __syncthreads();
-    double* so = sy + 9 * threadIdx.x;
-#pragma unroll
-    for (int q = 0; q < NCC_T; ++q) so[q] = r[q];
-    __syncthreads();
     double* cs = corr + (long long)cb * nc;
-    for (int t = threadIdx.x; t < NCC_TILE; t += 256) {
-        const int i = i0 + t;
-        if (i < nc) cs[i] = sy[ncc_pad(t)];
+    const int ntiles = (nc + NCC_TILE - 1) / NCC_TILE;
+    const int tile0 = blockIdx.x * NCC_SPAN;
+    const int tile1 = min(ntiles, tile0 + NCC_SPAN);
+    auto fetch = [&](int tile, double* sy) {    // asynchronous copy of the tile's 2110 samples (zeros beyond the row)
+        const int i0 = tile * NCC_TILE;
+        for (int t = threadIdx.x; t < NCC_IN; t += 256) {
+            const int j = i0 + t;
+            const bool in = j < n;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(sy + ncc_pad(t))),
+                         "l"(ys + (in ? j : 0)), "r"(in ? 8 : 0));
+        }
+        asm volatile("cp.async.commit_group;");
+    };
+    if (tile0 < tile1) fetch(tile0, ncc_sm);
+    for (int tile = tile0; tile < tile1; ++tile) {
+        double* sy = ncc_sm + ((tile - tile0) & 1) * BUF;
+        if (tile + 1 < tile1) {
+            fetch(tile + 1, ncc_sm + ((tile + 1 - tile0) & 1) * BUF);      // in flight during this tile's 600 DFMAs
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        const int i0 = tile * NCC_TILE;
+        const double* sv = sy + 9 * threadIdx.x;    // ncc_pad(8*t + m) = 9*t + m + (m >> 3)
+#define NCC_V(m) sv[(m) + ((m) >> 3)]
+        double d[NCC_T], win[NCC_T];
+#pragma unroll
+        for (int q = 0; q < NCC_T; ++q) d[q] = 0.0;
+#pragma unroll
+        for (int q = 0; q < NCC_T - 1; ++q) win[q] = NCC_V(q);
+        double core = 0.0;                          // sum of v[m]^2, m = 7..62: common to the 8 windows
+#pragma unroll
+        for (int k = 0; k < PRE_L; ++k) {
+            win[(k + NCC_T - 1) & (NCC_T - 1)] = NCC_V(k + NCC_T - 1);
+            const double w = c_tpl[band][k];
+#pragma unroll
+            for (int q = 0; q < NCC_T; ++q) d[q] = fma(win[(k + q) & (NCC_T - 1)], w, d[q]);
+            if (k >= NCC_T - 1) { const double v = win[k & (NCC_T - 1)]; core = fma(v, v, core); }
+        }
+        // window q = samples q..q+62 = head (q..6) + core (7..62) + tail (63..62+q)
+        double head[NCC_T], tail[NCC_T];
+        head[NCC_T - 1] = 0.0;
+#pragma unroll
+        for (int q = NCC_T - 2; q >= 0; --q) { const double v = NCC_V(q); head[q] = fma(v, v, head[q + 1]); }
+        tail[0] = 0.0;
+#pragma unroll
+        for (int q = 1; q < NCC_T; ++q) { const double v = NCC_V(PRE_L - 1 + q); tail[q] = fma(v, v, tail[q - 1]); }
+        double r[NCC_T];
+#pragma unroll
+        for (int q = 0; q < NCC_T; ++q) r[q] = d[q] / (sqrt((head[q] + core) + tail[q]) + 1e-12);
+#undef NCC_V
+        // stage the 8 results per thread through this tile's buffer for coalesced stores
+        __syncthreads();
+        double* so = sy + 9 * threadIdx.x;
+#pragma unroll
+        for (int q = 0; q < NCC_T; ++q) so[q] = r[q];
+        __syncthreads();
+        for (int t = threadIdx.x; t < NCC_TILE; t += 256) {
+            const int i = i0 + t;
+            if (i < nc) cs[i] = sy[ncc_pad(t)];
+        }
+        __syncthreads();                            // the buffer is refilled two tiles later
     }
 }
 
@@ -1455,8 +1478,15 @@ int es_rx_ncc(const double* y, int nclips, int n, double* corr, void* stream)
     if (!g_rx_ready) { set_error("es_rx_ncc: call es_rx_set_filters first"); return ES_ENOTREADY; }
     const int nc = n - (PRE_L - 1);
     if (nclips <= 0 || nc <= 0) return ES_OK;
-    dim3 grid((nc + NCC_TILE - 1) / NCC_TILE, nclips * NBANDS);
-    ncc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(y, n, nc, corr);
+    const int ntiles = (nc + NCC_TILE - 1) / NCC_TILE;
+    const size_t smem = 2 * (size_t)(ncc_pad(NCC_IN) + 1) * sizeof(double);
+    static int configured = 0;
+    if (!configured) {
+        ES_CUDA_OK(cudaFuncSetAttribute(ncc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = 1;
+    }
+    dim3 grid((ntiles + NCC_SPAN - 1) / NCC_SPAN, nclips * NBANDS);
+    ncc_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(y, n, nc, corr);
     ES_CUDA_OK(cudaGetLastError());
     return ES_OK;
 }
