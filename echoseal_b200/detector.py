@@ -190,6 +190,8 @@ def verify_batch(keys, audio, *, fs_target: int = 48_000, list_size: int = 8, mf
             return verdicts, results
         return verdicts
 
+    # y + corr of a sub-batch are 64 bytes per input sample: keep them under ~40 GB whatever the clip length
+    sub_batch = max(1, min(int(sub_batch), int(40e9 // (64 * max(n, 1)))))
     # sub-batch boundaries: full-size in the middle, tapered (1/4, 1/2) at both ends so that the pipeline's
     # fill (first scan + enumeration before any SCL kernel runs) and drain (last validation) are short
     sizes = []
