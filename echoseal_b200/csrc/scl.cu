@@ -391,11 +391,11 @@ template <int S> struct SclLayout {
     static constexpr int BROWS_S = 7;                                    // beta words of levels 3..5 in shared memory
     static constexpr int BROWS_G = 24;                                   // beta words of levels 1..2 in global memory
     static constexpr int SNAP_BYTES = 32 * 16;                           // per-lane (metric, bptr, ord|active) at bit 512
-    static constexpr int WARP_BYTES = AROWS * 256 + BROWS_S * 128 + SNAP_BYTES;
+    static constexpr int ABYTES = (AROWS * 256 > 32 * 128) ? AROWS * 256 : 32 * 128;   // alpha rows; also holds the root partial sums
+    static constexpr int WARP_BYTES = ABYTES + BROWS_S * 128 + SNAP_BYTES;
     static constexpr int TAB_BYTES = PHI_TAB_DOUBLES * 8;
     static constexpr size_t G_ROWS = 1024 - (1 << (11 - S));           // global alpha rows, levels 1..S-1
     static constexpr size_t G_DOUBLES = G_ROWS * 32 + 1024 * 4 + BROWS_G * 16;   // + level-0 copy [1024][4] + beta rows
-    static_assert(AROWS * 256 >= 32 * 128, "alpha region must hold the root partial sums");
 };
 
 template <int S, int W>
@@ -420,7 +420,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) scl_list_kernel(SclParams P)
     L.gbase = L.lane & ~7;
     L.tab = (uint32_t)__cvta_generic_to_shared(smem_raw);
     L.sa = reinterpret_cast<double*>(wbase) + L.gbase;
-    L.sb = reinterpret_cast<uint32_t*>(wbase + (size_t)LY::AROWS * 256);
+    L.sb = reinterpret_cast<uint32_t*>(wbase + (size_t)LY::ABYTES);
     const int gwarp = blockIdx.x * W + warp;
     double* gscr = P.scratch + (size_t)gwarp * P.scratch_stride;
     L.ga = gscr + L.gbase;
@@ -430,7 +430,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) scl_list_kernel(SclParams P)
     const int nbytes = (K - 8) >> 3;
     const int ngroups = (P.nunits + 3) >> 2;
     const int nwarps = gridDim.x * W;
-    uint4* snap = reinterpret_cast<uint4*>(wbase + (size_t)LY::AROWS * 256 + LY::BROWS_S * 128) + L.lane;
+    uint4* snap = reinterpret_cast<uint4*>(wbase + (size_t)LY::ABYTES + LY::BROWS_S * 128) + L.lane;
 
     for (int grp = gwarp; grp < ngroups; grp += nwarps) {
         const int j = grp * 4 + (L.lane >> 3);
