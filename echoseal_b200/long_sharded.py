@@ -191,7 +191,9 @@ def run_simulated(det, signal48: np.ndarray, world: int, dev=None):
                 alive = False
         reqs = nxt
     if outs[0]["overflow"]:
-        raise RuntimeError("long_sharded: a selection buffer overflowed (degenerate data); use WatermarkDetector.verify")
+        # degenerate data (e.g. long digital silence: > 32768 equal values in the median's sub-bin): the single-GPU
+        # path has the radix-select fallback for that
+        return bool(det.verify(signal48, det.fs_target)), outs
     return _decode(det, outs[0], dev), outs
 
 
@@ -224,7 +226,7 @@ def verify_recording_time_sharded(det, audio, fs_in: int, device=None) -> bool:
             req = g.send(reply)
         except StopIteration:
             break
-    if out["overflow"]:
-        raise RuntimeError("long_sharded: a selection buffer overflowed (degenerate data); use WatermarkDetector.verify")
     det.last_sharded = out
+    if out["overflow"]:       # same on every rank (the flag is part of the exchanged records): all fall back together
+        return bool(det.verify(signal, det.fs_target))
     return _decode(det, out, dev)

@@ -412,3 +412,9 @@ def test_time_sharded_recording_equals_single_gpu(env):
             assert o["n_scl"] == r.n_scl, (name, world)
             for other in outs[1:]:
                 assert (other["peaks"] == o["peaks"]).all() and torch.equal(other["frames"], o["frames"])
+    # degenerate data (long digital silence): the selection buffers overflow and every rank falls back to the single-GPU path
+    sig = np.concatenate([np.zeros(300_000, np.float32), a[2][:100_500]])
+    ref = detector.WatermarkDetector(keys[2], list_size=8)
+    det = detector.WatermarkDetector(keys[2], list_size=8)
+    v, outs = long_sharded.run_simulated(det, sig, 2)
+    assert outs[0]["overflow"] and v == ref.verify(sig, 48000)
