@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libechoseal_b200.so")
+# ES_B200_LIB: developer override used by tools/build_variants.py to A/B kernel variants; the product build is in-tree
+LIB_PATH = os.environ.get("ES_B200_LIB") or os.path.join(_HERE, "libechoseal_b200.so")
 _lib = None
 
 

@@ -46,31 +46,112 @@ static int g_K = 0;
 // ---------------------------------------------------------------------------------------------
 // phi(d) = log1p(exp(-d)), d >= 0: branch-free table-driven double routine (phi_impl.h), < 1.4 ulp —
 // the same accuracy class as the reference's libm composition, a quarter of the instructions.
-// numpy's npy_logaddexp: x==y -> x+ln2 ; else max + log1p(exp(-|x-y|))
-__device__ __forceinline__ double np_logaddexp(double x, double y, uint32_t tab)
+//
+// The routine exists exactly THREE times in the kernel image, as out-of-line functions of 4, 2 and 1
+// interleaved evaluations.  The kernel is instruction-cache sensitive: with phi
+// inlined, every phi-heavy loop cost 4 KB of SASS and the hot code sat on the 32 KB edge.  ptxas
+// allocates registers across these calls (no marshalling: a call costs CALL + RET + one MOV).
+// Each routine returns mx_j + phi(d_j): the callers' "max" terms ride along, so that nothing but the results is live
+// in the caller across the call.
+struct D4 { double a, b, c, d; };
+struct D2 { double a, b; };
+
+__device__ __noinline__ D4 lse4(double m0, double d0, double m1, double d1, double m2, double d2, double m3, double d3,
+                                uint32_t tab)
 {
-    // x == y needs no special case here: phi_fast(0) == ln2 exactly (table entry 256)
-    const double d = x - y;
-    const double mx = (d > 0.0) ? x : y;
-    return mx + phi_fast(d, tab);          // phi_fast takes |d| itself
+    D4 r;
+    r.a = m0 + phi_fast(d0, tab); r.b = m1 + phi_fast(d1, tab); r.c = m2 + phi_fast(d2, tab); r.d = m3 + phi_fast(d3, tab);
+    return r;
+}
+__device__ __noinline__ D2 phi2(double d0, double d1, uint32_t tab)
+{
+    D2 r;
+    r.a = phi_fast(d0, tab); r.b = phi_fast(d1, tab);
+    return r;
+}
+__device__ __noinline__ double phi1(double d0, uint32_t tab) { return phi_fast(d0, tab); }
+
+// numpy's npy_logaddexp: x==y -> x+ln2 ; else max + log1p(exp(-|x-y|)).  x == y needs no special case here:
+// phi_fast(0) == ln2 exactly (table entry 256).  f = logaddexp(a,b) - logaddexp(0,a+b) for two element pairs
+// at once (four independent phi chains).
+__device__ __forceinline__ void fcomb2(double a0, double b0, double a1, double b1, uint32_t tab, double& r0, double& r1)
+{
+    const double d0 = a0 - b0, s0 = a0 + b0, d1 = a1 - b1, s1 = a1 + b1;
+    const D4 P = lse4((d0 > 0.0) ? a0 : b0, d0, ((0.0 - s0) > 0.0) ? 0.0 : s0, s0,
+                      (d1 > 0.0) ? a1 : b1, d1, ((0.0 - s1) > 0.0) ? 0.0 : s1, s1, tab);     // phi takes |d| itself
+    r0 = P.a - P.b;
+    r1 = P.c - P.d;
 }
 
-__device__ __forceinline__ double fcomb(double a, double b, uint32_t tab)
-{
-    return np_logaddexp(a, b, tab) - np_logaddexp(0.0, a + b, tab);
-}
-
-// same value as fcomb(a, b), also handing out the two phi terms: fm = phi(|a-b|), fp = phi(|a+b|).
+// same value as f(a, b), also handing out the two phi terms: fm = phi(|a-b|), fp = phi(|a+b|).
 // They are exactly the phi values the reference's penalty needs for the NEXT (odd) leaf, whose LLR is
 // b-a or b+a (rtwm/fastpolar.py:26-40) — so that penalty costs nothing.
 __device__ __forceinline__ double fcomb_parts(double a, double b, uint32_t tab, double& fm, double& fp)
 {
     const double d = a - b, s = a + b;
-    fm = phi_fast(d, tab);
-    fp = phi_fast(s, tab);
+    const D2 P = phi2(d, s, tab);
+    fm = P.a;
+    fp = P.b;
     const double A = ((d > 0.0) ? a : b) + fm;
     const double B = (((0.0 - s) > 0.0) ? 0.0 : s) + fp;
     return A - B;
+}
+
+// g = b + (1-2u) a (rtwm/fastpolar.py:26-29): (1-2u)*a is exact, so flipping the sign bit of a is the same number
+__device__ __forceinline__ double gcomb(double a, double b, uint32_t u)
+{
+    const double sa = __hiloint2double(__double2hiint(a) ^ (int)(u << 31), __double2loint(a));
+    return b + sa;
+}
+
+// ---------------------------------------------------------------------------------------------
+// asynchronous staging: cp.async.bulk (TMA, SASS UBLKCP) global -> shared, completion on an mbarrier
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// generic-proxy writes (st.global / st.shared) before, async-proxy accesses (bulk copies) after
+#ifndef ES_SCL_DBG_DELAY
+#define ES_SCL_DBG_DELAY 0
+#endif
+#ifndef ES_SCL_DBG_FENCE
+#define ES_SCL_DBG_FENCE 0
+#endif
+__device__ __forceinline__ void fence_proxy_async()
+{
+#if ES_SCL_DBG_FENCE
+    __threadfence_system();
+    asm volatile("fence.proxy.async.global;" ::: "memory");
+#endif
+    asm volatile("fence.proxy.async;" ::: "memory");
+#if ES_SCL_DBG_DELAY
+    __threadfence();
+    __nanosleep(ES_SCL_DBG_DELAY);
+#endif
+}
+__device__ __forceinline__ double lds_f64(uint32_t addr)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -93,19 +174,80 @@ struct SclParams {
     int32_t* npaths;         // [ncw_total]
 };
 
+constexpr int SCL_S = 6;   // first LLR-tree level kept in shared memory
+#ifndef ES_SCL_STAGED
+#define ES_SCL_STAGED 1      // fused g+f passes over the DRAM-resident levels (0: one g pass, then one f pass per level)
+#endif
+#ifndef ES_SCL_TMA
+#define ES_SCL_TMA 0         // 1: the passes read their source rows from the TMA-fed ring; 0: straight from global memory (faster so far)
+#endif
+#ifndef ES_SCL_TMA_GF
+#define ES_SCL_TMA_GF ES_SCL_TMA
+#endif
+#ifndef ES_SCL_TMA_F
+#define ES_SCL_TMA_F ES_SCL_TMA
+#endif
+constexpr int RING_STAGES = 2;      // the passes toggle between two stages (st ^= 1)
+constexpr int RING_STAGE_ROWS = 8;
+constexpr int RING_STAGE_BYTES = RING_STAGE_ROWS * 256;
+
+#ifndef ES_SCL_W
+#define ES_SCL_W 16
+#endif
+#ifndef ES_SCL_MAXNREG
+#define ES_SCL_MAXNREG ((65536 / (ES_SCL_W * 32)) / 8 * 8 > 255 ? 255 : (65536 / (ES_SCL_W * 32)) / 8 * 8)   // one CTA per SM owns the register file
+#endif
+template <int S> struct SclLayout {
+    static constexpr int AROWS = (1 << (11 - S)) - 4;                   // levels S..8 (9 and 10 live in registers)
+    static constexpr int BROWS_S = 7;                                    // beta words of levels 3..5 in shared memory
+    static constexpr int BROWS_G = 24;                                   // beta words of levels 1..2 in global memory
+    static constexpr int SNAP_BYTES = 32 * 16;                           // per-lane (metric, bptr, ord|active) at bit 512
+    static constexpr int ABYTES = (AROWS * 256 > 32 * 128) ? AROWS * 256 : 32 * 128;   // alpha rows; also holds the root partial sums
+    static constexpr int RING_BYTES = RING_STAGES * RING_STAGE_BYTES;     // TMA staging ring of the DRAM-level passes
+    static constexpr int RING_OFF = ABYTES + BROWS_S * 128 + SNAP_BYTES;
+    static constexpr int BAR_OFF = RING_OFF + RING_BYTES;                 // one 8-byte mbarrier per stage
+    static constexpr int WARP_BYTES = BAR_OFF + 16;
+    static constexpr int TAB_BYTES = PHI_TAB_DOUBLES * 8;
+    static constexpr size_t G_ROWS = 1024 - (1 << (11 - S));           // global alpha rows, levels 1..S-1
+    static constexpr size_t G_DOUBLES = G_ROWS * 32 + 1024 * 4 + BROWS_G * 16;   // + level-0 copy [1024][4] + beta rows
+};
+
+using SclLY = SclLayout<SCL_S>;
+
+// shared-window address of the CTA's dynamic shared memory (the phi tables sit at its start)
+__device__ __forceinline__ uint32_t smem_base()
+{
+    extern __shared__ __align__(16) unsigned char es_smem[];
+    return (uint32_t)__cvta_generic_to_shared(es_smem);
+}
+
+// The per-lane addresses are all derived from three words (the warp's shared-memory window address, its global
+// scratch pointer, the lane id) on the spot: a dozen pointer registers held across the whole decode were what
+// kept ptxas from interleaving the four chains of phi4 at 128 registers per thread.
 struct Lane {
-    double* sa;          // shared alpha rows (+gbase)
-    uint32_t* sb;        // shared beta words, levels 3..5 (row stride 32 words)
-    uint32_t* gb;        // global beta words, levels 1..2 (rarely touched)
-    double* ga;          // global alpha rows, levels 1..S-1 (+gbase)
-    double* g0;          // global level-0 copy of this warp's 4 codewords, [k][4] (+codeword)
-    uint32_t tab;        // shared-window address of the phi tables
-    int lane, p, gbase;
+    uint32_t wsm;        // shared-window address of this warp's region (alpha rows first)
+    double* gw;          // this warp's global scratch: alpha rows of levels 1..S-1, level-0 copy, beta rows
+    int lane;
     double m;
     uint32_t ptr, bptr, bs;
     int ord;
     bool active;
     bool neg;            // decoding the sign-flipped variant: level 0 is negated when bit 512 is reached
+    uint32_t rphase;     // staging ring: bit st = parity the next wait on stage st has to see
+
+    __device__ __forceinline__ int p() const { return lane & 7; }               // list path = slot owned by this lane
+    __device__ __forceinline__ int gbase() const { return lane & 24; }          // first lane of this lane's codeword
+    __device__ __forceinline__ double* sa() const                               // shared alpha rows (+gbase)
+    { return reinterpret_cast<double*>(__cvta_shared_to_generic(wsm)) + gbase(); }
+    __device__ __forceinline__ uint32_t* sb() const                             // shared beta words, levels 3..5
+    { return reinterpret_cast<uint32_t*>(__cvta_shared_to_generic(wsm + SclLY::ABYTES)); }
+    __device__ __forceinline__ uint32_t* gb() const                             // global beta words, levels 1..2
+    { return reinterpret_cast<uint32_t*>(gw + SclLY::G_ROWS * 32 + 1024 * 4); }
+    __device__ __forceinline__ double* ga() const { return gw + gbase(); }      // global alpha rows (+gbase)
+    __device__ __forceinline__ double* g0() const { return gw + SclLY::G_ROWS * 32 + (lane >> 3); }   // level-0 copy [k][4]
+    __device__ __forceinline__ uint32_t tab() const { return smem_base(); }     // phi tables
+    __device__ __forceinline__ uint32_t ring() const { return wsm + SclLY::RING_OFF; }   // stage st at + st * RING_STAGE_BYTES
+    __device__ __forceinline__ uint32_t rbar() const { return wsm + SclLY::BAR_OFF; }    // its mbarrier at + 8 * st
 };
 
 struct LvlRef { double* base; int stride; };
@@ -114,36 +256,33 @@ struct LvlRef { double* base; int stride; };
 __device__ __forceinline__ uint32_t* beta_rows(const Lane& L, int l)
 {
     // shared: level 5 -> row 0, level 4 -> rows 1..2, level 3 -> rows 3..6 ; global: level 2 -> rows 0..7, level 1 -> rows 8..23
-    return (l >= 3) ? L.sb + ((1 << (5 - l)) - 1) * 32 : L.gb + ((l == 2) ? 0 : 8) * 32;
+    return (l >= 3) ? L.sb() + ((1 << (5 - l)) - 1) * 32 : L.gb() + ((l == 2) ? 0 : 8) * 32;
 }
 
 // element k of level lv in `slot` lives at ref.base[k * ref.stride]
 template <int S> __device__ __forceinline__ LvlRef lvl_ref(const Lane& L, int lv, int slot)
 {
     LvlRef r;
-    if (lv == 0) { r.base = L.g0; r.stride = 4; }
-    else if (lv >= S) { r.base = L.sa + (((1 << (11 - S)) - (1 << (11 - lv))) * 32) + slot; r.stride = 32; }
-    else { r.base = L.ga + ((1024 - (1 << (11 - lv))) * 32) + slot; r.stride = 32; }
+    if (lv == 0) { r.base = L.g0(); r.stride = 4; }
+    else if (lv >= S) { r.base = L.sa() + (((1 << (11 - S)) - (1 << (11 - lv))) * 32) + slot; r.stride = 32; }
+    else { r.base = L.ga() + ((1024 - (1 << (11 - lv))) * 32) + slot; r.stride = 32; }
     return r;
 }
 
-// the one place the f-combine of a whole level is evaluated: dst[k*ds] = f(a[k*ss], b[k*ss]), k < count,
-// count even (callers guarantee it).  Two elements per trip (4 independent phi chains) with the next
-// pair's operands prefetched.  ONE copy on purpose: the kernel is instruction-cache sensitive.
+// f-combine of a whole node through generic pointers (the shared-memory levels and the bit-0 spine; the DRAM
+// levels go through pass_gf / pass_f): dst[k*ds] = f(a[k*ss], b[k*ss]), k < count, count even (callers
+// guarantee it).  Two elements per trip = four independent phi chains.
 __device__ __noinline__ void f_loop(const double* a, const double* b, int ss, double* dst, int ds, int count,
                                     uint32_t tab)
 {
     if (count < 2) return;
-    double a0 = a[0], b0 = b[0], a1 = a[ss], b1 = b[ss];
 #pragma unroll 1
     for (int k = 0; k + 2 <= count; k += 2) {
-        const int kn = (k + 4 <= count) ? (k + 2) : k;      // prefetch (re-reads the last pair at the end)
-        const double na0 = a[kn * ss], nb0 = b[kn * ss], na1 = a[(kn + 1) * ss], nb1 = b[(kn + 1) * ss];
-        const double r0 = fcomb(a0, b0, tab);
-        const double r1 = fcomb(a1, b1, tab);
+        const double a0 = a[k * ss], b0 = b[k * ss], a1 = a[(k + 1) * ss], b1 = b[(k + 1) * ss];
+        double r0, r1;
+        fcomb2(a0, b0, a1, b1, tab, r0, r1);
         dst[k * ds] = r0;
         dst[(k + 1) * ds] = r1;
-        a0 = na0; b0 = nb0; a1 = na1; b1 = nb1;
     }
 }
 
@@ -151,10 +290,10 @@ template <int S>
 __device__ __forceinline__ void f_level(Lane& L, int lv)   // 2 <= lv <= 10, parent in own slot
 {
     const int s = 1 << (10 - lv);
-    const LvlRef src = lvl_ref<S>(L, lv - 1, L.p);
-    const LvlRef dst = lvl_ref<S>(L, lv, L.p);
-    f_loop(src.base, src.base + s * src.stride, src.stride, dst.base, dst.stride, s, L.tab);
-    L.ptr = (L.ptr & ~(7u << (3 * (lv - 1)))) | ((uint32_t)L.p << (3 * (lv - 1)));
+    const LvlRef src = lvl_ref<S>(L, lv - 1, L.p());
+    const LvlRef dst = lvl_ref<S>(L, lv, L.p());
+    f_loop(src.base, src.base + s * src.stride, src.stride, dst.base, dst.stride, s, L.tab());
+    L.ptr = (L.ptr & ~(7u << (3 * (lv - 1)))) | ((uint32_t)L.p() << (3 * (lv - 1)));
 }
 
 // g over one level l0 (1..10): dst[k] = par[k+s] +- par[k], sign from the left-child partial sums
@@ -164,7 +303,7 @@ __device__ __forceinline__ void g_level(Lane& L, int l0)
     const int s = 1 << (10 - l0);
     const int ps = (l0 >= 2) ? ((L.ptr >> (3 * (l0 - 2))) & 7) : 0;
     const LvlRef src = lvl_ref<S>(L, l0 - 1, ps);
-    const LvlRef dst = lvl_ref<S>(L, l0, L.p);
+    const LvlRef dst = lvl_ref<S>(L, l0, L.p());
     const double* pa = src.base;
     const double* pb = src.base + s * src.stride;
     if (s <= 16) {   // levels 6..8: bits in the bs register; all loads first (s = 4, 8 or 16)
@@ -180,7 +319,7 @@ __device__ __forceinline__ void g_level(Lane& L, int l0)
         }
     } else {         // levels 1..5: bits in pointer-indirected words; 16 elements (32 loads) in flight
         const int bsl = (L.bptr >> (3 * (l0 - 1))) & 7;
-        const uint32_t* bw = beta_rows(L, l0) + L.gbase + bsl;
+        const uint32_t* bw = beta_rows(L, l0) + L.gbase() + bsl;
 #pragma unroll 1
         for (int k0 = 0; k0 < s; k0 += 16) {
             const uint32_t word = bw[(k0 >> 5) * 32] >> (k0 & 31);
@@ -195,7 +334,7 @@ __device__ __forceinline__ void g_level(Lane& L, int l0)
                 dst.base[(k0 + kk) * dst.stride] = ((word >> kk) & 1u) ? (vb[kk] - va[kk]) : (vb[kk] + va[kk]);
         }
     }
-    L.ptr = (L.ptr & ~(7u << (3 * (l0 - 1)))) | ((uint32_t)L.p << (3 * (l0 - 1)));
+    L.ptr = (L.ptr & ~(7u << (3 * (l0 - 1)))) | ((uint32_t)L.p() << (3 * (l0 - 1)));
 }
 
 // level-0 copy of one codeword, this lane's share (k = p, p+8, ...): x -> -x.  Out of line: runs once per decode.
@@ -215,23 +354,231 @@ __device__ __forceinline__ void spine(Lane& L)
         const LvlRef src = lvl_ref<S>(L, lv - 1, 0);
         const LvlRef dst = lvl_ref<S>(L, lv, 0);
         const int P = (s >= 16) ? 8 : (s >> 1);              // participating lanes; each gets an even count
-        const int count = (L.p < P) ? (s / P) : 0;
-        const double* pa = src.base + L.p * src.stride;
-        f_loop(pa, pa + s * src.stride, P * src.stride, dst.base + L.p * dst.stride, P * dst.stride, count, L.tab);
+        const int count = (L.p() < P) ? (s / P) : 0;
+        const double* pa = src.base + L.p() * src.stride;
+        f_loop(pa, pa + s * src.stride, P * src.stride, dst.base + L.p() * dst.stride, P * dst.stride, count, L.tab());
         __syncwarp();
     }
     L.ptr = 0;
 }
 
-// levels 1..8 for the quad starting at bit i (i % 4 == 0, i > 0): one g node, then f nodes down to level 8.
+// ---------------------------------------------------------------------------------------------
+// passes over the DRAM-resident levels (1..S-1).  A level is [element][codeword(4)][slot(8)], one 256-byte row
+// per element, so the rows a pass needs are contiguous: lane 0 streams them into the warp's ring with
+// cp.async.bulk (TMA) two stages ahead, completion on one mbarrier per stage, and every lane reads its own
+// (codeword, slot) column of the landed rows.  Results go straight to their level (coalesced 256-byte rows).
+// ---------------------------------------------------------------------------------------------
+#ifndef ES_SCL_DBG_VERIFY
+#define ES_SCL_DBG_VERIFY 0
+#endif
+#if ES_SCL_DBG_VERIFY
+__device__ unsigned long long g_dbg[256];
+__device__ __forceinline__ void dbg_check(double staged, const double* direct, int kind, int lvl, int c, int which, int lane)
+{
+    const double v = __ldcg(direct);
+    if (__double_as_longlong(v) != __double_as_longlong(staged)) {
+        const unsigned long long n = atomicAdd(&g_dbg[0], 1ull);
+        if (n < 60) {
+            g_dbg[4 + 4 * n] = ((unsigned long long)kind << 56) | ((unsigned long long)lvl << 48) | ((unsigned long long)c << 32) |
+                               ((unsigned long long)which << 8) | (unsigned long long)lane | ((unsigned long long)blockIdx.x << 16);
+            g_dbg[5 + 4 * n] = (unsigned long long)__double_as_longlong(staged);
+            g_dbg[6 + 4 * n] = (unsigned long long)__double_as_longlong(v);
+            g_dbg[7 + 4 * n] = clock64();
+        }
+    }
+}
+#endif
+// first global row of level lv (1..5)
+__device__ __forceinline__ int lvl_row0(int lv) { return 1024 - (1 << (11 - lv)); }
+
+// lane 0: queue one stage of `nseg` segments of `segbytes` each; segment j starts at source row seg_row[j]
+__device__ __forceinline__ void ring_issue(const Lane& L, const double* gw, int st, int nseg, uint32_t segbytes,
+                                           int r0, int r1, int r2, int r3)
+{
+    const uint32_t bar = L.rbar() + 8u * st;
+    const uint32_t dst = L.ring() + (uint32_t)st * RING_STAGE_BYTES;
+    mbar_expect_tx(bar, segbytes * nseg);
+    bulk_g2s(dst, gw + (size_t)r0 * 32, segbytes, bar);
+    bulk_g2s(dst + segbytes, gw + (size_t)r1 * 32, segbytes, bar);
+    if (nseg == 4) {
+        bulk_g2s(dst + 2 * segbytes, gw + (size_t)r2 * 32, segbytes, bar);
+        bulk_g2s(dst + 3 * segbytes, gw + (size_t)r3 * 32, segbytes, bar);
+    }
+}
+
+// All lanes hold the eight values of the current stage in registers: the stage may be refilled.  A plain
+// __syncwarp() is not enough — the loads above are only ISSUED at that point, and a bulk copy queued right
+// behind them was measured to overtake them (about one corrupted group in 3000).  A warp vote on the loaded
+// words cannot issue before every lane's loads have returned; the branch it feeds is never taken for the
+// finite numbers of an LLR tree and would be harmless if it were.
+__device__ __forceinline__ void ring_release(double v0, double v1, double v2, double v3, double v4, double v5, double v6,
+                                             double v7)
+{
+    const int w = __double2hiint(v0) ^ __double2hiint(v1) ^ __double2hiint(v2) ^ __double2hiint(v3) ^
+                  __double2hiint(v4) ^ __double2hiint(v5) ^ __double2hiint(v6) ^ __double2hiint(v7);
+    if (__any_sync(0xffffffffu, w == 0x7ff80123)) __nanosleep(2000);
+}
+
+// g node of level l0 (2..5) from its parent (slot ps of level l0-1), fused with the f node of level l0+1 below
+// it when do_f: per trip the parent rows k, k+h, k+s, k+s+h (two elements each) give g[k], g[k+h] (stored: the
+// g node of level l0+1 needs them later) and f(g[k], g[k+h]) — the g node is never read back for its f child.
+template <int S>
+__device__ __forceinline__ void pass_gf(Lane& L, const double* gw, int l0, bool do_f)
+{
+    const int s = 1 << (10 - l0), h = s >> 1;
+    const int ps = (L.ptr >> (3 * (l0 - 2))) & 7;
+    const int srow = lvl_row0(l0 - 1);
+    double* gdst = L.ga() + lvl_row0(l0) * 32 + L.p();
+    double* fdst = lvl_ref<S>(L, l0 + 1, L.p()).base;           // global (l0+1 < S) or shared; row stride 32 doubles
+    const uint32_t* bw = beta_rows(L, l0) + L.gbase() + ((L.bptr >> (3 * (l0 - 1))) & 7);
+    const int nch = h >> 1;
+#if ES_SCL_TMA_GF
+    const uint32_t col = (uint32_t)(L.gbase() + ps) * 8u;
+    fence_proxy_async();
+    __syncwarp();
+    if (L.lane == 0) {
+        ring_issue(L, gw, 0, 4, 512u, srow, srow + h, srow + s, srow + s + h);
+        if (nch > 1) ring_issue(L, gw, 1, 4, 512u, srow + 2, srow + h + 2, srow + s + 2, srow + s + h + 2);
+    }
+    __syncwarp();
+    int st = 0;
+#else
+    const double* src = gw + (size_t)srow * 32 + L.gbase() + ps;
+#endif
+#pragma unroll 1
+    for (int c = 0; c < nch; ++c) {
+        const int k = 2 * c;
+        double a0, a1, ah0, ah1, b0, b1, bh0, bh1;
+#if ES_SCL_TMA_GF
+        mbar_wait(L.rbar() + 8u * st, (L.rphase >> st) & 1u);
+        L.rphase ^= 1u << st;
+        const uint32_t sb = L.ring() + (uint32_t)st * RING_STAGE_BYTES + col;
+        a0 = lds_f64(sb); a1 = lds_f64(sb + 256);
+        ah0 = lds_f64(sb + 512); ah1 = lds_f64(sb + 768);
+        b0 = lds_f64(sb + 1024); b1 = lds_f64(sb + 1280);
+        bh0 = lds_f64(sb + 1536); bh1 = lds_f64(sb + 1792);
+#if ES_SCL_DBG_VERIFY
+        {
+            const double* dsrc = gw + (size_t)srow * 32 + L.gbase() + ps;
+            const int k = 2 * c;
+            dbg_check(a0, dsrc + k * 32, 1, l0, c, 0, L.lane); dbg_check(a1, dsrc + (k + 1) * 32, 1, l0, c, 1, L.lane);
+            dbg_check(ah0, dsrc + (k + h) * 32, 1, l0, c, 2, L.lane); dbg_check(ah1, dsrc + (k + h + 1) * 32, 1, l0, c, 3, L.lane);
+            dbg_check(b0, dsrc + (s + k) * 32, 1, l0, c, 4, L.lane); dbg_check(b1, dsrc + (s + k + 1) * 32, 1, l0, c, 5, L.lane);
+            dbg_check(bh0, dsrc + (s + k + h) * 32, 1, l0, c, 6, L.lane); dbg_check(bh1, dsrc + (s + k + h + 1) * 32, 1, l0, c, 7, L.lane);
+        }
+#endif
+        ring_release(a0, a1, ah0, ah1, b0, b1, bh0, bh1);
+        if (L.lane == 0 && c + RING_STAGES < nch) {
+            const int r = srow + 2 * (c + RING_STAGES);
+            ring_issue(L, gw, st, 4, 512u, r, r + h, r + s, r + s + h);
+        }
+        st ^= 1;
+#else
+        a0 = src[k * 32]; a1 = src[(k + 1) * 32];
+        ah0 = src[(k + h) * 32]; ah1 = src[(k + h + 1) * 32];
+        b0 = src[(s + k) * 32]; b1 = src[(s + k + 1) * 32];
+        bh0 = src[(s + k + h) * 32]; bh1 = src[(s + k + h + 1) * 32];
+#endif
+        const uint32_t w0 = bw[(k >> 5) * 32] >> (k & 31);
+        const uint32_t w1 = bw[((k + h) >> 5) * 32] >> ((k + h) & 31);
+        const double g0 = gcomb(a0, b0, w0 & 1u), g1 = gcomb(a1, b1, (w0 >> 1) & 1u);
+        const double gh0 = gcomb(ah0, bh0, w1 & 1u), gh1 = gcomb(ah1, bh1, (w1 >> 1) & 1u);
+        gdst[k * 32] = g0; gdst[(k + 1) * 32] = g1;
+        gdst[(k + h) * 32] = gh0; gdst[(k + h + 1) * 32] = gh1;
+        if (do_f) {
+            double r0, r1;
+            fcomb2(g0, gh0, g1, gh1, L.tab(), r0, r1);
+            fdst[k * 32] = r0; fdst[(k + 1) * 32] = r1;
+        }
+    }
+    uint32_t ptr = (L.ptr & ~(7u << (3 * (l0 - 1)))) | ((uint32_t)L.p() << (3 * (l0 - 1)));
+    if (do_f) ptr = (ptr & ~(7u << (3 * l0))) | ((uint32_t)L.p() << (3 * l0));
+    L.ptr = ptr;
+}
+
+// f node of level lv (2..S) from the node of level lv-1 in the lane's own slot (just written by the pass above it)
+template <int S>
+__device__ __forceinline__ void pass_f(Lane& L, const double* gw, int lv)
+{
+    const int s = 1 << (10 - lv);
+    const int srow = lvl_row0(lv - 1);
+    double* fdst = lvl_ref<S>(L, lv, L.p()).base;
+    const int nch = s >> 2;                                   // four elements per stage (s >= 16 for lv <= 6)
+#if ES_SCL_TMA_F
+    const uint32_t col = (uint32_t)(L.gbase() + L.p()) * 8u;
+    fence_proxy_async();
+    __syncwarp();
+    if (L.lane == 0) {
+        ring_issue(L, gw, 0, 2, 1024u, srow, srow + s, 0, 0);
+        if (nch > 1) ring_issue(L, gw, 1, 2, 1024u, srow + 4, srow + s + 4, 0, 0);
+    }
+    __syncwarp();
+    int st = 0;
+#else
+    const double* src = gw + (size_t)srow * 32 + L.gbase() + L.p();
+#endif
+#pragma unroll 1
+    for (int c = 0; c < nch; ++c) {
+        const int k = 4 * c;
+        double a0, a1, a2, a3, b0, b1, b2, b3;
+#if ES_SCL_TMA_F
+        mbar_wait(L.rbar() + 8u * st, (L.rphase >> st) & 1u);
+        L.rphase ^= 1u << st;
+        const uint32_t sb = L.ring() + (uint32_t)st * RING_STAGE_BYTES + col;
+        a0 = lds_f64(sb); a1 = lds_f64(sb + 256); a2 = lds_f64(sb + 512); a3 = lds_f64(sb + 768);
+        b0 = lds_f64(sb + 1024); b1 = lds_f64(sb + 1280); b2 = lds_f64(sb + 1536); b3 = lds_f64(sb + 1792);
+#if ES_SCL_DBG_VERIFY
+        {
+            const double* dsrc = gw + (size_t)srow * 32 + L.gbase() + L.p();
+            const int k = 4 * c;
+            dbg_check(a0, dsrc + k * 32, 2, lv, c, 0, L.lane); dbg_check(a1, dsrc + (k + 1) * 32, 2, lv, c, 1, L.lane);
+            dbg_check(a2, dsrc + (k + 2) * 32, 2, lv, c, 2, L.lane); dbg_check(a3, dsrc + (k + 3) * 32, 2, lv, c, 3, L.lane);
+            dbg_check(b0, dsrc + (s + k) * 32, 2, lv, c, 4, L.lane); dbg_check(b1, dsrc + (s + k + 1) * 32, 2, lv, c, 5, L.lane);
+            dbg_check(b2, dsrc + (s + k + 2) * 32, 2, lv, c, 6, L.lane); dbg_check(b3, dsrc + (s + k + 3) * 32, 2, lv, c, 7, L.lane);
+        }
+#endif
+        ring_release(a0, a1, a2, a3, b0, b1, b2, b3);
+        if (L.lane == 0 && c + RING_STAGES < nch) {
+            const int r = srow + 4 * (c + RING_STAGES);
+            ring_issue(L, gw, st, 2, 1024u, r, r + s, 0, 0);
+        }
+        st ^= 1;
+#else
+        a0 = src[k * 32]; a1 = src[(k + 1) * 32]; a2 = src[(k + 2) * 32]; a3 = src[(k + 3) * 32];
+        b0 = src[(s + k) * 32]; b1 = src[(s + k + 1) * 32]; b2 = src[(s + k + 2) * 32]; b3 = src[(s + k + 3) * 32];
+#endif
+        double r0, r1, r2, r3;
+        fcomb2(a0, b0, a1, b1, L.tab(), r0, r1);
+        fcomb2(a2, b2, a3, b3, L.tab(), r2, r3);
+        fdst[k * 32] = r0; fdst[(k + 1) * 32] = r1; fdst[(k + 2) * 32] = r2; fdst[(k + 3) * 32] = r3;
+    }
+    L.ptr = (L.ptr & ~(7u << (3 * (lv - 1)))) | ((uint32_t)L.p() << (3 * (lv - 1)));
+}
+
+// levels 1..8 for the quad starting at bit i (i % 4 == 0, i > 0): one g node, then f nodes down to level `last`.
 // Levels 9 and 10 never touch memory: the quad routine in the kernel keeps them in registers.
 template <int S>
-__device__ __forceinline__ void llr_update8(Lane& L, int i, int last)   // last: deepest level wanted, l0 <= last <= 8
+__device__ __forceinline__ void llr_update8(Lane& L, const double* gw, int i, int last)   // l0 <= last <= 8
 {
     const int l0 = 11 - __ffs(i);    // <= 8
-    g_level<S>(L, l0);
+    int lv;
+#if ES_SCL_STAGED
+    if (l0 >= 2 && l0 < S) {
+        const bool fuse = last > l0;
+        pass_gf<S>(L, gw, l0, fuse);
+        lv = l0 + (fuse ? 2 : 1);
+    } else
+#endif
+    {
+        g_level<S>(L, l0);
+        lv = l0 + 1;
+    }
+#if ES_SCL_STAGED
 #pragma unroll 1
-    for (int lv = l0 + 1; lv <= last; ++lv) f_level<S>(L, lv);
+    for (; lv <= last && lv <= S; ++lv) pass_f<S>(L, gw, lv);
+#endif
+#pragma unroll 1
+    for (; lv <= last; ++lv) f_level<S>(L, lv);
 }
 
 // Rate-0 node: all `count` (multiple of 4) bits below the node are frozen, so every path's decisions there
@@ -244,10 +591,11 @@ __device__ __noinline__ double r0_sum(const double* a, int stride, int count, ui
 #pragma unroll 1
     for (int k = 0; k < count; k += 4) {
         const double a0 = a[k * stride], a1 = a[(k + 1) * stride], a2 = a[(k + 2) * stride], a3 = a[(k + 3) * stride];
-        s0 += phi_fast(fabs(a0), tab) + fmax(a0, 0.0);
-        s1 += phi_fast(fabs(a1), tab) + fmax(a1, 0.0);
-        s2 += phi_fast(fabs(a2), tab) + fmax(a2, 0.0);
-        s3 += phi_fast(fabs(a3), tab) + fmax(a3, 0.0);
+        const D4 P = lse4(fmax(a0, 0.0), a0, fmax(a1, 0.0), a1, fmax(a2, 0.0), a2, fmax(a3, 0.0), a3, tab);   // phi takes |a| itself
+        s0 += P.a;
+        s1 += P.b;
+        s2 += P.c;
+        s3 += P.d;
     }
     return (s0 + s1) + (s2 + s3);
 }
@@ -290,12 +638,12 @@ __device__ __forceinline__ int info_step(Lane& L, int list_size, double pen0, do
     }
     const bool s0 = L.active && (r0 < list_size);
     const bool s1 = L.active && (r1 < list_size);
-    const uint32_t cm = (__ballot_sync(full, s0 && s1) >> L.gbase) & 0xffu;
-    const uint32_t fm = (__ballot_sync(full, !(s0 || s1)) >> L.gbase) & 0xffu;
+    const uint32_t cm = (__ballot_sync(full, s0 && s1) >> L.gbase()) & 0xffu;
+    const uint32_t fm = (__ballot_sync(full, !(s0 || s1)) >> L.gbase()) & 0xffu;
     // clone source for free lanes (j-th free lane takes the j-th clone)
-    const int jfree = __popc(fm & ((1u << L.p) - 1u));
+    const int jfree = __popc(fm & ((1u << L.p()) - 1u));
     const bool take = !(s0 || s1) && (jfree < __popc(cm));
-    const int src = take ? nth_set8(cm, jfree) : L.p;
+    const int src = take ? nth_set8(cm, jfree) : L.p();
     const double cm1 = __shfl_sync(full, m1, src, 8);
     const int cr1 = __shfl_sync(full, r1, src, 8);
     const uint32_t cptr = __shfl_sync(full, L.ptr, src, 8);
@@ -346,8 +694,8 @@ __device__ __forceinline__ void beta_update_quad(Lane& L, int q, uint32_t X, uin
         const uint32_t mask = (s == 16) ? 0xffff0000u : (((1u << s) - 1u) << s);
         L.bs = (L.bs & ~mask) | (X << s);
     } else if (t1 == 3) {
-        L.sb[L.lane] = X;                       // level 5, word offset 0
-        L.bptr = (L.bptr & ~(7u << 12)) | ((uint32_t)L.p << 12);
+        L.sb()[L.lane] = X;                       // level 5, word offset 0
+        L.bptr = (L.bptr & ~(7u << 12)) | ((uint32_t)L.p() << 12);
     } else {
         const int lstar = 8 - t1;               // 4..0
         uint32_t* D = (lstar == 0) ? (xroot + L.lane) : (beta_rows(L, lstar) + L.lane);
@@ -355,7 +703,7 @@ __device__ __forceinline__ void beta_update_quad(Lane& L, int q, uint32_t X, uin
         int n = 1;
         for (int l = 5; l > lstar; --l) {
             const int bsl = (L.bptr >> (3 * (l - 1))) & 7;
-            const uint32_t* Lp = beta_rows(L, l) + L.gbase + bsl;
+            const uint32_t* Lp = beta_rows(L, l) + L.gbase() + bsl;
             for (int w = 0; w < n; ++w) {
                 const uint32_t x = D[w * 32];
                 D[(n + w) * 32] = x;
@@ -363,7 +711,7 @@ __device__ __forceinline__ void beta_update_quad(Lane& L, int q, uint32_t X, uin
             }
             n <<= 1;
         }
-        if (lstar > 0) L.bptr = (L.bptr & ~(7u << (3 * (lstar - 1)))) | ((uint32_t)L.p << (3 * (lstar - 1)));
+        if (lstar > 0) L.bptr = (L.bptr & ~(7u << (3 * (lstar - 1)))) | ((uint32_t)L.p() << (3 * (lstar - 1)));
     }
 }
 
@@ -386,20 +734,8 @@ __device__ __forceinline__ uint8_t crc8_step_bit(uint8_t reg, uint32_t bit)
 // ---------------------------------------------------------------------------------------------
 // list decoder kernel: W warps per CTA share the phi tables; each warp decodes 4 codewords at a time
 // ---------------------------------------------------------------------------------------------
-template <int S> struct SclLayout {
-    static constexpr int AROWS = (1 << (11 - S)) - 4;                   // levels S..8 (9 and 10 live in registers)
-    static constexpr int BROWS_S = 7;                                    // beta words of levels 3..5 in shared memory
-    static constexpr int BROWS_G = 24;                                   // beta words of levels 1..2 in global memory
-    static constexpr int SNAP_BYTES = 32 * 16;                           // per-lane (metric, bptr, ord|active) at bit 512
-    static constexpr int ABYTES = (AROWS * 256 > 32 * 128) ? AROWS * 256 : 32 * 128;   // alpha rows; also holds the root partial sums
-    static constexpr int WARP_BYTES = ABYTES + BROWS_S * 128 + SNAP_BYTES;
-    static constexpr int TAB_BYTES = PHI_TAB_DOUBLES * 8;
-    static constexpr size_t G_ROWS = 1024 - (1 << (11 - S));           // global alpha rows, levels 1..S-1
-    static constexpr size_t G_DOUBLES = G_ROWS * 32 + 1024 * 4 + BROWS_G * 16;   // + level-0 copy [1024][4] + beta rows
-};
-
 template <int S, int W>
-__global__ void __launch_bounds__(W * 32, 16 / W) scl_list_kernel(SclParams P)
+__global__ void __maxnreg__(ES_SCL_MAXNREG) scl_list_kernel(SclParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     using LY = SclLayout<S>;
@@ -408,29 +744,32 @@ __global__ void __launch_bounds__(W * 32, 16 / W) scl_list_kernel(SclParams P)
     {
         double* st = reinterpret_cast<double*>(smem_raw);
         for (int q = threadIdx.x; q < PHI_TAB_DOUBLES; q += W * 32) st[q] = P.phi_tab[q];
-        __syncthreads();
     }
     const int warp = threadIdx.x >> 5;
-    unsigned char* wbase = smem_raw + LY::TAB_BYTES + (size_t)warp * LY::WARP_BYTES;
-    uint32_t* xroot = reinterpret_cast<uint32_t*>(wbase);               // aliases alpha (dead by then)
-
     Lane L;
     L.lane = threadIdx.x & 31;
-    L.p = L.lane & 7;
-    L.gbase = L.lane & ~7;
-    L.tab = (uint32_t)__cvta_generic_to_shared(smem_raw);
-    L.sa = reinterpret_cast<double*>(wbase) + L.gbase;
-    L.sb = reinterpret_cast<uint32_t*>(wbase + (size_t)LY::ABYTES);
+    L.wsm = smem_base() + (uint32_t)LY::TAB_BYTES + (uint32_t)warp * (uint32_t)LY::WARP_BYTES;
+    L.rphase = 0;
+    {   // the warp's staging ring: one mbarrier per stage, a single arrival (lane 0's expect_tx) per phase
+        if (L.lane == 0) {
+#pragma unroll
+            for (int st = 0; st < RING_STAGES; ++st) mbar_init(L.rbar() + 8u * st, 1u);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        fence_proxy_async();
+        __syncthreads();
+    }
     const int gwarp = blockIdx.x * W + warp;
-    double* gscr = P.scratch + (size_t)gwarp * P.scratch_stride;
-    L.ga = gscr + L.gbase;
-    L.g0 = gscr + LY::G_ROWS * 32 + (L.lane >> 3);
-    L.gb = reinterpret_cast<uint32_t*>(gscr + LY::G_ROWS * 32 + 1024 * 4);
+    L.gw = P.scratch + (size_t)gwarp * P.scratch_stride;
     const int K = c_K;
     const int nbytes = (K - 8) >> 3;
     const int ngroups = (P.nunits + 3) >> 2;
     const int nwarps = gridDim.x * W;
-    uint4* snap = reinterpret_cast<uint4*>(wbase + (size_t)LY::ABYTES + LY::BROWS_S * 128) + L.lane;
+    // per-lane (metric, bptr, ord|active) saved at bit 512 for the second decode of a +/- pair
+    uint4* const snap_base = reinterpret_cast<uint4*>(__cvta_shared_to_generic(L.wsm + LY::ABYTES + LY::BROWS_S * 128));
+#define snap (snap_base + L.lane)
+#define xroot (reinterpret_cast<uint32_t*>(__cvta_shared_to_generic(L.wsm)))   /* root partial sums: aliases alpha (dead by then) */
+#define gscr (L.gw)
 
     for (int grp = gwarp; grp < ngroups; grp += nwarps) {
         const int j = grp * 4 + (L.lane >> 3);
@@ -443,10 +782,10 @@ __global__ void __launch_bounds__(W * 32, 16 / W) scl_list_kernel(SclParams P)
             const float* src = P.llr + (size_t)row * 1024;
             double* dst = gscr + LY::G_ROWS * 32 + (L.lane >> 3);
 #pragma unroll 4
-            for (int k = L.p; k < 1024; k += 8) dst[k * 4] = (double)__ldg(src + k);
+            for (int k = L.p(); k < 1024; k += 8) dst[k * 4] = (double)__ldg(src + k);
         }
         L.m = 0.0; L.ptr = 0; L.bptr = 0; L.bs = 0; L.ord = 0;
-        L.active = (L.p == 0);
+        L.active = (L.p() == 0);
         L.neg = P.neg_mode && (w & 1);
         __syncwarp();
 
@@ -463,7 +802,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) scl_list_kernel(SclParams P)
                                    ((uint32_t)L.ord << 1) | (L.active ? 1u : 0u));
             }
             if (q == 128) {
-                if (L.neg) negate_level0(gscr + LY::G_ROWS * 32 + (L.lane >> 3) + L.p * 4);
+                if (L.neg) negate_level0(gscr + LY::G_ROWS * 32 + (L.lane >> 3) + L.p() * 4);
                 __syncwarp();
             }
             // rate-0 nodes: the first quad adds the whole node's penalty, every quad feeds zeros upward
@@ -471,14 +810,14 @@ __global__ void __launch_bounds__(W * 32, 16 / W) scl_list_kernel(SclParams P)
             const int last = (r0 == 0) ? 8 : (9 - r0);
             if (r0 != 255) {
                 if (q == 0) spine<S>(L);
-                else llr_update8<S>(L, i, last);
+                else llr_update8<S>(L, gscr, i, last);
                 __syncwarp();
             }
             Carry cy; cy.qb = 0;
             if (r0 != 0) {
                 if (r0 != 255) {
-                    const LvlRef nd = lvl_ref<S>(L, last, L.p);
-                    const double pen = r0_sum(nd.base, nd.stride, 4 << (r0 - 1), L.tab);
+                    const LvlRef nd = lvl_ref<S>(L, last, L.p());
+                    const double pen = r0_sum(nd.base, nd.stride, 4 << (r0 - 1), L.tab());
                     if (L.active) L.m += pen;
                 }
             } else {
@@ -494,15 +833,15 @@ __global__ void __launch_bounds__(W * 32, 16 / W) scl_list_kernel(SclParams P)
                     const double a0 = l8[0], a1 = l8[32], a2 = l8[64], a3 = l8[96];
                     double x0, x1;
                     if (t == 0) {
-                        x0 = fcomb(a0, a2, L.tab); x1 = fcomb(a1, a3, L.tab);
+                        fcomb2(a0, a2, a1, a3, L.tab(), x0, x1);
                     } else {
                         const uint32_t u0 = cy.qb & 1u, u1 = (cy.qb >> 1) & 1u;
                         x0 = (u0 ^ u1) ? (a2 - a0) : (a2 + a0);
                         x1 = u1 ? (a3 - a1) : (a3 + a1);
                     }
                     // even leaf: f of the pair; its two phi terms are the odd leaf's penalty terms
-                    leaf = fcomb_parts(x0, x1, L.tab, fm, fp);
-                    ph = phi_fast(leaf, L.tab);
+                    leaf = fcomb_parts(x0, x1, L.tab(), fm, fp);
+                    ph = phi1(leaf, L.tab());
                     cy.c0 = x0; cy.c1 = x1; cy.c2 = fm; cy.c3 = fp;
                 } else {
                     // odd leaf: g of the pair
@@ -529,9 +868,9 @@ __global__ void __launch_bounds__(W * 32, 16 / W) scl_list_kernel(SclParams P)
             const int oj = __shfl_sync(full, L.ord, q, 8);
             if (aj && (mj < L.m || (mj == L.m && oj < L.ord))) ++rank;
         }
-        const uint32_t am = (__ballot_sync(full, L.active) >> L.gbase) & 0xffu;
+        const uint32_t am = (__ballot_sync(full, L.active) >> L.gbase()) & 0xffu;
         const int np = __popc(am);
-        if (!L.active) rank = np + __popc((~am & 0xffu) & ((1u << L.p) - 1u));
+        if (!L.active) rank = np + __popc((~am & 0xffu) & ((1u << L.p()) - 1u));
 
         // u-hat = transform(x-hat), in registers
         uint32_t x[32];
@@ -566,7 +905,7 @@ __global__ void __launch_bounds__(W * 32, 16 / W) scl_list_kernel(SclParams P)
             P.path_crc[orow] = (L.active && crcreg == crcbits) ? 1 : 0;
             P.path_metric[orow] = L.active ? L.m : CUDART_INF;
         }
-        if (valid && L.p == 0) P.npaths[w] = np;
+        if (valid && L.p() == 0) P.npaths[w] = np;
         __syncwarp();
         if (!P.pair || pass == 1) break;
         // second pass: the sign-flipped variant of the same row, restarted at bit 512
@@ -581,6 +920,10 @@ __global__ void __launch_bounds__(W * 32, 16 / W) scl_list_kernel(SclParams P)
         }
     }
 }
+
+#undef snap
+#undef xroot
+#undef gscr
 
 // ---------------------------------------------------------------------------------------------
 // hard-decision fast path (rtwm/fastpolar.py:261-276): one warp per codeword
@@ -724,10 +1067,7 @@ __global__ void __launch_bounds__(128) polar_encode_kernel(const uint8_t* __rest
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-constexpr int SCL_S = 6;   // first LLR-tree level kept in shared memory
-constexpr int SCL_W = 16;  // warps per CTA = one CTA per SM: one copy of the phi tables per SM (4 warps x 4 CTAs measured 4 % slower)
-using SclLY = SclLayout<SCL_S>;
-
+constexpr int SCL_W = ES_SCL_W;  // warps per CTA = one CTA per SM: one copy of the phi tables per SM (4 warps x 4 CTAs measured 4 % slower)
 static size_t scl_smem_bytes() { return (size_t)SclLY::TAB_BYTES + (size_t)SCL_W * SclLY::WARP_BYTES; }
 static size_t scl_scratch_doubles_per_warp() { return SclLY::G_DOUBLES; }
 
@@ -807,6 +1147,15 @@ int es_polar_set_code(const uint8_t* frozen_host, int K)
     g_K = K;
     return ES_OK;
 }
+
+#if ES_SCL_DBG_VERIFY
+int es_scl_debug_read(unsigned long long* out, int n)
+{
+    ES_CUDA_OK(cudaDeviceSynchronize());
+    ES_CUDA_OK(cudaMemcpyFromSymbol(out, es::g_dbg, sizeof(unsigned long long) * (size_t)(n < 256 ? n : 256)));
+    return ES_OK;
+}
+#endif
 
 int es_scl_grid_ctas(void)
 {

@@ -15,6 +15,10 @@ KEYS = ['gpu__time_duration.sum', 'sm__cycles_elapsed.avg.per_second', 'smsp__in
         'lts__t_sector_hit_rate.pct', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum',
         'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'smsp__thread_inst_executed_per_inst_executed.ratio']
 
+STALLS = ['stall_barrier', 'stall_branch_resolving', 'stall_dispatch', 'stall_drain', 'stall_lg', 'stall_long_sb',
+          'stall_math', 'stall_membar', 'stall_mio', 'stall_misc', 'stall_no_inst', 'stall_not_selected',
+          'stall_selected', 'stall_short_sb', 'stall_sleep', 'stall_tex', 'stall_wait']
+
 def main():
     rep = sys.argv[1]
     rows = page(rep, "raw")
@@ -33,18 +37,21 @@ def main():
     for k, r in enumerate(data):
         if cur and abs(ex[k] - cur['ex']) <= 0.02 * max(cur['ex'], 1):
             cur['n'] += 1; cur['s'] += sm[k]; cur['end'] = k
-            for key in ('stall_long_sb', 'stall_wait', 'stall_short_sb', 'stall_math'):
+            for key in STALLS:
                 cur[key] += int(r[ci[key]])
         else:
-            cur = dict(start=k, end=k, ex=ex[k], n=1, s=sm[k], stall_long_sb=int(r[ci['stall_long_sb']]),
-                       stall_wait=int(r[ci['stall_wait']]), stall_short_sb=int(r[ci['stall_short_sb']]),
-                       stall_math=int(r[ci['stall_math']]))
+            cur = dict(start=k, end=k, ex=ex[k], n=1, s=sm[k])
+            for key in STALLS:
+                cur[key] = int(r[ci[key]])
             runs.append(cur)
     for r in runs:
         if r['ex'] * r['n'] > 0.005 * tot or r['s'] > 0.01 * totS:
+            top = sorted(((r[k], k[6:]) for k in STALLS if r[k] > 0.04 * max(r['s'], 1)), reverse=True)
             print(f"{r['start']:5d}-{r['end']:5d} n={r['n']:4d} exec={r['ex']:>11d} inst%={r['ex']*r['n']/tot*100:5.1f} "
-                  f"samp%={r['s']/totS*100:5.1f} long_sb={r['stall_long_sb']} wait={r['stall_wait']} "
-                  f"short_sb={r['stall_short_sb']} math={r['stall_math']} | {data[r['start']][ci['Source']].strip()[:40]}")
+                  f"samp%={r['s']/totS*100:5.1f} " + " ".join(f"{n}={v}" for v, n in top) +
+                  f" | {data[r['start']][ci['Source']].strip()[:40]}")
+    tots = {k: sum(int(r[ci[k]]) for r in data) for k in STALLS}
+    print("stall samples total: " + " ".join(f"{k[6:]}={v} ({v/totS*100:.1f}%)" for k, v in sorted(tots.items(), key=lambda kv: -kv[1]) if v))
 
 if __name__ == "__main__":
     main()
