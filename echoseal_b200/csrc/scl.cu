@@ -175,11 +175,8 @@ struct SclParams {
 };
 
 constexpr int SCL_S = 6;   // first LLR-tree level kept in shared memory
-#ifndef ES_SCL_STAGED
-#define ES_SCL_STAGED 1      // fused g+f passes over the DRAM-resident levels (0: one g pass, then one f pass per level)
-#endif
 #ifndef ES_SCL_TMA
-#define ES_SCL_TMA 0         // 1: the passes read their source rows from the TMA-fed ring; 0: straight from global memory (faster so far)
+#define ES_SCL_TMA 1         // 1: the passes read their source rows from the TMA-fed ring; 0: straight from global memory
 #endif
 #ifndef ES_SCL_TMA_GF
 #define ES_SCL_TMA_GF ES_SCL_TMA
@@ -250,7 +247,20 @@ struct Lane {
     __device__ __forceinline__ uint32_t rbar() const { return wsm + SclLY::BAR_OFF; }    // its mbarrier at + 8 * st
 };
 
-struct LvlRef { double* base; int stride; };
+// ---------------------------------------------------------------------------------------------
+// addressing.  Levels >= S live in shared memory in natural element order.  Levels 0..S-1 live in global memory
+// QUARTER-INTERLEAVED: element k = j*q + r of a node of n = 4q elements sits at position 4r + j, so the four
+// elements (r, r+q, r+2q, r+3q) that every consumer of the node needs together are adjacent, and a pass reads
+// its source node front to back in contiguous 8-row chunks: one bulk copy per stage.
+// ---------------------------------------------------------------------------------------------
+// first global row of level lv (1..S-1)
+__device__ __forceinline__ int lvl_row0(int lv) { return 1024 - (1 << (11 - lv)); }
+// position of element k inside the node of level lv (0..S-1)
+__device__ __forceinline__ int ipos(int lv, int k)
+{
+    const int lq = 8 - lv;                                   // log2 of the quarter size
+    return ((k & ((1 << lq) - 1)) << 2) | (k >> lq);
+}
 
 // row 0 of the left-child partial-sum words of level l (1..5): 2^(5-l) rows of 32 words
 __device__ __forceinline__ uint32_t* beta_rows(const Lane& L, int l)
@@ -259,89 +269,295 @@ __device__ __forceinline__ uint32_t* beta_rows(const Lane& L, int l)
     return (l >= 3) ? L.sb() + ((1 << (5 - l)) - 1) * 32 : L.gb() + ((l == 2) ? 0 : 8) * 32;
 }
 
-// element k of level lv in `slot` lives at ref.base[k * ref.stride]
-template <int S> __device__ __forceinline__ LvlRef lvl_ref(const Lane& L, int lv, int slot)
+// element 0 of the shared-memory level lv (>= S) in `slot`; element k is k * 32 doubles further
+template <int S> __device__ __forceinline__ double* slvl(const Lane& L, int lv, int slot)
 {
-    LvlRef r;
-    if (lv == 0) { r.base = L.g0(); r.stride = 4; }
-    else if (lv >= S) { r.base = L.sa() + (((1 << (11 - S)) - (1 << (11 - lv))) * 32) + slot; r.stride = 32; }
-    else { r.base = L.ga() + ((1024 - (1 << (11 - lv))) * 32) + slot; r.stride = 32; }
-    return r;
+    return L.sa() + (((1 << (11 - S)) - (1 << (11 - lv))) * 32) + slot;
+}
+// element k of any level in `slot` (level 0: the warp's copy of the channel LLRs, [position][codeword])
+template <int S> __device__ __forceinline__ double* elem_ptr(const Lane& L, int lv, int slot, int k)
+{
+    if (lv == 0) return L.g0() + ipos(0, k) * 4;
+    if (lv >= S) return slvl<S>(L, lv, slot) + k * 32;
+    return L.ga() + (lvl_row0(lv) + ipos(lv, k)) * 32 + slot;
 }
 
-// f-combine of a whole node through generic pointers (the shared-memory levels and the bit-0 spine; the DRAM
-// levels go through pass_gf / pass_f): dst[k*ds] = f(a[k*ss], b[k*ss]), k < count, count even (callers
-// guarantee it).  Two elements per trip = four independent phi chains.
-__device__ __noinline__ void f_loop(const double* a, const double* b, int ss, double* dst, int ds, int count,
-                                    uint32_t tab)
+// f-combine of a whole shared-memory node: dst[k*32] = f(a[k*32], b[k*32]), k < count, count even.
+// Two elements per trip = four independent phi chains.
+__device__ __noinline__ void f_loop(const double* a, const double* b, double* dst, int count, uint32_t tab)
 {
-    if (count < 2) return;
 #pragma unroll 1
     for (int k = 0; k + 2 <= count; k += 2) {
-        const double a0 = a[k * ss], b0 = b[k * ss], a1 = a[(k + 1) * ss], b1 = b[(k + 1) * ss];
+        const double a0 = a[k * 32], b0 = b[k * 32], a1 = a[(k + 1) * 32], b1 = b[(k + 1) * 32];
         double r0, r1;
         fcomb2(a0, b0, a1, b1, tab, r0, r1);
-        dst[k * ds] = r0;
-        dst[(k + 1) * ds] = r1;
+        dst[k * 32] = r0;
+        dst[(k + 1) * 32] = r1;
     }
 }
 
 template <int S>
-__device__ __forceinline__ void f_level(Lane& L, int lv)   // 2 <= lv <= 10, parent in own slot
+__device__ __forceinline__ void f_level(Lane& L, int lv)   // S < lv <= 8: parent (level lv-1 >= S) in own slot
 {
     const int s = 1 << (10 - lv);
-    const LvlRef src = lvl_ref<S>(L, lv - 1, L.p());
-    const LvlRef dst = lvl_ref<S>(L, lv, L.p());
-    f_loop(src.base, src.base + s * src.stride, src.stride, dst.base, dst.stride, s, L.tab());
+    const double* src = slvl<S>(L, lv - 1, L.p());
+    f_loop(src, src + s * 32, slvl<S>(L, lv, L.p()), s, L.tab());
     L.ptr = (L.ptr & ~(7u << (3 * (lv - 1)))) | ((uint32_t)L.p() << (3 * (lv - 1)));
 }
 
-// g over one level l0 (1..10): dst[k] = par[k+s] +- par[k], sign from the left-child partial sums
+// g over one shared-memory level l0 (S..8): dst[k] = par[k+s] +- par[k], sign from the left-child partial sums in the
+// bs register; the parent (slot ps of level l0-1) is the DRAM-resident level S-1 when l0 == S.  All loads first.
 template <int S>
 __device__ __forceinline__ void g_level(Lane& L, int l0)
 {
-    const int s = 1 << (10 - l0);
-    const int ps = (l0 >= 2) ? ((L.ptr >> (3 * (l0 - 2))) & 7) : 0;
-    const LvlRef src = lvl_ref<S>(L, l0 - 1, ps);
-    const LvlRef dst = lvl_ref<S>(L, l0, L.p());
-    const double* pa = src.base;
-    const double* pb = src.base + s * src.stride;
-    if (s <= 16) {   // levels 6..8: bits in the bs register; all loads first (s = 4, 8 or 16)
-        const uint32_t bits = L.bs >> s;
+    const int s = 1 << (10 - l0);                              // 16, 8 or 4
+    const int ps = (L.ptr >> (3 * (l0 - 2))) & 7;
+    double* dst = slvl<S>(L, l0, L.p());
+    const uint32_t bits = L.bs >> s;
 #pragma unroll 1
-        for (int k0 = 0; k0 < s; k0 += 4) {
-            double va[4], vb[4];
+    for (int k0 = 0; k0 < s; k0 += 4) {
+        double va[4], vb[4];
+        if (l0 == S) {
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk) { va[kk] = pa[(k0 + kk) * src.stride]; vb[kk] = pb[(k0 + kk) * src.stride]; }
-#pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-                dst.base[(k0 + kk) * dst.stride] = ((bits >> (k0 + kk)) & 1u) ? (vb[kk] - va[kk]) : (vb[kk] + va[kk]);
-        }
-    } else {         // levels 1..5: bits in pointer-indirected words; 16 elements (32 loads) in flight
-        const int bsl = (L.bptr >> (3 * (l0 - 1))) & 7;
-        const uint32_t* bw = beta_rows(L, l0) + L.gbase() + bsl;
-#pragma unroll 1
-        for (int k0 = 0; k0 < s; k0 += 16) {
-            const uint32_t word = bw[(k0 >> 5) * 32] >> (k0 & 31);
-            double va[16], vb[16];
-#pragma unroll
-            for (int kk = 0; kk < 16; ++kk) {
-                va[kk] = pa[(k0 + kk) * src.stride];
-                vb[kk] = pb[(k0 + kk) * src.stride];
+            for (int kk = 0; kk < 4; ++kk) {
+                va[kk] = *elem_ptr<S>(L, S - 1, ps, k0 + kk);
+                vb[kk] = *elem_ptr<S>(L, S - 1, ps, k0 + kk + s);
             }
+        } else {
+            const double* pa = slvl<S>(L, l0 - 1, ps);
 #pragma unroll
-            for (int kk = 0; kk < 16; ++kk)
-                dst.base[(k0 + kk) * dst.stride] = ((word >> kk) & 1u) ? (vb[kk] - va[kk]) : (vb[kk] + va[kk]);
+            for (int kk = 0; kk < 4; ++kk) { va[kk] = pa[(k0 + kk) * 32]; vb[kk] = pa[(k0 + kk + s) * 32]; }
         }
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) dst[(k0 + kk) * 32] = gcomb(va[kk], vb[kk], (bits >> (k0 + kk)) & 1u);
     }
     L.ptr = (L.ptr & ~(7u << (3 * (l0 - 1)))) | ((uint32_t)L.p() << (3 * (l0 - 1)));
 }
 
-// level-0 copy of one codeword, this lane's share (k = p, p+8, ...): x -> -x.  Out of line: runs once per decode.
+// level-0 copy of one codeword, this lane's share (positions p, p+8, ...): x -> -x.  Out of line: runs once per decode.
 __device__ __noinline__ void negate_level0(double* l0)
 {
 #pragma unroll 4
     for (int k = 0; k < 128; ++k) l0[k * 32] = -l0[k * 32];
+}
+
+// ---------------------------------------------------------------------------------------------
+// passes over the DRAM-resident levels (0..S-1).  Lane 0 streams the source node into the warp's ring with
+// cp.async.bulk (TMA), one 8-row chunk per stage and two stages ahead, completion on one mbarrier per stage;
+// every lane reads its own (codeword, slot) column of the landed rows.  Results go straight to their level
+// (each store instruction writes one full 256-byte row).
+// ---------------------------------------------------------------------------------------------
+#ifndef ES_SCL_DBG_VERIFY
+#define ES_SCL_DBG_VERIFY 0
+#endif
+
+// lane 0: queue one stage
+__device__ __forceinline__ void ring_issue(const Lane& L, int st, const void* src, uint32_t bytes)
+{
+    const uint32_t bar = L.rbar() + 8u * st;
+    mbar_expect_tx(bar, bytes);
+    bulk_g2s(L.ring() + (uint32_t)st * RING_STAGE_BYTES, src, bytes, bar);
+}
+
+// All lanes hold the eight values of the current stage in registers: the stage may be refilled.  A plain
+// __syncwarp() is not enough — the loads above are only ISSUED at that point, and a bulk copy queued right
+// behind them was measured to overtake them (about one corrupted group in 3000).  A warp vote on the loaded
+// words cannot issue before every lane's loads have returned; the branch it feeds is practically never taken
+// and harmless when it is.
+__device__ __forceinline__ void ring_release(int w)      // w: xor of the high words of the values just loaded
+{
+    if (__any_sync(0xffffffffu, w == 0x7ff80123)) __nanosleep(2000);
+}
+__device__ __forceinline__ int hi4(double a, double b, double c, double d)
+{
+    return __double2hiint(a) ^ __double2hiint(b) ^ __double2hiint(c) ^ __double2hiint(d);
+}
+
+// the eight rows of chunk c of a source node (row pitch rs bytes, this lane's column at byte offset col)
+struct PassSrc {
+    const unsigned char* base;    // row 0 of the node, warp-uniform
+    uint32_t rs, col;
+    int nch;
+};
+
+template <bool TMA>
+__device__ __forceinline__ void pass_begin(Lane& L, const PassSrc& ps)
+{
+    if (TMA) {
+        fence_proxy_async();      // the node was written with ordinary stores (this warp, earlier passes)
+        __syncwarp();
+        if (L.lane == 0) {
+            ring_issue(L, 0, ps.base, 8u * ps.rs);
+            if (ps.nch > 1) ring_issue(L, 1, ps.base + 8u * ps.rs, 8u * ps.rs);
+        }
+        __syncwarp();
+    }
+}
+// wait for chunk c (stage st); returns the address this lane's column of row 0 is read from
+template <bool TMA>
+__device__ __forceinline__ size_t pass_wait(Lane& L, const PassSrc& ps, int c, int st)
+{
+    if (TMA) {
+        mbar_wait(L.rbar() + 8u * st, (L.rphase >> st) & 1u);
+        L.rphase ^= 1u << st;
+        return (size_t)(L.ring() + (uint32_t)st * RING_STAGE_BYTES + ps.col);
+    }
+    return reinterpret_cast<size_t>(ps.base + (size_t)c * 8u * ps.rs + ps.col);
+}
+// rows i0 .. i0+3 of the chunk
+template <bool TMA>
+__device__ __forceinline__ void pass_ld4(size_t at, const PassSrc& ps, int i0, double& a, double& b, double& c, double& d)
+{
+    if (TMA) {
+        const uint32_t sb = (uint32_t)at + (uint32_t)i0 * ps.rs;
+        a = lds_f64(sb); b = lds_f64(sb + ps.rs); c = lds_f64(sb + 2 * ps.rs); d = lds_f64(sb + 3 * ps.rs);
+    } else {
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(at) + (size_t)i0 * ps.rs;
+        a = *reinterpret_cast<const double*>(src); b = *reinterpret_cast<const double*>(src + ps.rs);
+        c = *reinterpret_cast<const double*>(src + 2 * ps.rs); d = *reinterpret_cast<const double*>(src + 3 * ps.rs);
+    }
+}
+// every lane holds the values of the stage in registers (w covers the loads not consumed yet): refill it
+template <bool TMA>
+__device__ __forceinline__ void pass_refill(Lane& L, const PassSrc& ps, int c, int& st, int w)
+{
+    if (TMA) {
+        ring_release(w);
+        if (L.lane == 0 && c + RING_STAGES < ps.nch)
+            ring_issue(L, st, ps.base + (size_t)(c + RING_STAGES) * 8u * ps.rs, 8u * ps.rs);
+        st ^= 1;
+    }
+}
+
+// g node of level l0 (1..S-1) from its parent (slot ps of level l0-1; level 0 = the channel LLRs), fused with the
+// f node of level l0+1 below it when do_f: chunk c holds the parent elements k, k+h, k+s, k+s+h for k = 2c, 2c+1
+// and gives g[k], g[k+h] (stored: the g node of level l0+1 needs them later) and f(g[k], g[k+h]) — the g node is
+// never read back for its f child.
+template <int S>
+__device__ __forceinline__ void pass_gf_body(Lane& L, int l0, bool do_f)
+{
+    const int s = 1 << (10 - l0), h = s >> 1;
+    PassSrc src;
+    src.nch = h >> 1;
+    if (l0 == 1) {
+        src.base = reinterpret_cast<const unsigned char*>(L.gw + SclLY::G_ROWS * 32);
+        src.rs = 32u;
+        src.col = (uint32_t)(L.lane >> 3) * 8u;
+    } else {
+        src.base = reinterpret_cast<const unsigned char*>(L.gw + (size_t)lvl_row0(l0 - 1) * 32);
+        src.rs = 256u;
+        src.col = (uint32_t)(L.gbase() + ((L.ptr >> (3 * (l0 - 2))) & 7)) * 8u;
+    }
+    double* gdst = L.ga() + lvl_row0(l0) * 32 + L.p();          // position 0 of the g node, own slot
+    double* fdst = (l0 + 1 >= S) ? slvl<S>(L, l0 + 1, L.p()) : L.ga() + lvl_row0(l0 + 1) * 32 + L.p();
+    const int lqf = (l0 + 1 >= S) ? -1 : 8 - (l0 + 1);          // f node: natural order in shared memory
+    const uint32_t* bw = beta_rows(L, l0) + L.gbase() + ((L.bptr >> (3 * (l0 - 1))) & 7);
+    pass_begin<ES_SCL_TMA_GF != 0>(L, src);
+    int st = 0;
+    const int half = src.nch >> 1;
+#pragma unroll 1
+    for (int c = 0; c < src.nch; ++c) {
+        double v[8];     // A(k) A(k+h) B(k) B(k+h) A(k+1) A(k+1+h) B(k+1) B(k+1+h)
+        {
+            const size_t at = pass_wait<ES_SCL_TMA_GF != 0>(L, src, c, st);
+            pass_ld4<ES_SCL_TMA_GF != 0>(at, src, 0, v[0], v[1], v[2], v[3]);
+            pass_ld4<ES_SCL_TMA_GF != 0>(at, src, 4, v[4], v[5], v[6], v[7]);
+            pass_refill<ES_SCL_TMA_GF != 0>(L, src, c, st, hi4(v[0], v[1], v[2], v[3]) ^ hi4(v[4], v[5], v[6], v[7]));
+        }
+        const int k = 2 * c;
+        const uint32_t w0 = bw[(k >> 5) * 32] >> (k & 31);
+        const uint32_t w1 = bw[((k + h) >> 5) * 32] >> ((k + h) & 31);
+        const double g0 = gcomb(v[0], v[2], w0 & 1u), gh0 = gcomb(v[1], v[3], w1 & 1u);
+        const double g1 = gcomb(v[4], v[6], (w0 >> 1) & 1u), gh1 = gcomb(v[5], v[7], (w1 >> 1) & 1u);
+        double* gd = gdst + ((c < half) ? 8 * c : 8 * (c - half) + 1) * 32;      // position of g[k]; g[k+1] +4, g[k+h] +2
+        gd[0] = g0; gd[2 * 32] = gh0; gd[4 * 32] = g1; gd[6 * 32] = gh1;
+        if (do_f) {
+            double r0, r1;
+            fcomb2(g0, gh0, g1, gh1, L.tab(), r0, r1);
+            double* fd = fdst + ((lqf < 0) ? k : (((k & ((1 << lqf) - 1)) << 2) | (k >> lqf))) * 32;
+            fd[0] = r0; fd[((lqf < 0) ? 1 : 4) * 32] = r1;
+        }
+    }
+}
+
+// Out of line on purpose (one copy, and its working set does not add to the register pressure of the
+// decode loop): only the words the pass needs travel; the caller re-points the level's slot.
+template <int S>
+__device__ __noinline__ uint32_t pass_gf_fn(uint32_t wsm, double* gw, int lane, uint32_t rphase, uint32_t ptr, uint32_t bptr,
+                                            int l0, bool do_f)
+{
+    Lane T;
+    T.wsm = wsm; T.gw = gw; T.lane = lane; T.rphase = rphase; T.ptr = ptr; T.bptr = bptr;
+    pass_gf_body<S>(T, l0, do_f);
+    return T.rphase;
+}
+template <int S>
+__device__ __forceinline__ void pass_gf(Lane& L, int l0, bool do_f)
+{
+    L.rphase = pass_gf_fn<S>(L.wsm, L.gw, L.lane, L.rphase, L.ptr, L.bptr, l0, do_f);
+    uint32_t ptr = (L.ptr & ~(7u << (3 * (l0 - 1)))) | ((uint32_t)L.p() << (3 * (l0 - 1)));
+    if (do_f) ptr = (ptr & ~(7u << (3 * l0))) | ((uint32_t)L.p() << (3 * l0));
+    L.ptr = ptr;
+}
+
+// f node of level lv (1..S) from the node of level lv-1: chunk c holds the source elements r, r+q, r+2q, r+3q for
+// r = 2c, 2c+1 (q = quarter of the source node) and gives f[r], f[r+q], f[r+1], f[r+1+q].
+//   coop = false: every lane walks the whole node of its own slot (written by the pass above it), staged through the ring;
+//   coop = true (bit 0, one path): the 8 lanes of a codeword share the chunks of slot 0, read straight from memory.
+template <int S>
+__device__ __forceinline__ void pass_f_body(Lane& L, int lv, bool coop)
+{
+    const int s = 1 << (10 - lv), q = s >> 1;
+    const int slot = coop ? 0 : L.p();
+    PassSrc src;
+    src.nch = s >> 2;
+    if (lv == 1) {
+        src.base = reinterpret_cast<const unsigned char*>(L.gw + SclLY::G_ROWS * 32);
+        src.rs = 32u;
+        src.col = (uint32_t)(L.lane >> 3) * 8u;
+    } else {
+        src.base = reinterpret_cast<const unsigned char*>(L.gw + (size_t)lvl_row0(lv - 1) * 32);
+        src.rs = 256u;
+        src.col = (uint32_t)(L.gbase() + slot) * 8u;
+    }
+    const bool nat = lv >= S;
+    double* fdst = nat ? slvl<S>(L, lv, slot) : L.ga() + lvl_row0(lv) * 32 + slot;
+    const bool tma = (ES_SCL_TMA_F != 0) && !coop;
+    if (tma) pass_begin<true>(L, src);
+    int st = 0;
+    const int half = src.nch >> 1;
+    const int cstep = coop ? 8 : 1;
+#pragma unroll 1
+    for (int c = coop ? L.p() : 0; c < src.nch; c += cstep) {
+        // rows of the chunk: e(r) e(r+q) e(r+2q) e(r+3q) | e(r+1) e(r+1+q) e(r+1+2q) e(r+1+3q); one call per half,
+        // the second half loaded after the first call so that nothing of it is live across that call
+        double* fd = nat ? fdst + 2 * c * 32 : fdst + ((c < half) ? 8 * c : 8 * (c - half) + 1) * 32;   // f[r]
+        const int dq = nat ? q * 32 : 2 * 32, d1 = nat ? 32 : 4 * 32;                                        // f[r+q], f[r+1]
+        double v0, v1, v2, v3, r0, r1;
+        const size_t at = tma ? pass_wait<true>(L, src, c, st) : pass_wait<false>(L, src, c, st);
+        if (tma) pass_ld4<true>(at, src, 0, v0, v1, v2, v3); else pass_ld4<false>(at, src, 0, v0, v1, v2, v3);
+        fcomb2(v0, v2, v1, v3, L.tab(), r0, r1);               // f[r], f[r+q]
+        fd[0] = r0; fd[dq] = r1;
+        if (tma) pass_ld4<true>(at, src, 4, v0, v1, v2, v3); else pass_ld4<false>(at, src, 4, v0, v1, v2, v3);
+        if (tma) pass_refill<true>(L, src, c, st, hi4(v0, v1, v2, v3));
+        fcomb2(v0, v2, v1, v3, L.tab(), r0, r1);               // f[r+1], f[r+1+q]
+        fd[d1] = r0; fd[d1 + dq] = r1;
+    }
+}
+
+template <int S>
+__device__ __noinline__ uint32_t pass_f_fn(uint32_t wsm, double* gw, int lane, uint32_t rphase, int lv, bool coop)
+{
+    Lane T;
+    T.wsm = wsm; T.gw = gw; T.lane = lane; T.rphase = rphase;
+    pass_f_body<S>(T, lv, coop);
+    return T.rphase;
+}
+template <int S>
+__device__ __forceinline__ void pass_f(Lane& L, int lv, bool coop)
+{
+    L.rphase = pass_f_fn<S>(L.wsm, L.gw, L.lane, L.rphase, lv, coop);
+    L.ptr = (L.ptr & ~(7u << (3 * (lv - 1)))) | ((uint32_t)(coop ? 0 : L.p()) << (3 * (lv - 1)));
 }
 
 // bit 0: only one path exists; the 8 lanes of the codeword share the work, everything goes to slot 0
@@ -349,234 +565,37 @@ template <int S>
 __device__ __forceinline__ void spine(Lane& L)
 {
 #pragma unroll 1
-    for (int lv = 1; lv <= 8; ++lv) {
+    for (int lv = 1; lv <= S; ++lv) {
+        pass_f<S>(L, lv, true);
+        __syncwarp();
+    }
+#pragma unroll 1
+    for (int lv = S + 1; lv <= 8; ++lv) {     // 8 and 4 elements: one pair per lane
         const int s = 1 << (10 - lv);
-        const LvlRef src = lvl_ref<S>(L, lv - 1, 0);
-        const LvlRef dst = lvl_ref<S>(L, lv, 0);
-        const int P = (s >= 16) ? 8 : (s >> 1);              // participating lanes; each gets an even count
-        const int count = (L.p() < P) ? (s / P) : 0;
-        const double* pa = src.base + L.p() * src.stride;
-        f_loop(pa, pa + s * src.stride, P * src.stride, dst.base + L.p() * dst.stride, P * dst.stride, count, L.tab());
+        const double* src = slvl<S>(L, lv - 1, 0) + 2 * L.p() * 32;
+        f_loop(src, src + s * 32, slvl<S>(L, lv, 0) + 2 * L.p() * 32, (2 * L.p() < s) ? 2 : 0, L.tab());
         __syncwarp();
     }
     L.ptr = 0;
 }
 
-// ---------------------------------------------------------------------------------------------
-// passes over the DRAM-resident levels (1..S-1).  A level is [element][codeword(4)][slot(8)], one 256-byte row
-// per element, so the rows a pass needs are contiguous: lane 0 streams them into the warp's ring with
-// cp.async.bulk (TMA) two stages ahead, completion on one mbarrier per stage, and every lane reads its own
-// (codeword, slot) column of the landed rows.  Results go straight to their level (coalesced 256-byte rows).
-// ---------------------------------------------------------------------------------------------
-#ifndef ES_SCL_DBG_VERIFY
-#define ES_SCL_DBG_VERIFY 0
-#endif
-#if ES_SCL_DBG_VERIFY
-__device__ unsigned long long g_dbg[256];
-__device__ __forceinline__ void dbg_check(double staged, const double* direct, int kind, int lvl, int c, int which, int lane)
-{
-    const double v = __ldcg(direct);
-    if (__double_as_longlong(v) != __double_as_longlong(staged)) {
-        const unsigned long long n = atomicAdd(&g_dbg[0], 1ull);
-        if (n < 60) {
-            g_dbg[4 + 4 * n] = ((unsigned long long)kind << 56) | ((unsigned long long)lvl << 48) | ((unsigned long long)c << 32) |
-                               ((unsigned long long)which << 8) | (unsigned long long)lane | ((unsigned long long)blockIdx.x << 16);
-            g_dbg[5 + 4 * n] = (unsigned long long)__double_as_longlong(staged);
-            g_dbg[6 + 4 * n] = (unsigned long long)__double_as_longlong(v);
-            g_dbg[7 + 4 * n] = clock64();
-        }
-    }
-}
-#endif
-// first global row of level lv (1..5)
-__device__ __forceinline__ int lvl_row0(int lv) { return 1024 - (1 << (11 - lv)); }
-
-// lane 0: queue one stage of `nseg` segments of `segbytes` each; segment j starts at source row seg_row[j]
-__device__ __forceinline__ void ring_issue(const Lane& L, const double* gw, int st, int nseg, uint32_t segbytes,
-                                           int r0, int r1, int r2, int r3)
-{
-    const uint32_t bar = L.rbar() + 8u * st;
-    const uint32_t dst = L.ring() + (uint32_t)st * RING_STAGE_BYTES;
-    mbar_expect_tx(bar, segbytes * nseg);
-    bulk_g2s(dst, gw + (size_t)r0 * 32, segbytes, bar);
-    bulk_g2s(dst + segbytes, gw + (size_t)r1 * 32, segbytes, bar);
-    if (nseg == 4) {
-        bulk_g2s(dst + 2 * segbytes, gw + (size_t)r2 * 32, segbytes, bar);
-        bulk_g2s(dst + 3 * segbytes, gw + (size_t)r3 * 32, segbytes, bar);
-    }
-}
-
-// All lanes hold the eight values of the current stage in registers: the stage may be refilled.  A plain
-// __syncwarp() is not enough — the loads above are only ISSUED at that point, and a bulk copy queued right
-// behind them was measured to overtake them (about one corrupted group in 3000).  A warp vote on the loaded
-// words cannot issue before every lane's loads have returned; the branch it feeds is never taken for the
-// finite numbers of an LLR tree and would be harmless if it were.
-__device__ __forceinline__ void ring_release(double v0, double v1, double v2, double v3, double v4, double v5, double v6,
-                                             double v7)
-{
-    const int w = __double2hiint(v0) ^ __double2hiint(v1) ^ __double2hiint(v2) ^ __double2hiint(v3) ^
-                  __double2hiint(v4) ^ __double2hiint(v5) ^ __double2hiint(v6) ^ __double2hiint(v7);
-    if (__any_sync(0xffffffffu, w == 0x7ff80123)) __nanosleep(2000);
-}
-
-// g node of level l0 (2..5) from its parent (slot ps of level l0-1), fused with the f node of level l0+1 below
-// it when do_f: per trip the parent rows k, k+h, k+s, k+s+h (two elements each) give g[k], g[k+h] (stored: the
-// g node of level l0+1 needs them later) and f(g[k], g[k+h]) — the g node is never read back for its f child.
-template <int S>
-__device__ __forceinline__ void pass_gf(Lane& L, const double* gw, int l0, bool do_f)
-{
-    const int s = 1 << (10 - l0), h = s >> 1;
-    const int ps = (L.ptr >> (3 * (l0 - 2))) & 7;
-    const int srow = lvl_row0(l0 - 1);
-    double* gdst = L.ga() + lvl_row0(l0) * 32 + L.p();
-    double* fdst = lvl_ref<S>(L, l0 + 1, L.p()).base;           // global (l0+1 < S) or shared; row stride 32 doubles
-    const uint32_t* bw = beta_rows(L, l0) + L.gbase() + ((L.bptr >> (3 * (l0 - 1))) & 7);
-    const int nch = h >> 1;
-#if ES_SCL_TMA_GF
-    const uint32_t col = (uint32_t)(L.gbase() + ps) * 8u;
-    fence_proxy_async();
-    __syncwarp();
-    if (L.lane == 0) {
-        ring_issue(L, gw, 0, 4, 512u, srow, srow + h, srow + s, srow + s + h);
-        if (nch > 1) ring_issue(L, gw, 1, 4, 512u, srow + 2, srow + h + 2, srow + s + 2, srow + s + h + 2);
-    }
-    __syncwarp();
-    int st = 0;
-#else
-    const double* src = gw + (size_t)srow * 32 + L.gbase() + ps;
-#endif
-#pragma unroll 1
-    for (int c = 0; c < nch; ++c) {
-        const int k = 2 * c;
-        double a0, a1, ah0, ah1, b0, b1, bh0, bh1;
-#if ES_SCL_TMA_GF
-        mbar_wait(L.rbar() + 8u * st, (L.rphase >> st) & 1u);
-        L.rphase ^= 1u << st;
-        const uint32_t sb = L.ring() + (uint32_t)st * RING_STAGE_BYTES + col;
-        a0 = lds_f64(sb); a1 = lds_f64(sb + 256);
-        ah0 = lds_f64(sb + 512); ah1 = lds_f64(sb + 768);
-        b0 = lds_f64(sb + 1024); b1 = lds_f64(sb + 1280);
-        bh0 = lds_f64(sb + 1536); bh1 = lds_f64(sb + 1792);
-#if ES_SCL_DBG_VERIFY
-        {
-            const double* dsrc = gw + (size_t)srow * 32 + L.gbase() + ps;
-            const int k = 2 * c;
-            dbg_check(a0, dsrc + k * 32, 1, l0, c, 0, L.lane); dbg_check(a1, dsrc + (k + 1) * 32, 1, l0, c, 1, L.lane);
-            dbg_check(ah0, dsrc + (k + h) * 32, 1, l0, c, 2, L.lane); dbg_check(ah1, dsrc + (k + h + 1) * 32, 1, l0, c, 3, L.lane);
-            dbg_check(b0, dsrc + (s + k) * 32, 1, l0, c, 4, L.lane); dbg_check(b1, dsrc + (s + k + 1) * 32, 1, l0, c, 5, L.lane);
-            dbg_check(bh0, dsrc + (s + k + h) * 32, 1, l0, c, 6, L.lane); dbg_check(bh1, dsrc + (s + k + h + 1) * 32, 1, l0, c, 7, L.lane);
-        }
-#endif
-        ring_release(a0, a1, ah0, ah1, b0, b1, bh0, bh1);
-        if (L.lane == 0 && c + RING_STAGES < nch) {
-            const int r = srow + 2 * (c + RING_STAGES);
-            ring_issue(L, gw, st, 4, 512u, r, r + h, r + s, r + s + h);
-        }
-        st ^= 1;
-#else
-        a0 = src[k * 32]; a1 = src[(k + 1) * 32];
-        ah0 = src[(k + h) * 32]; ah1 = src[(k + h + 1) * 32];
-        b0 = src[(s + k) * 32]; b1 = src[(s + k + 1) * 32];
-        bh0 = src[(s + k + h) * 32]; bh1 = src[(s + k + h + 1) * 32];
-#endif
-        const uint32_t w0 = bw[(k >> 5) * 32] >> (k & 31);
-        const uint32_t w1 = bw[((k + h) >> 5) * 32] >> ((k + h) & 31);
-        const double g0 = gcomb(a0, b0, w0 & 1u), g1 = gcomb(a1, b1, (w0 >> 1) & 1u);
-        const double gh0 = gcomb(ah0, bh0, w1 & 1u), gh1 = gcomb(ah1, bh1, (w1 >> 1) & 1u);
-        gdst[k * 32] = g0; gdst[(k + 1) * 32] = g1;
-        gdst[(k + h) * 32] = gh0; gdst[(k + h + 1) * 32] = gh1;
-        if (do_f) {
-            double r0, r1;
-            fcomb2(g0, gh0, g1, gh1, L.tab(), r0, r1);
-            fdst[k * 32] = r0; fdst[(k + 1) * 32] = r1;
-        }
-    }
-    uint32_t ptr = (L.ptr & ~(7u << (3 * (l0 - 1)))) | ((uint32_t)L.p() << (3 * (l0 - 1)));
-    if (do_f) ptr = (ptr & ~(7u << (3 * l0))) | ((uint32_t)L.p() << (3 * l0));
-    L.ptr = ptr;
-}
-
-// f node of level lv (2..S) from the node of level lv-1 in the lane's own slot (just written by the pass above it)
-template <int S>
-__device__ __forceinline__ void pass_f(Lane& L, const double* gw, int lv)
-{
-    const int s = 1 << (10 - lv);
-    const int srow = lvl_row0(lv - 1);
-    double* fdst = lvl_ref<S>(L, lv, L.p()).base;
-    const int nch = s >> 2;                                   // four elements per stage (s >= 16 for lv <= 6)
-#if ES_SCL_TMA_F
-    const uint32_t col = (uint32_t)(L.gbase() + L.p()) * 8u;
-    fence_proxy_async();
-    __syncwarp();
-    if (L.lane == 0) {
-        ring_issue(L, gw, 0, 2, 1024u, srow, srow + s, 0, 0);
-        if (nch > 1) ring_issue(L, gw, 1, 2, 1024u, srow + 4, srow + s + 4, 0, 0);
-    }
-    __syncwarp();
-    int st = 0;
-#else
-    const double* src = gw + (size_t)srow * 32 + L.gbase() + L.p();
-#endif
-#pragma unroll 1
-    for (int c = 0; c < nch; ++c) {
-        const int k = 4 * c;
-        double a0, a1, a2, a3, b0, b1, b2, b3;
-#if ES_SCL_TMA_F
-        mbar_wait(L.rbar() + 8u * st, (L.rphase >> st) & 1u);
-        L.rphase ^= 1u << st;
-        const uint32_t sb = L.ring() + (uint32_t)st * RING_STAGE_BYTES + col;
-        a0 = lds_f64(sb); a1 = lds_f64(sb + 256); a2 = lds_f64(sb + 512); a3 = lds_f64(sb + 768);
-        b0 = lds_f64(sb + 1024); b1 = lds_f64(sb + 1280); b2 = lds_f64(sb + 1536); b3 = lds_f64(sb + 1792);
-#if ES_SCL_DBG_VERIFY
-        {
-            const double* dsrc = gw + (size_t)srow * 32 + L.gbase() + L.p();
-            const int k = 4 * c;
-            dbg_check(a0, dsrc + k * 32, 2, lv, c, 0, L.lane); dbg_check(a1, dsrc + (k + 1) * 32, 2, lv, c, 1, L.lane);
-            dbg_check(a2, dsrc + (k + 2) * 32, 2, lv, c, 2, L.lane); dbg_check(a3, dsrc + (k + 3) * 32, 2, lv, c, 3, L.lane);
-            dbg_check(b0, dsrc + (s + k) * 32, 2, lv, c, 4, L.lane); dbg_check(b1, dsrc + (s + k + 1) * 32, 2, lv, c, 5, L.lane);
-            dbg_check(b2, dsrc + (s + k + 2) * 32, 2, lv, c, 6, L.lane); dbg_check(b3, dsrc + (s + k + 3) * 32, 2, lv, c, 7, L.lane);
-        }
-#endif
-        ring_release(a0, a1, a2, a3, b0, b1, b2, b3);
-        if (L.lane == 0 && c + RING_STAGES < nch) {
-            const int r = srow + 4 * (c + RING_STAGES);
-            ring_issue(L, gw, st, 2, 1024u, r, r + s, 0, 0);
-        }
-        st ^= 1;
-#else
-        a0 = src[k * 32]; a1 = src[(k + 1) * 32]; a2 = src[(k + 2) * 32]; a3 = src[(k + 3) * 32];
-        b0 = src[(s + k) * 32]; b1 = src[(s + k + 1) * 32]; b2 = src[(s + k + 2) * 32]; b3 = src[(s + k + 3) * 32];
-#endif
-        double r0, r1, r2, r3;
-        fcomb2(a0, b0, a1, b1, L.tab(), r0, r1);
-        fcomb2(a2, b2, a3, b3, L.tab(), r2, r3);
-        fdst[k * 32] = r0; fdst[(k + 1) * 32] = r1; fdst[(k + 2) * 32] = r2; fdst[(k + 3) * 32] = r3;
-    }
-    L.ptr = (L.ptr & ~(7u << (3 * (lv - 1)))) | ((uint32_t)L.p() << (3 * (lv - 1)));
-}
-
 // levels 1..8 for the quad starting at bit i (i % 4 == 0, i > 0): one g node, then f nodes down to level `last`.
 // Levels 9 and 10 never touch memory: the quad routine in the kernel keeps them in registers.
 template <int S>
-__device__ __forceinline__ void llr_update8(Lane& L, const double* gw, int i, int last)   // l0 <= last <= 8
+__device__ __forceinline__ void llr_update8(Lane& L, int i, int last)   // l0 <= last <= 8
 {
     const int l0 = 11 - __ffs(i);    // <= 8
     int lv;
-#if ES_SCL_STAGED
-    if (l0 >= 2 && l0 < S) {
+    if (l0 < S) {
         const bool fuse = last > l0;
-        pass_gf<S>(L, gw, l0, fuse);
+        pass_gf<S>(L, l0, fuse);
         lv = l0 + (fuse ? 2 : 1);
-    } else
-#endif
-    {
+#pragma unroll 1
+        for (; lv <= last && lv <= S; ++lv) pass_f<S>(L, lv, false);
+    } else {
         g_level<S>(L, l0);
         lv = l0 + 1;
     }
-#if ES_SCL_STAGED
-#pragma unroll 1
-    for (; lv <= last && lv <= S; ++lv) pass_f<S>(L, gw, lv);
-#endif
 #pragma unroll 1
     for (; lv <= last; ++lv) f_level<S>(L, lv);
 }
@@ -584,13 +603,17 @@ __device__ __forceinline__ void llr_update8(Lane& L, const double* gw, int i, in
 // Rate-0 node: all `count` (multiple of 4) bits below the node are frozen, so every path's decisions there
 // are zeros and its metric grows by -ln P(x = 0 | node LLRs) = sum_k ln(1 + exp(a_k)) -- the same quantity the
 // leaf-by-leaf walk (rtwm/fastpolar.py:305-312) accumulates, summed in another order (DESIGN.md section 4,
-// "tie contract").  Four interleaved partial sums, combined as (s0 + s1) + (s2 + s3).
-__device__ __noinline__ double r0_sum(const double* a, int stride, int count, uint32_t tab)
+// "tie contract").  Four interleaved partial sums over the elements in natural order, combined as
+// (s0 + s1) + (s2 + s3).  a = position 0 of the node in the lane's slot; lq >= 0: quarter-interleaved node
+// with quarters of 2^lq elements (>= 8), lq < 0: natural order.
+__device__ __noinline__ double r0_sum(const double* a, int lq, int count, uint32_t tab)
 {
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    const int step = (lq < 0) ? 32 : 128;
 #pragma unroll 1
     for (int k = 0; k < count; k += 4) {
-        const double a0 = a[k * stride], a1 = a[(k + 1) * stride], a2 = a[(k + 2) * stride], a3 = a[(k + 3) * stride];
+        const double* e = a + ((lq < 0) ? k : (((k & ((1 << lq) - 1)) << 2) | (k >> lq))) * 32;
+        const double a0 = e[0], a1 = e[step], a2 = e[2 * step], a3 = e[3 * step];
         const D4 P = lse4(fmax(a0, 0.0), a0, fmax(a1, 0.0), a1, fmax(a2, 0.0), a2, fmax(a3, 0.0), a3, tab);   // phi takes |a| itself
         s0 += P.a;
         s1 += P.b;
@@ -619,13 +642,34 @@ struct Carry { double c0, c1, c2, c3; uint32_t qb; };
 // pen0/pen1 = penalties of deciding 0 / 1 (rtwm/fastpolar.py:32-40).  Metrics are non-negative finite
 // doubles, so their bit patterns order like unsigned integers; the reference's stable tie-break
 // (candidate index 2*ord+bit) folds into the comparison as  (kj < k) + (kj == k && c) == (kj < k + c).
-__device__ __forceinline__ int info_step(Lane& L, int list_size, double pen0, double pen1, Carry& cy)
+#ifndef ES_SCL_RANK_FP
+#define ES_SCL_RANK_FP 1     // candidate ranking with FP64 compares (2 DSETP per pair) instead of 64-bit integer compares
+#endif
+// carry: the quad-local values have to follow a clone only after an EVEN leaf (the odd leaf right after it reads
+// c0, c1 and - a clone always took bit 1 - c2); after an odd leaf nothing of them is read again.
+__device__ __forceinline__ int info_step(Lane& L, int list_size, double pen0, double pen1, Carry& cy, bool carry)
 {
     const unsigned full = 0xffffffffu;
     const double m0 = L.m + pen0, m1 = L.m + pen1;
+    int r0 = 0, r1 = 0;
+#if ES_SCL_RANK_FP
+    // metrics are non-negative finite doubles; candidates of inactive lanes are +inf: never "before" anything.
+    // The reference's stable tie-break (candidate index 2*ord+bit) makes "<" a "<=" against later candidates.
+    const double k0 = L.active ? m0 : CUDART_INF, k1 = L.active ? m1 : CUDART_INF;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const double k0j = __shfl_sync(full, k0, j, 8);
+        const double k1j = __shfl_sync(full, k1, j, 8);
+        const int oj = __shfl_sync(full, L.ord, j, 8);
+        const bool lt = oj < L.ord, le = oj <= L.ord;
+        r0 += (int)((k0j < k0) || (lt && k0j == k0)) + (int)((k1j < k0) || (lt && k1j == k0));
+        r1 += (int)((k0j < k1) || (le && k0j == k1)) + (int)((k1j < k1) || (lt && k1j == k1));
+    }
+#else
+    // bit patterns of non-negative doubles order like unsigned integers; the tie-break folds into the comparison as
+    // (kj < k) + (kj == k && c) == (kj < k + c)
     const unsigned long long k0 = L.active ? (unsigned long long)__double_as_longlong(m0) : ~0ull;
     const unsigned long long k1 = L.active ? (unsigned long long)__double_as_longlong(m1) : ~0ull;
-    int r0 = 0, r1 = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const unsigned long long k0j = __shfl_sync(full, k0, j, 8);
@@ -636,6 +680,7 @@ __device__ __forceinline__ int info_step(Lane& L, int list_size, double pen0, do
         r0 += (k0j < a0) + (k1j < a0);
         r1 += (k0j < a1) + (k1j < a2);
     }
+#endif
     const bool s0 = L.active && (r0 < list_size);
     const bool s1 = L.active && (r1 < list_size);
     const uint32_t cm = (__ballot_sync(full, s0 && s1) >> L.gbase()) & 0xffu;
@@ -650,21 +695,23 @@ __device__ __forceinline__ int info_step(Lane& L, int list_size, double pen0, do
     const uint32_t cbptr = __shfl_sync(full, L.bptr, src, 8);
     const uint32_t cbs = __shfl_sync(full, L.bs, src, 8);
     const uint32_t cqb = __shfl_sync(full, cy.qb, src, 8);
-    const double q0 = __shfl_sync(full, cy.c0, src, 8), q1 = __shfl_sync(full, cy.c1, src, 8);
-    const double q2 = __shfl_sync(full, cy.c2, src, 8), q3 = __shfl_sync(full, cy.c3, src, 8);
+    if (carry) {
+        const double q0 = __shfl_sync(full, cy.c0, src, 8), q1 = __shfl_sync(full, cy.c1, src, 8);
+        const double q2 = __shfl_sync(full, cy.c2, src, 8);
+        if (take) { cy.c0 = q0; cy.c1 = q1; cy.c2 = q2; }
+    }
     int bit = 0;
     if (s0) { L.m = m0; L.ord = r0; bit = 0; }
     else if (s1) { L.m = m1; L.ord = r1; bit = 1; }
     else if (take) {
         L.m = cm1; L.ord = cr1; L.ptr = cptr; L.bptr = cbptr; L.bs = cbs; bit = 1; L.active = true;
         cy.qb = cqb;
-        cy.c0 = q0; cy.c1 = q1; cy.c2 = q2; cy.c3 = q3;
     } else { L.active = false; }
     return bit;
 }
 
 // one decision (frozen or information bit) given the leaf LLR and phi(|leaf|)
-__device__ __forceinline__ int decide(Lane& L, bool frozen, double leaf, double ph, int list_size, Carry& cy)
+__device__ __forceinline__ int decide(Lane& L, bool frozen, double leaf, double ph, int list_size, Carry& cy, bool carry)
 {
     const double al = fabs(leaf);
     const bool pref1 = (leaf >= 0.0);
@@ -674,7 +721,7 @@ __device__ __forceinline__ int decide(Lane& L, bool frozen, double leaf, double 
         if (L.active) L.m += pen0;
         return 0;
     }
-    return info_step(L, list_size, pen0, pen1, cy);
+    return info_step(L, list_size, pen0, pen1, cy, carry);
 }
 
 // partial-sum update after a quad (bits 4q..4q+3): X = the 4 partial sums of the finished level-8 node
@@ -701,9 +748,11 @@ __device__ __forceinline__ void beta_update_quad(Lane& L, int q, uint32_t X, uin
         uint32_t* D = (lstar == 0) ? (xroot + L.lane) : (beta_rows(L, lstar) + L.lane);
         D[0] = X;
         int n = 1;
+#pragma unroll 1                                 // one quad in sixteen gets here: keep it small, not unrolled
         for (int l = 5; l > lstar; --l) {
             const int bsl = (L.bptr >> (3 * (l - 1))) & 7;
             const uint32_t* Lp = beta_rows(L, l) + L.gbase() + bsl;
+#pragma unroll 1
             for (int w = 0; w < n; ++w) {
                 const uint32_t x = D[w * 32];
                 D[(n + w) * 32] = x;
@@ -759,30 +808,25 @@ __global__ void __maxnreg__(ES_SCL_MAXNREG) scl_list_kernel(SclParams P)
         fence_proxy_async();
         __syncthreads();
     }
-    const int gwarp = blockIdx.x * W + warp;
-    L.gw = P.scratch + (size_t)gwarp * P.scratch_stride;
-    const int K = c_K;
-    const int nbytes = (K - 8) >> 3;
-    const int ngroups = (P.nunits + 3) >> 2;
-    const int nwarps = gridDim.x * W;
+    L.gw = P.scratch + (size_t)(blockIdx.x * W + warp) * P.scratch_stride;
     // per-lane (metric, bptr, ord|active) saved at bit 512 for the second decode of a +/- pair
-    uint4* const snap_base = reinterpret_cast<uint4*>(__cvta_shared_to_generic(L.wsm + LY::ABYTES + LY::BROWS_S * 128));
-#define snap (snap_base + L.lane)
+#define snap (reinterpret_cast<uint4*>(__cvta_shared_to_generic(L.wsm + LY::ABYTES + LY::BROWS_S * 128)) + L.lane)
 #define xroot (reinterpret_cast<uint32_t*>(__cvta_shared_to_generic(L.wsm)))   /* root partial sums: aliases alpha (dead by then) */
 #define gscr (L.gw)
 
-    for (int grp = gwarp; grp < ngroups; grp += nwarps) {
+#pragma unroll 1
+    for (int grp = blockIdx.x * W + warp; grp < ((P.nunits + 3) >> 2); grp += gridDim.x * W) {
         const int j = grp * 4 + (L.lane >> 3);
         const bool valid = j < P.nunits;
         const int jj = valid ? j : (P.nunits - 1);
         int w = P.pair ? 2 * jj : (P.index ? P.index[jj] : jj);
-        {   // level 0: widen this warp's 4 rows to double, [k][4].  Always +row: f(-a,-b) = f(a,b), so the first
+        {   // level 0: widen this warp's 4 rows to double, [position][4] (quarter-interleaved like the levels below).  Always +row: f(-a,-b) = f(a,b), so the first
             // half of the tree of -row is that of +row; the copy is negated at bit 512 (below) for the second half.
             const int row = P.neg_mode ? (w >> 1) : w;
             const float* src = P.llr + (size_t)row * 1024;
             double* dst = gscr + LY::G_ROWS * 32 + (L.lane >> 3);
 #pragma unroll 4
-            for (int k = L.p(); k < 1024; k += 8) dst[k * 4] = (double)__ldg(src + k);
+            for (int k = L.p(); k < 1024; k += 8) dst[ipos(0, k) * 4] = (double)__ldg(src + k);
         }
         L.m = 0.0; L.ptr = 0; L.bptr = 0; L.bs = 0; L.ord = 0;
         L.active = (L.p() == 0);
@@ -790,6 +834,8 @@ __global__ void __maxnreg__(ES_SCL_MAXNREG) scl_list_kernel(SclParams P)
         __syncwarp();
 
         int qfirst = 0;
+        spine<S>(L);              // bit 0 (quad 0 is never a rate-0 node)
+        __syncwarp();
 #pragma unroll 1
         for (int pass = 0; ; ++pass) {
 #pragma unroll 1
@@ -808,16 +854,15 @@ __global__ void __maxnreg__(ES_SCL_MAXNREG) scl_list_kernel(SclParams P)
             // rate-0 nodes: the first quad adds the whole node's penalty, every quad feeds zeros upward
             const int r0 = c_r0[q];
             const int last = (r0 == 0) ? 8 : (9 - r0);
-            if (r0 != 255) {
-                if (q == 0) spine<S>(L);
-                else llr_update8<S>(L, gscr, i, last);
+            if (r0 != 255 && q != 0) {
+                llr_update8<S>(L, i, last);
                 __syncwarp();
             }
             Carry cy; cy.qb = 0;
             if (r0 != 0) {
                 if (r0 != 255) {
-                    const LvlRef nd = lvl_ref<S>(L, last, L.p());
-                    const double pen = r0_sum(nd.base, nd.stride, 4 << (r0 - 1), L.tab());
+                    const double* nd = (last >= S) ? slvl<S>(L, last, L.p()) : L.ga() + lvl_row0(last) * 32 + L.p();
+                    const double pen = r0_sum(nd, (last >= S) ? -1 : 8 - last, 4 << (r0 - 1), L.tab());
                     if (L.active) L.m += pen;
                 }
             } else {
@@ -829,7 +874,7 @@ __global__ void __maxnreg__(ES_SCL_MAXNREG) scl_list_kernel(SclParams P)
                 double leaf, ph;
                 if ((t & 1) == 0) {
                     // level-9 node t/2 of the current level-8 node, read through the (possibly re-pointed) slot
-                    const double* l8 = lvl_ref<S>(L, 8, (L.ptr >> 21) & 7).base;
+                    const double* l8 = slvl<S>(L, 8, (L.ptr >> 21) & 7);
                     const double a0 = l8[0], a1 = l8[32], a2 = l8[64], a3 = l8[96];
                     double x0, x1;
                     if (t == 0) {
@@ -848,7 +893,7 @@ __global__ void __maxnreg__(ES_SCL_MAXNREG) scl_list_kernel(SclParams P)
                     leaf = prev ? (cy.c1 - cy.c0) : (cy.c1 + cy.c0);
                     ph = prev ? cy.c2 : cy.c3;
                 }
-                prev = decide(L, (fz >> t) & 1u, leaf, ph, P.list_size, cy);
+                prev = decide(L, (fz >> t) & 1u, leaf, ph, P.list_size, cy, (t & 1) == 0);
                 cy.qb |= (uint32_t)prev << t;
             }
             }
@@ -886,6 +931,8 @@ __global__ void __maxnreg__(ES_SCL_MAXNREG) scl_list_kernel(SclParams P)
 
         const bool wr = valid && (rank < P.list_size);
         const size_t orow = (size_t)w * P.list_size + (size_t)(wr ? rank : 0);
+        const int K = c_K;
+        const int nbytes = (K - 8) >> 3;
         uint8_t* out = P.path_payload + orow * nbytes;
         uint8_t crcreg = 0, crcbits = 0;
         uint32_t acc = 0;
