@@ -15,15 +15,21 @@ void set_error(const char* fmt, ...)
     va_end(ap);
 }
 
+int current_device()
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= ES_MAX_DEVICES) return 0;
+    return dev;
+}
+
 int sm_count()
 {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    static int n[ES_MAX_DEVICES] = {0};
+    const int dev = current_device();
+    if (n[dev] == 0) {
+        if (cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n[dev] <= 0) n[dev] = 148;
     }
-    return n;
+    return n[dev];
 }
 
 }  // namespace es

@@ -25,8 +25,12 @@ constexpr int ES_ENOTREADY = -2;
 constexpr int POLAR_N = 1024;
 constexpr int POLAR_NLOG = 10;
 
-// device info cache
-int sm_count();
+// Per-device state: constant tables, function attributes and SM counts are cached PER DEVICE (index = cudaGetDevice()),
+// never process-wide.  A table upload whose content differs from what the device already holds first drains the
+// device (cudaDeviceSynchronize), so kernels in flight on other streams keep reading consistent tables.
+constexpr int ES_MAX_DEVICES = 64;
+int current_device();          // cudaGetDevice(), clamped to [0, ES_MAX_DEVICES)
+int sm_count();                // of the current device
 
 // tx.cu keeps its own constant-memory copy of the polar code layout
 int tx_set_code(const uint16_t* pos, int K);

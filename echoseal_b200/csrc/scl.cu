@@ -38,8 +38,11 @@ __device__ uint16_t d_datapos[1024];     // the same positions in global memory,
 __constant__ uint8_t c_r0[256];
 __constant__ uint8_t c_crc8[256];        // CRC-8 (poly 0x07, MSB first) of one byte
 
-static int g_code_ready = 0;
-static int g_K = 0;
+// what each device's constant tables currently hold (es_polar_set_code)
+struct CodeDev { int ready = 0; int K = 0; uint32_t frozen[32] = {0}; };
+static CodeDev g_code[ES_MAX_DEVICES];
+#define g_code_ready (g_code[current_device()].ready)
+#define g_K (g_code[current_device()].K)
 
 // ---------------------------------------------------------------------------------------------
 // arithmetic
@@ -74,13 +77,36 @@ __device__ __noinline__ double phi1(double d0, uint32_t tab) { return phi_fast(d
 // numpy's npy_logaddexp: x==y -> x+ln2 ; else max + log1p(exp(-|x-y|)).  x == y needs no special case here:
 // phi_fast(0) == ln2 exactly (table entry 256).  f = logaddexp(a,b) - logaddexp(0,a+b) for two element pairs
 // at once (four independent phi chains).
+#ifndef ES_SCL_F2FN
+#define ES_SCL_F2FN 0       // f of two element pairs as ONE out-of-line routine taking the four operands (0: through lse4)
+#endif
+#if ES_SCL_F2FN
+__device__ __noinline__ D2 f2_fn(double a0, double b0, double a1, double b1, uint32_t tab)
+{
+    const double d0 = a0 - b0, s0 = a0 + b0, d1 = a1 - b1, s1 = a1 + b1;
+    const double A0 = ((d0 > 0.0) ? a0 : b0) + phi_fast(d0, tab);              // phi takes |d| itself
+    const double B0 = (((0.0 - s0) > 0.0) ? 0.0 : s0) + phi_fast(s0, tab);
+    const double A1 = ((d1 > 0.0) ? a1 : b1) + phi_fast(d1, tab);
+    const double B1 = (((0.0 - s1) > 0.0) ? 0.0 : s1) + phi_fast(s1, tab);
+    D2 r;
+    r.a = A0 - B0;
+    r.b = A1 - B1;
+    return r;
+}
+#endif
 __device__ __forceinline__ void fcomb2(double a0, double b0, double a1, double b1, uint32_t tab, double& r0, double& r1)
 {
+#if ES_SCL_F2FN
+    const D2 R = f2_fn(a0, b0, a1, b1, tab);
+    r0 = R.a;
+    r1 = R.b;
+#else
     const double d0 = a0 - b0, s0 = a0 + b0, d1 = a1 - b1, s1 = a1 + b1;
     const D4 P = lse4((d0 > 0.0) ? a0 : b0, d0, ((0.0 - s0) > 0.0) ? 0.0 : s0, s0,
                       (d1 > 0.0) ? a1 : b1, d1, ((0.0 - s1) > 0.0) ? 0.0 : s1, s1, tab);     // phi takes |d| itself
     r0 = P.a - P.b;
     r1 = P.c - P.d;
+#endif
 }
 
 // same value as f(a, b), also handing out the two phi terms: fm = phi(|a-b|), fp = phi(|a+b|).
@@ -172,6 +198,7 @@ struct SclParams {
     uint8_t* path_crc;       // [ncw_total][list_size]
     double* path_metric;     // [ncw_total][list_size]
     int32_t* npaths;         // [ncw_total]
+    double* min_margin;      // [ncw_total] or nullptr: smallest relative gap between the last kept and the first dropped candidate
 };
 
 constexpr int SCL_S = 6;   // first LLR-tree level kept in shared memory
@@ -198,7 +225,7 @@ template <int S> struct SclLayout {
     static constexpr int AROWS = (1 << (11 - S)) - 4;                   // levels S..8 (9 and 10 live in registers)
     static constexpr int BROWS_S = 7;                                    // beta words of levels 3..5 in shared memory
     static constexpr int BROWS_G = 24;                                   // beta words of levels 1..2 in global memory
-    static constexpr int SNAP_BYTES = 32 * 16;                           // per-lane (metric, bptr, ord|active) at bit 512
+    static constexpr int SNAP_BYTES = 32 * 32;                           // per-lane (metric, bptr, ord|active) + prune margin at bit 512
     static constexpr int ABYTES = (AROWS * 256 > 32 * 128) ? AROWS * 256 : 32 * 128;   // alpha rows; also holds the root partial sums
     static constexpr int RING_BYTES = RING_STAGES * RING_STAGE_BYTES;     // TMA staging ring of the DRAM-level passes
     static constexpr int RING_OFF = ABYTES + BROWS_S * 128 + SNAP_BYTES;
@@ -231,6 +258,7 @@ struct Lane {
     bool active;
     bool neg;            // decoding the sign-flipped variant: level 0 is negated when bit 512 is reached
     uint32_t rphase;     // staging ring: bit st = parity the next wait on stage st has to see
+    double mg_gap, mg_den;   // prune margin (kernels built with MG): running minimum of gap / den, kept as the pair
 
     __device__ __forceinline__ int p() const { return lane & 7; }               // list path = slot owned by this lane
     __device__ __forceinline__ int gbase() const { return lane & 24; }          // first lane of this lane's codeword
@@ -448,10 +476,17 @@ __device__ __forceinline__ void pass_gf_body(Lane& L, int l0, bool do_f)
         src.rs = 256u;
         src.col = (uint32_t)(L.gbase() + ((L.ptr >> (3 * (l0 - 2))) & 7)) * 8u;
     }
-    double* gdst = L.ga() + lvl_row0(l0) * 32 + L.p();          // position 0 of the g node, own slot
+    // running output pointers: g[k] sits at position 8c (c < half) or 8(c-half)+1, with g[k+1] +4 rows and g[k+h] +2
+    // rows; f[k] at k (shared memory, natural order) or at its interleaved position, which advances by 8 rows per
+    // chunk inside a quarter of nch/4... (recomputed per chunk: two shifts)
+    double* gd = L.ga() + lvl_row0(l0) * 32 + L.p();
+    double* const gd_odd = gd + 32;
     double* fdst = (l0 + 1 >= S) ? slvl<S>(L, l0 + 1, L.p()) : L.ga() + lvl_row0(l0 + 1) * 32 + L.p();
     const int lqf = (l0 + 1 >= S) ? -1 : 8 - (l0 + 1);          // f node: natural order in shared memory
+    // left-child partial sums of the g node: bit k of the lane's beta words; 32 consecutive k per word, h is a
+    // multiple of 16: the two words in use are reloaded every 16 chunks only
     const uint32_t* bw = beta_rows(L, l0) + L.gbase() + ((L.bptr >> (3 * (l0 - 1))) & 7);
+    uint32_t w0 = 0, w1 = 0;
     pass_begin<ES_SCL_TMA_GF != 0>(L, src);
     int st = 0;
     const int half = src.nch >> 1;
@@ -465,12 +500,16 @@ __device__ __forceinline__ void pass_gf_body(Lane& L, int l0, bool do_f)
             pass_refill<ES_SCL_TMA_GF != 0>(L, src, c, st, hi4(v[0], v[1], v[2], v[3]) ^ hi4(v[4], v[5], v[6], v[7]));
         }
         const int k = 2 * c;
-        const uint32_t w0 = bw[(k >> 5) * 32] >> (k & 31);
-        const uint32_t w1 = bw[((k + h) >> 5) * 32] >> ((k + h) & 31);
+        if ((c & 15) == 0) {
+            w0 = bw[(k >> 5) * 32];
+            w1 = bw[((k + h) >> 5) * 32] >> (h & 31);         // h = 16 (level 5): the upper half of the same word
+        }
+        if (c == half) gd = gd_odd;
         const double g0 = gcomb(v[0], v[2], w0 & 1u), gh0 = gcomb(v[1], v[3], w1 & 1u);
         const double g1 = gcomb(v[4], v[6], (w0 >> 1) & 1u), gh1 = gcomb(v[5], v[7], (w1 >> 1) & 1u);
-        double* gd = gdst + ((c < half) ? 8 * c : 8 * (c - half) + 1) * 32;      // position of g[k]; g[k+1] +4, g[k+h] +2
+        w0 >>= 2; w1 >>= 2;
         gd[0] = g0; gd[2 * 32] = gh0; gd[4 * 32] = g1; gd[6 * 32] = gh1;
+        gd += 8 * 32;
         if (do_f) {
             double r0, r1;
             fcomb2(g0, gh0, g1, gh1, L.tab(), r0, r1);
@@ -647,6 +686,7 @@ struct Carry { double c0, c1, c2, c3; uint32_t qb; };
 #endif
 // carry: the quad-local values have to follow a clone only after an EVEN leaf (the odd leaf right after it reads
 // c0, c1 and - a clone always took bit 1 - c2); after an odd leaf nothing of them is read again.
+template <bool MG>
 __device__ __forceinline__ int info_step(Lane& L, int list_size, double pen0, double pen1, Carry& cy, bool carry)
 {
     const unsigned full = 0xffffffffu;
@@ -681,6 +721,20 @@ __device__ __forceinline__ int info_step(Lane& L, int list_size, double pen0, do
         r1 += (k0j < a1) + (k1j < a2);
     }
 #endif
+    if (MG) {
+        // prune margin (rtwm/fastpolar.py:288-299 sorts the 2|P| candidates and keeps L): relative gap between rank L-1
+        // and rank L, minimum over the decode.  gap/den is compared by cross-multiplication; one division at the end.
+        const bool hasA = L.active && (r0 == list_size - 1 || r1 == list_size - 1);
+        const bool hasB = L.active && (r0 == list_size || r1 == list_size);
+        const double vA = (r0 == list_size - 1) ? m0 : m1, vB = (r0 == list_size) ? m0 : m1;
+        const uint32_t bA = (__ballot_sync(full, hasA) >> L.gbase()) & 0xffu;
+        const uint32_t bB = (__ballot_sync(full, hasB) >> L.gbase()) & 0xffu;
+        const double mA = __shfl_sync(full, vA, __ffs(bA) - 1, 8), mB = __shfl_sync(full, vB, __ffs(bB) - 1, 8);
+        if (bB) {        // more than L candidates: this step prunes
+            const double gap = mB - mA;
+            if (gap * L.mg_den < L.mg_gap * mB) { L.mg_gap = gap; L.mg_den = mB; }
+        }
+    }
     const bool s0 = L.active && (r0 < list_size);
     const bool s1 = L.active && (r1 < list_size);
     const uint32_t cm = (__ballot_sync(full, s0 && s1) >> L.gbase()) & 0xffu;
@@ -711,6 +765,7 @@ __device__ __forceinline__ int info_step(Lane& L, int list_size, double pen0, do
 }
 
 // one decision (frozen or information bit) given the leaf LLR and phi(|leaf|)
+template <bool MG>
 __device__ __forceinline__ int decide(Lane& L, bool frozen, double leaf, double ph, int list_size, Carry& cy, bool carry)
 {
     const double al = fabs(leaf);
@@ -721,7 +776,7 @@ __device__ __forceinline__ int decide(Lane& L, bool frozen, double leaf, double 
         if (L.active) L.m += pen0;
         return 0;
     }
-    return info_step(L, list_size, pen0, pen1, cy, carry);
+    return info_step<MG>(L, list_size, pen0, pen1, cy, carry);
 }
 
 // partial-sum update after a quad (bits 4q..4q+3): X = the 4 partial sums of the finished level-8 node
@@ -783,7 +838,7 @@ __device__ __forceinline__ uint8_t crc8_step_bit(uint8_t reg, uint32_t bit)
 // ---------------------------------------------------------------------------------------------
 // list decoder kernel: W warps per CTA share the phi tables; each warp decodes 4 codewords at a time
 // ---------------------------------------------------------------------------------------------
-template <int S, int W>
+template <int S, int W, bool MG>
 __global__ void __maxnreg__(ES_SCL_MAXNREG) scl_list_kernel(SclParams P)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -829,6 +884,7 @@ __global__ void __maxnreg__(ES_SCL_MAXNREG) scl_list_kernel(SclParams P)
             for (int k = L.p(); k < 1024; k += 8) dst[ipos(0, k) * 4] = (double)__ldg(src + k);
         }
         L.m = 0.0; L.ptr = 0; L.bptr = 0; L.bs = 0; L.ord = 0;
+        L.mg_gap = CUDART_INF; L.mg_den = 1.0;
         L.active = (L.p() == 0);
         L.neg = P.neg_mode && (w & 1);
         __syncwarp();
@@ -846,6 +902,7 @@ __global__ void __maxnreg__(ES_SCL_MAXNREG) scl_list_kernel(SclParams P)
                 // (global rows, never rewritten) plus these per-lane words
                 *snap = make_uint4((uint32_t)__double2loint(L.m), (uint32_t)__double2hiint(L.m), L.bptr,
                                    ((uint32_t)L.ord << 1) | (L.active ? 1u : 0u));
+                if (MG) *reinterpret_cast<double2*>(snap + 32) = make_double2(L.mg_gap, L.mg_den);
             }
             if (q == 128) {
                 if (L.neg) negate_level0(gscr + LY::G_ROWS * 32 + (L.lane >> 3) + L.p() * 4);
@@ -893,7 +950,7 @@ __global__ void __maxnreg__(ES_SCL_MAXNREG) scl_list_kernel(SclParams P)
                     leaf = prev ? (cy.c1 - cy.c0) : (cy.c1 + cy.c0);
                     ph = prev ? cy.c2 : cy.c3;
                 }
-                prev = decide(L, (fz >> t) & 1u, leaf, ph, P.list_size, cy, (t & 1) == 0);
+                prev = decide<MG>(L, (fz >> t) & 1u, leaf, ph, P.list_size, cy, (t & 1) == 0);
                 cy.qb |= (uint32_t)prev << t;
             }
             }
@@ -952,7 +1009,10 @@ __global__ void __maxnreg__(ES_SCL_MAXNREG) scl_list_kernel(SclParams P)
             P.path_crc[orow] = (L.active && crcreg == crcbits) ? 1 : 0;
             P.path_metric[orow] = L.active ? L.m : CUDART_INF;
         }
-        if (valid && L.p() == 0) P.npaths[w] = np;
+        if (valid && L.p() == 0) {
+            P.npaths[w] = np;
+            if (MG) P.min_margin[w] = L.mg_gap / L.mg_den;      // +inf when no step pruned
+        }
         __syncwarp();
         if (!P.pair || pass == 1) break;
         // second pass: the sign-flipped variant of the same row, restarted at bit 512
@@ -961,6 +1021,7 @@ __global__ void __maxnreg__(ES_SCL_MAXNREG) scl_list_kernel(SclParams P)
         L.bptr = sn.z;
         L.ord = (int)(sn.w >> 1);
         L.active = (sn.w & 1u) != 0u;
+        if (MG) { const double2 mg = *reinterpret_cast<const double2*>(snap + 32); L.mg_gap = mg.x; L.mg_den = mg.y; }
         L.neg = true;
         w += 1;
         qfirst = 128;
@@ -1118,18 +1179,33 @@ constexpr int SCL_W = ES_SCL_W;  // warps per CTA = one CTA per SM: one copy of 
 static size_t scl_smem_bytes() { return (size_t)SclLY::TAB_BYTES + (size_t)SCL_W * SclLY::WARP_BYTES; }
 static size_t scl_scratch_doubles_per_warp() { return SclLY::G_DOUBLES; }
 
-static int g_scl_ctas_per_sm = 0;
-static double* g_phi_tab_dev = nullptr;
+// per-device launch state (the phi tables and the function attributes belong to a device's context)
+struct SclDev { int ctas_per_sm = 0; double* phi_tab = nullptr; };
+static SclDev g_scl_dev[ES_MAX_DEVICES];
 
-static int scl_configure()
+static int scl_configure(SclDev** out)
 {
-    if (g_scl_ctas_per_sm) return ES_OK;
-    auto kern = scl_list_kernel<SCL_S, SCL_W>;
-    ES_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scl_smem_bytes()));
-    ES_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                    cudaSharedmemCarveoutMaxShared));
+    int dev = 0;
+    ES_CUDA_OK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= ES_MAX_DEVICES) { set_error("device %d out of range", dev); return ES_EINVAL; }
+    SclDev& D = g_scl_dev[dev];
+    *out = &D;
+    if (D.ctas_per_sm) return ES_OK;
     int nb = 0;
-    ES_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, SCL_W * 32, scl_smem_bytes()));
+    {
+        auto kern = scl_list_kernel<SCL_S, SCL_W, false>;
+        ES_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scl_smem_bytes()));
+        ES_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        ES_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, SCL_W * 32, scl_smem_bytes()));
+    }
+    {
+        auto kern = scl_list_kernel<SCL_S, SCL_W, true>;
+        int nb2 = 0;
+        ES_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scl_smem_bytes()));
+        ES_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        ES_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, kern, SCL_W * 32, scl_smem_bytes()));
+        if (nb2 < nb) nb = nb2;
+    }
     if (nb < 1) { set_error("scl_list_kernel does not fit on an SM"); return ES_EINVAL; }
     // phi tables (phi_impl.h layout)
     static double tab[PHI_TAB_DOUBLES];
@@ -1137,9 +1213,9 @@ static int scl_configure()
     double kk[PHI_NK];
     phi_fill_k(kk);
     ES_CUDA_OK(cudaMemcpyToSymbol(c_phi_k, kk, sizeof(kk)));
-    ES_CUDA_OK(cudaMalloc(&g_phi_tab_dev, sizeof(tab)));
-    ES_CUDA_OK(cudaMemcpy(g_phi_tab_dev, tab, sizeof(tab), cudaMemcpyHostToDevice));
-    g_scl_ctas_per_sm = nb;
+    ES_CUDA_OK(cudaMalloc(&D.phi_tab, sizeof(tab)));
+    ES_CUDA_OK(cudaMemcpy(D.phi_tab, tab, sizeof(tab), cudaMemcpyHostToDevice));
+    D.ctas_per_sm = nb;
     return ES_OK;
 }
 
@@ -1160,6 +1236,11 @@ int es_polar_set_code(const uint8_t* frozen_host, int K)
         else { if (n < 1024) pos[n] = (uint16_t)i; ++n; }
     }
     if (n != K) { set_error("es_polar_set_code: %d unfrozen positions != K=%d", n, K); return ES_EINVAL; }
+    CodeDev& CD = g_code[current_device()];
+    if (CD.ready) {
+        if (CD.K == K && memcmp(CD.frozen, words, sizeof(words)) == 0) return ES_OK;      // this device already holds this code
+        ES_CUDA_OK(cudaDeviceSynchronize());      // a different code: nothing in flight may still be reading the old tables
+    }
     ES_CUDA_OK(cudaMemcpyToSymbol(c_frozen, words, sizeof(words)));
     ES_CUDA_OK(cudaMemcpyToSymbol(c_datapos, pos, sizeof(pos)));
     ES_CUDA_OK(cudaMemcpyToSymbol(d_datapos, pos, sizeof(pos)));
@@ -1190,8 +1271,9 @@ int es_polar_set_code(const uint8_t* frozen_host, int K)
         ES_CUDA_OK(cudaMemcpyToSymbol(c_crc8, tab, sizeof(tab)));
     }
     { const int rc = tx_set_code(pos, K); if (rc != ES_OK) return rc; }
-    g_code_ready = 1;
-    g_K = K;
+    CD.ready = 1;
+    CD.K = K;
+    memcpy(CD.frozen, words, sizeof(words));
     return ES_OK;
 }
 
@@ -1206,14 +1288,16 @@ int es_scl_debug_read(unsigned long long* out, int n)
 
 int es_scl_grid_ctas(void)
 {
-    if (scl_configure() != ES_OK) return -1;
-    return sm_count() * g_scl_ctas_per_sm;
+    SclDev* D;
+    if (scl_configure(&D) != ES_OK) return -1;
+    return sm_count() * D->ctas_per_sm;
 }
 
 int es_scl_ctas_per_sm(void)
 {
-    if (scl_configure() != ES_OK) return -1;
-    return g_scl_ctas_per_sm;
+    SclDev* D;
+    if (scl_configure(&D) != ES_OK) return -1;
+    return D->ctas_per_sm;
 }
 
 size_t es_scl_scratch_bytes(void)
@@ -1235,19 +1319,21 @@ int es_scl_hard(const float* llr, int ncw, int neg_mode, uint8_t* hard_payload, 
     return ES_OK;
 }
 
-int es_scl_list(const float* llr, const int32_t* index, int ncw, int neg_mode, int list_size,
-                void* scratch, size_t scratch_bytes,
-                uint8_t* path_payload, uint8_t* path_crc, double* path_metric, int32_t* npaths, void* stream)
+int es_scl_list_margin(const float* llr, const int32_t* index, int ncw, int neg_mode, int list_size,
+                       void* scratch, size_t scratch_bytes,
+                       uint8_t* path_payload, uint8_t* path_crc, double* path_metric, int32_t* npaths, double* min_margin,
+                       void* stream)
 {
     if (!g_code_ready) { set_error("es_scl_list: call es_polar_set_code first"); return ES_ENOTREADY; }
     if (list_size < 1 || list_size > 8) { set_error("es_scl_list: list_size %d not in 1..8", list_size); return ES_EINVAL; }
     if (ncw <= 0) return ES_OK;
-    int rc = scl_configure();
+    SclDev* D;
+    int rc = scl_configure(&D);
     if (rc != ES_OK) return rc;
     const int pair = (neg_mode && !index && (ncw % 2) == 0) ? 1 : 0;
     const int nunits = pair ? ncw / 2 : ncw;
     const int ngroups = (nunits + 3) / 4;
-    int ctas = sm_count() * g_scl_ctas_per_sm;
+    int ctas = sm_count() * D->ctas_per_sm;
     const int need_ctas = (ngroups + SCL_W - 1) / SCL_W;
     if (ctas > need_ctas) ctas = need_ctas;
     const size_t need = (size_t)ctas * SCL_W * scl_scratch_doubles_per_warp() * sizeof(double);
@@ -1256,11 +1342,21 @@ int es_scl_list(const float* llr, const int32_t* index, int ncw, int neg_mode, i
     P.llr = llr; P.index = index; P.ncw = ncw; P.neg_mode = neg_mode; P.list_size = list_size;
     P.pair = pair; P.nunits = nunits;
     P.scratch = (double*)scratch; P.scratch_stride = scl_scratch_doubles_per_warp();
-    P.phi_tab = g_phi_tab_dev;
+    P.phi_tab = D->phi_tab;
     P.path_payload = path_payload; P.path_crc = path_crc; P.path_metric = path_metric; P.npaths = npaths;
-    scl_list_kernel<SCL_S, SCL_W><<<ctas, SCL_W * 32, scl_smem_bytes(), (cudaStream_t)stream>>>(P);
+    P.min_margin = min_margin;
+    if (min_margin) scl_list_kernel<SCL_S, SCL_W, true><<<ctas, SCL_W * 32, scl_smem_bytes(), (cudaStream_t)stream>>>(P);
+    else scl_list_kernel<SCL_S, SCL_W, false><<<ctas, SCL_W * 32, scl_smem_bytes(), (cudaStream_t)stream>>>(P);
     ES_CUDA_OK(cudaGetLastError());
     return ES_OK;
+}
+
+int es_scl_list(const float* llr, const int32_t* index, int ncw, int neg_mode, int list_size,
+                void* scratch, size_t scratch_bytes,
+                uint8_t* path_payload, uint8_t* path_crc, double* path_metric, int32_t* npaths, void* stream)
+{
+    return es_scl_list_margin(llr, index, ncw, neg_mode, list_size, scratch, scratch_bytes, path_payload, path_crc,
+                              path_metric, npaths, nullptr, stream);
 }
 
 int es_scl_collect_hits(const uint8_t* hard_crc, const uint8_t* path_crc, const uint8_t* hard_payload,

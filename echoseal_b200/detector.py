@@ -428,9 +428,11 @@ class WatermarkDetector:
         out = rx_gpu.llr(fr["mf_aligned"], torch.tensor([pidx], dtype=torch.int32, device=dev), pn)
         return out[1 if pn_variant else 0].cpu().numpy()
 
-    def _try_decode_frame(self, frame: np.ndarray, frame_ctr: int) -> bool:
+    def _try_decode_frame(self, frame: np.ndarray, frame_ctr: int, _llr_rows=None) -> bool:
         """rtwm/detector.py:154-233: the 4-variant SCL ladder with the AEAD validator, magic / counter
-        checks and the session-nonce latch, for one band-passed frame and one counter."""
+        checks and the session-nonce latch, for one band-passed frame and one counter.
+        _llr_rows (additive, float32[2,1024]): decode these two LLR variants (PN convention 0 / 1) instead of the
+        frame's own — the ladder of rtwm/detector.py:168-190 from given LLRs, e.g. the reference's."""
         band_idx = BAND_PLAN.index(choose_band(self._band_key, frame_ctr))
         fr, pidx = self._frame_front(frame, band_idx)
         enum = dict(band_count=np.zeros((1, 4), np.int32), item_offset=np.array([0, 1], np.int64),
@@ -440,7 +442,16 @@ class WatermarkDetector:
         ns = np.zeros((1, 9), np.uint8)
         if self.session_nonce:
             ns[0, 0] = 1; ns[0, 1:] = np.frombuffer(self.session_nonce, np.uint8)
-        v, _ = _decode_phase(self._bank, np.zeros(1, np.int32), enum, fr["mf_aligned"], self._list_size, ns, self._dev())
+        d = _Decode(self._bank, np.zeros(1, np.int32), enum, fr["mf_aligned"], self._list_size, self._dev())
+        if _llr_rows is None:
+            d.enqueue_llr()
+        else:
+            rows = np.ascontiguousarray(_llr_rows, dtype=np.float32)
+            if rows.shape != (2, 1024):
+                raise ValueError("_llr_rows must be float32[2,1024]")
+            d.llr = torch.from_numpy(rows).to(self._dev())
+        d.enqueue_scl()
+        v, _ = d.finish(ns)
         if ns[0, 0]:
             self.session_nonce = ns[0, 1:].tobytes()
         return bool(v[0])

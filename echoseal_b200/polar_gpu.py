@@ -25,7 +25,9 @@ def set_code(N_: int = 1024, K: int = 448):
 
 
 def _get_scratch(device):
-    key = (device.index if device.index is not None else torch.cuda.current_device())
+    """SCL scratch of the (device, current stream) pair: two decodes in flight on two streams must not share it."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(),
+           torch.cuda.current_stream(device).cuda_stream)
     s = _scratch.get(key)
     if s is None:
         nbytes = int(N.lib().es_scl_scratch_bytes())
@@ -53,9 +55,12 @@ def hard_decide(llr: torch.Tensor, neg_mode: int = 0, K: int = 448):
 
 
 def list_decode(llr: torch.Tensor, list_size: int = 8, neg_mode: int = 0, index: torch.Tensor | None = None,
-                K: int = 448):
+                K: int = 448, want_margin: bool = False):
     """CA-SCL list stage.  Returns dict(payload uint8[ncw,L,55], crc uint8[ncw,L], metric f64[ncw,L],
-    npaths i32[ncw]) — paths in ascending-metric order; rows not listed in `index` are left zero/inf."""
+    npaths i32[ncw]) — paths in ascending-metric order; rows not listed in `index` are left zero/inf.
+    want_margin adds min_margin f64[ncw]: the smallest relative gap between the last kept and the first dropped
+    candidate over the decode's pruning steps (rtwm/fastpolar.py:288-299); below ~1e-11 the reference's own survivor
+    choice depends on libm rounding."""
     N.require_cuda(llr, index)
     if llr.dtype != torch.float32 or llr.dim() != 2 or llr.shape[1] != 1024:
         raise ValueError("llr must be float32 [rows,1024]")
@@ -71,6 +76,8 @@ def list_decode(llr: torch.Tensor, list_size: int = 8, neg_mode: int = 0, index:
         metric=torch.full((ncw_total, list_size), float("inf"), dtype=torch.float64, device=dev),
         npaths=torch.zeros((ncw_total,), dtype=torch.int32, device=dev),
     )
+    if want_margin:
+        out["min_margin"] = torch.full((ncw_total,), float("inf"), dtype=torch.float64, device=dev)
     if index is not None:
         if index.dtype != torch.int32:
             raise ValueError("index must be int32")
@@ -81,10 +88,10 @@ def list_decode(llr: torch.Tensor, list_size: int = 8, neg_mode: int = 0, index:
         return out
     scratch = _get_scratch(dev)
     with N.timed("scl_list"):
-        N.check(N.lib().es_scl_list(N.ptr(llr), N.ptr(index), C.c_int(n), C.c_int(neg_mode), C.c_int(list_size),
-                                    N.ptr(scratch), C.c_size_t(scratch.numel()),
-                                    N.ptr(out["payload"]), N.ptr(out["crc"]), N.ptr(out["metric"]),
-                                    N.ptr(out["npaths"]), N.stream_ptr()), "es_scl_list")
+        N.check(N.lib().es_scl_list_margin(N.ptr(llr), N.ptr(index), C.c_int(n), C.c_int(neg_mode), C.c_int(list_size),
+                                           N.ptr(scratch), C.c_size_t(scratch.numel()),
+                                           N.ptr(out["payload"]), N.ptr(out["crc"]), N.ptr(out["metric"]),
+                                           N.ptr(out["npaths"]), N.ptr(out.get("min_margin")), N.stream_ptr()), "es_scl_list")
     return out
 
 

@@ -43,6 +43,14 @@ int es_scl_list(const float* llr, const int32_t* index, int ncw, int neg_mode, i
                 void* scratch, size_t scratch_bytes,
                 uint8_t* path_payload /*[ncw_total][L][(K-8)/8]*/, uint8_t* path_crc /*[ncw_total][L]*/,
                 double* path_metric /*[ncw_total][L]*/, int32_t* npaths /*[ncw_total]*/, void* stream);
+/* The same decode, also reporting per codeword the smallest RELATIVE gap between the last candidate kept and the first
+ * one dropped over all pruning steps — (m[L] - m[L-1]) / m[L] in the sorted candidate list of rtwm/fastpolar.py:288-299
+ * (+inf when no step pruned).  A margin within a few ulp (< 1e-11) marks a codeword whose survivor choice the
+ * reference itself leaves to libm rounding (tie contract).  min_margin: [ncw_total] doubles. */
+int es_scl_list_margin(const float* llr, const int32_t* index, int ncw, int neg_mode, int list_size,
+                       void* scratch, size_t scratch_bytes,
+                       uint8_t* path_payload, uint8_t* path_crc, double* path_metric, int32_t* npaths,
+                       double* min_margin /*[ncw_total]*/, void* stream);
 /* compaction of the CRC-passing candidates (hard decision = slot 0, list rank r = slot r+1): the inputs of the
  * validator callback of PolarCode.decode (rtwm/fastpolar.py:269-276, 335-349). Unordered; *counter may exceed cap. */
 int es_scl_collect_hits(const uint8_t* hard_crc, const uint8_t* path_crc, const uint8_t* hard_payload,

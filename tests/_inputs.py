@@ -106,3 +106,14 @@ def make_clip_spec(kind, key, seed, secs, start_ctr, mode, embedder_factory=None
     tx = embedder_factory(key, seed)
     tx.frame_ctr = start_ctr
     return np.ascontiguousarray(tx.process(host), dtype=np.float32), key
+
+
+def assert_llr_close(got, ref, what=""):
+    """LLR parity (north_star: 1e-4 relative): |got - ref| <= 1e-4 |ref| + 2e-5.  The absolute floor covers values next
+    to zero, where (despread - mean) cancels in float32 (rtwm/detector.py:396-405): 2e-5 is 1.7e-6 of the +-12 clip
+    range, the size of the float32 rounding the reference itself carries (oracle vs reference: 1e-6)."""
+    got = np.asarray(got, np.float64); ref = np.asarray(ref, np.float64)
+    err = np.abs(got - ref)
+    lim = 1e-4 * np.abs(ref) + 2e-5
+    assert (err <= lim).all(), f"{what}: max err {err.max():.3e} at ref {ref[np.argmax(err - lim)]:.4f}"
+    return float(err.max())

@@ -50,7 +50,7 @@ def test_scl_bit_exact_vs_oracle_awgn(gpu, L):
     # tie-free codewords (oracle's min relative prune gap > 1e-11): every final
     # path, in order, bit-exact, metrics to 1e-12.  Near-tie codewords (gap within a few ulp of the
     # metric — the reference's own glibc/SVML rounding decides those) are only counted.
-    near = ref["stats"][:, 1] < 1e-11
+    near = polar_gpu.list_decode(torch.from_numpy(llr).cuda(), list_size=L, want_margin=True)["min_margin"].cpu().numpy() < 1e-11
     bad = np.array([not (pay[w] == refpay[w]).all() for w in range(llr.shape[0])])
     assert not (bad & ~near).any(), f"payload mismatch on tie-free codewords: {np.flatnonzero(bad & ~near)[:8]}"
     print(f"L={L}: {int((~near).sum())} tie-free codewords bit-exact; near-tie {int(near.sum())}, "
@@ -60,6 +60,33 @@ def test_scl_bit_exact_vs_oracle_awgn(gpu, L):
     np.testing.assert_allclose(met[ok], ref["path_metric"][ok], rtol=1e-12, atol=1e-12)
     if L == 8:
         assert near.mean() < 0.25 and bad.sum() <= 2
+
+
+def test_prune_margin_export(gpu):
+    """es_scl_list_margin: the kernel's own min relative prune gap (rtwm/fastpolar.py:288-299) equals the one the
+    device-arithmetic model records, plain and in the detector's +/- pairing, and classifies the same codewords as
+    near-tie as the glibc oracle does (the product can count its near-ties without a CPU oracle)."""
+    torch, polar_gpu = gpu
+    from oracle import polar_oracle as po
+    llr, _ = awgn_llr_set(256, seed=7)
+    tl = detector_like_llr_set(96, seed=3)
+    for data, neg in ((llr, 0), (tl, 0), (tl, 1)):
+        d = torch.from_numpy(data).cuda()
+        for L in (8, 4):
+            out = polar_gpu.list_decode(d, list_size=L, neg_mode=neg, want_margin=True)
+            got = out["min_margin"].cpu().numpy()
+            model = po.scl_batch(data, L=L, device_arith=True, neg_mode=bool(neg))["stats"][:, 1]
+            fin = np.isfinite(model)
+            assert (np.isfinite(got) == fin).all()
+            np.testing.assert_allclose(got[fin], model[fin], rtol=1e-9, atol=0)
+            plain = polar_gpu.list_decode(d, list_size=L, neg_mode=neg)
+            assert (plain["payload"] == out["payload"]).all() and (plain["metric"] == out["metric"]).all()
+    # tie-free classification against the glibc oracle on the AWGN set
+    d = torch.from_numpy(llr).cuda()
+    got = polar_gpu.list_decode(d, list_size=8, want_margin=True)["min_margin"].cpu().numpy()
+    ref = po.scl_batch(llr, L=8)["stats"][:, 1]
+    clear = (ref > 1e-9) | (ref < 1e-13)          # away from the 1e-11 line itself
+    assert ((got < 1e-11) == (ref < 1e-11))[clear].all()
 
 
 def test_scl_matches_reference_golden(gpu):
