@@ -30,7 +30,18 @@ N_SAMPLES = int(FS * SECS)
 ALG_BYTES_PER_AUDIO_S = 4 * FS             # RX reads each float32 input sample once
 SCL_ALG_BYTES_PER_CW = 4096 + 55           # fp32 LLR in + payload out
 SCL_NODE_UPDATES_PER_CW = 81920            # N log2 N * L
-SCL_DRAM_BYTES_PER_CW = 555e3              # dram read+write per codeword, ncu --set full (profiles/r01_scl_list_ncu_full.txt: 10.51 GB / 18944 cw, +/- pairs)
+PHI_FP64_INSTR = 18                        # FP64 instructions of one phi evaluation (csrc/phi_impl.h; SASS census in profiles/r02_scl_sass_census.txt)
+
+
+def scl_measured_traffic():
+    """DRAM bytes (read + write) per codeword of scl_list_kernel in the detector's +/- pairing, taken from the committed
+    ncu --set full capture of the shipped kernel (profiles/r02_scl_traffic.json, written by tools/ncu_summary.py --traffic).
+    None when no capture is committed: the bench then reports traffic = null rather than a stale constant."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r02_scl_traffic.json")))
+        return float(d["dram_bytes_per_codeword"]), d.get("source")
+    except Exception:
+        return None, None
 
 
 def scl_phi_counts():
@@ -257,7 +268,7 @@ def run_reference(args, rank, world):
     emit(line)
 
 
-def run_scl(args):
+def run_scl(args, emit_line=True):
     """configs[3]: Polar(1024,448)+CRC-8 SCL-8 microbench on synthetic AWGN LLRs (sigma cycling over
     0.15/0.3/0.4/0.5), reference semantics with validator=None: hard-decision fast path first, list decoder
     only for codewords whose hard decision fails the CRC.  Checked bit-exactly against the oracle on a sample."""
@@ -312,18 +323,38 @@ def run_scl(args):
     value = args.steps * ncw / (ms / 1e3)
     peaks, kind = measured_peaks()
     scl_ms = kt.get("scl_list", 0.0) / args.steps
-    emit({"metric": "polar_scl8_codewords_per_second", "value": value, "unit": "codewords/s", "n_gpus": 1,
-          "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-          "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-          "config": {"workload": f"configs[3]: {ncw} codewords of synthetic AWGN LLRs, Polar(1024,448)+CRC-8 SCL-8",
-                     "list_decoded": n_list, "fast_path": ncw - n_list},
-          "gpu_launches": N.LAUNCHES - l0,
-          "roofline_issue": {"kernel": "scl_list_kernel", "achieved": n_list / (scl_ms / 1e3) if scl_ms else None,
-                             "unit": "list-decoded codewords/s", "avg_launch_ms": scl_ms},
-          "parity": {"sample": m, "bit_exact_payload_and_ok": same}})
+    # CPU baseline: the oracle (C restatement of rtwm/fastpolar.py, reference semantics incl. the fast-path early return)
+    # on all host cores, on the same first m codewords
+    cores = os.cpu_count() or 1
+    t0 = time.perf_counter()
+    po.scl_batch(llr[:m].cpu().numpy(), L=8, skip_on_hard_crc=True, threads=cores)
+    cpu_s = time.perf_counter() - t0
+    # issue bound of the list stage: every list-decoded codeword is a full (unpaired) decode with the rate-0 shortcut
+    phi_walk, _ = scl_phi_counts()
+    fp64_lane_rate = 148 * 64 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6
+    bound = fp64_lane_rate / (phi_walk * PHI_FP64_INSTR)
+    list_cw_s = n_list / (scl_ms / 1e3) if scl_ms else None
+    line = {"metric": "polar_scl8_codewords_per_second", "value": value, "unit": "codewords/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"configs[3]: {ncw} codewords of synthetic AWGN LLRs, Polar(1024,448)+CRC-8 SCL-8",
+                       "list_decoded": n_list, "fast_path": ncw - n_list,
+                       "l2": "4 KB of LLRs per codeword: the 4 GB input set exceeds the 126 MB L2"},
+            "gpu_launches": N.LAUNCHES - l0,
+            "roofline": {"kernel": "scl_list_kernel", "bound": "fp64_issue", "achieved": list_cw_s, "peak": bound,
+                         "unit": "list-decoded codewords/s", "frac": (list_cw_s / bound) if list_cw_s else None,
+                         "avg_launch_ms": scl_ms, "traffic": None,
+                         "bound_def": f"148 SM x 64 FP64 lanes x sm_max_mhz / ({phi_walk:.0f} phi of the leaf-by-leaf walk x "
+                                      f"{PHI_FP64_INSTR} FP64 instr)"},
+            "cpu_baseline": {"value": m / cpu_s, "unit": "codewords/s", "cores": cores, "kind": "port",
+                             "sample": f"first {m} codewords of the same set, oracle SCL-8 with the fast-path early return, {cpu_s:.2f} s"},
+            "parity": {"sample": m, "bit_exact_payload_and_ok": same}}
+    if emit_line:
+        emit(line)
+    return line
 
 
-def run_tx(args):
+def run_tx(args, emit_line=True):
     """configs[4]: TX embed throughput, 4096 concurrent 48 kHz streams x 1024-sample blocks (rtwm/audioio.py:18),
     per-stream key / counter / session nonce; host crypto (seal, PN, hop) inside the timed region."""
     import torch
@@ -358,7 +389,39 @@ def run_tx(args):
             "streams": S, "blocks": int(lat.size),
             "note": "wall time of TxService.process_block: pinned H2D + frame kernel when due + mix + D2H, per block of all streams"}
     peaks, kind = measured_peaks()
-    emit({"metric": "tx_samples_embedded_per_second", "value": value, "unit": "samples/s", "n_gpus": 1, "steps": steps,
+    # CPU baseline: the TX oracle (restatement of rtwm/embedder.py:44-168) on all host cores, one stream of 1 s per process
+    cores = os.cpu_count() or 1
+    import multiprocessing as mp
+    t0 = time.perf_counter()
+    with mp.get_context("fork").Pool(cores) as pool:
+        pool.map(_oracle_tx_one, list(range(2 * cores)), chunksize=1)
+    cpu_s = time.perf_counter() - t0
+    cpu_value = 2 * cores * 48000 / cpu_s
+    # parity: 8 streams x one 3000-sample block of a bank fed replayable randomness against the TX oracle given the same
+    # payload bytes (north_star: 1e-4 relative to the block peak)
+    from oracle import tx_oracle as txo
+    pkeys = [bench_key(100 + i) for i in range(8)]
+    stream = np.random.default_rng(0).integers(0, 256, 1 << 16, dtype=np.uint8).tobytes()
+    pos = [0]
+
+    def rand(n):
+        b_ = stream[pos[0]:pos[0] + n]; pos[0] += n
+        return b_
+    pbank = embedder.EmbedderBank(pkeys, rand=rand)
+    sn = pbank.session_nonce.copy()
+    px = (0.1 * np.random.default_rng(1).standard_normal((8, 3000))).astype(np.float32)
+    start = pos[0]
+    pout = pbank.process(px)
+    pout = pout.cpu().numpy() if hasattr(pout, "cpu") else np.asarray(pout)
+    rnd = np.frombuffer(stream[start:start + 23 * 8 * 3], np.uint8).reshape(8, 3, 23)
+    worst = 0.0
+    for s_ in range(8):
+        k = txo.Keys(pkeys[s_])
+        chips = np.concatenate([txo.frame_chips(k, f, txo.build_payload(k, f, sn[s_].tobytes(), rnd[s_, f, :11].tobytes(),
+                                                                         rnd[s_, f, 11:].tobytes())) for f in range(3)])
+        ref = txo.mix(px[s_], chips[:3000])
+        worst = max(worst, float(np.abs(pout[s_] - ref).max() / np.abs(ref).max()))
+    line = {"metric": "tx_samples_embedded_per_second", "value": value, "unit": "samples/s", "n_gpus": 1, "steps": steps,
           "warmup": args.warmup, "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak",
           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
           "config": {"workload": f"configs[4]: {S} concurrent 48 kHz streams x {B}-sample blocks, PN spread + HMAC hop + "
@@ -368,7 +431,103 @@ def run_tx(args):
           "roofline": {"kernel": "tx_mix_kernel+tx_frames_kernel", "bound": "hbm", "achieved": value * 8 / 1e9,
                        "peak": float(peaks.get("hbm_gbs", 6650.0)), "unit": "GB/s",
                        "frac": value * 8 / 1e9 / float(peaks.get("hbm_gbs", 6650.0)), "traffic": None,
-                       "note": "host crypto feeder (AEAD seal + AES PN + HMAC per frame) is inside the timed region"}})
+                       "note": "host crypto feeder (AEAD seal + AES PN + HMAC per frame) is inside the timed region"},
+          "cpu_baseline": {"value": cpu_value, "unit": "samples/s", "cores": cores, "kind": "port",
+                           "sample": f"{2 * cores} streams x 1 s through the TX oracle (Embedder.process, 1024-sample blocks), {cpu_s:.2f} s"},
+          "parity": {"sample": "8 streams x 3000 samples vs the TX oracle on the same payload bytes",
+                     "max_error_rel_to_block_peak": worst, "within_1e-4": bool(worst <= 1e-4)}}
+    if emit_line:
+        emit(line)
+    return line
+
+
+def _oracle_tx_one(i):
+    from oracle import tx_oracle as txo
+    tx = txo.Embedder(bench_key(i), txo.seeded_rand(i))
+    x = (0.1 * np.random.default_rng(i).standard_normal(48000)).astype(np.float32)
+    for b0 in range(0, 48000 - 1023, 1024):
+        tx.process(x[b0:b0 + 1024])
+    return 0
+
+
+def run_long(args, emit_line=True):
+    """configs[2]: one 1-hour 44.1 kHz synthetic recording, time-scaled x1.05, white noise at -15 dB SNR, through
+    WatermarkDetector.verify (resample to 48 kHz, 4-band scan with the global median/MAD threshold, <= 25 peaks per
+    band, full +-200 counter fallback, 400-try budget per band).  Parity and the CPU baseline on a 60 s cut of the same
+    recording (the oracle needs ~100 s for the whole hour: profiles/r02_config3_long_x105_oracle.json)."""
+    import torch
+    import __graft_entry__ as ge
+    ge.build()
+    from echoseal_b200 import rx_gpu, embedder, detector, _native as N
+    from test_gpu_rx import compare_with_oracle
+    dev = torch.device("cuda", 0)
+    hours = args.hours
+    n48 = int(hours * 3600 * 48000)
+    key = bench_key(2024)
+    g = torch.Generator(device=dev).manual_seed(2024)
+    host = 0.05 * torch.randn((1, n48), device=dev, generator=g)
+    wm = embedder.EmbedderBank([key]).process(host)
+    del host
+    a441 = rx_gpu.resample(rx_gpu.resample(wm, 20, 21), 48000, 44100)          # x21/20 slower, then to 44.1 kHz
+    del wm
+    p = float((a441.double() ** 2).mean())
+    a441 = a441 + torch.randn(a441.shape, device=dev, generator=g) * np.sqrt(p * 10 ** 1.5)
+    audio = a441[0].cpu().numpy()
+    del a441
+    rx = detector.WatermarkDetector(key, list_size=8)
+    for _ in range(max(1, min(args.warmup, 2))):
+        rx.session_nonce = None
+        ok = rx.verify(audio, 44100)
+    steps = max(1, min(args.steps, 3))
+    N.KERNEL_TIMES = {}
+    l0 = N.LAUNCHES
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    for _ in range(steps):
+        rx.session_nonce = None
+        ok = rx.verify(audio, 44100)                         # host buffer in, verdict out: this IS the end-to-end call
+    torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / steps
+    kt = {k: float(sum(a.elapsed_time(b) for a, b in v)) / steps for k, v in N.KERNEL_TIMES.items()}
+    N.KERNEL_TIMES = None
+    r = rx.last_result
+    scan_ms = sum(kt.get(k, 0.0) for k in ("resample", "bandpass", "ncc", "peaks_long", "peaks"))
+    peaks, kind = measured_peaks()
+    hbm = float(peaks.get("hbm_gbs", 6650.0))
+    gbs = audio.size * 4 / (scan_ms / 1e3) / 1e9 if scan_ms else None
+    # 60 s cut: GPU vs oracle on the same 48 kHz samples, and the oracle's speed
+    cut = np.ascontiguousarray(audio[: 60 * 44100])
+    rx2 = detector.WatermarkDetector(key, list_size=8)
+    ok2 = rx2.verify(cut, 44100)
+    a48 = rx2._resample(cut, 44100)
+    a48 = np.ascontiguousarray((a48.cpu().numpy() if isinstance(a48, torch.Tensor) else np.asarray(a48)).reshape(-1), dtype=np.float32)
+    t1 = time.perf_counter()
+    cmp_ = compare_with_oracle(rx2.last_result, a48, key)
+    cpu_s = time.perf_counter() - t1
+    parity = {"sample": "first 60 s of the recording", "verdict_equal": cmp_["oracle_verdict"] == bool(ok2),
+              "scl_decodes_equal": cmp_["oracle_scl_decodes"] == int(rx2.last_result.n_scl),
+              "sync_offsets_equal_bands": int(sum(b["sync_offsets_equal"] for b in cmp_["bands"])),
+              "attempt_lists_equal_bands": int(sum(b["attempts_equal"] for b in cmp_["bands"])),
+              "max_threshold_error": float(max(b["thr_err"] for b in cmp_["bands"])),
+              "full_hour": "profiles/r02_config3_long_x105_oracle.json"}
+    line = {"metric": "rx_audio_seconds_verified_per_second", "value": audio.size / 44100 / dt, "unit": "audio-s/s", "n_gpus": 1,
+            "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"configs[2]: one {hours} h 44.1 kHz recording, time-scale x21/20, -15 dB SNR, full +-200 "
+                                   "fallback search, host buffer in / verdict out",
+                       "samples_44k1": int(audio.size), "verdict": bool(ok), "scl_decodes": int(r.n_scl),
+                       "attempts_per_band": [len(a) for a in r.attempts],
+                       "l2": "667 MB of input and 5.8 GB of per-band intermediates exceed the 126 MB L2"},
+            "gpu_launches": (N.LAUNCHES - l0) // steps,
+            "kernel_ms_per_step": kt,
+            "roofline": {"kernel": "resample+bandpass+ncc+peaks_long", "bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s",
+                         "frac": (gbs / hbm) if gbs else None, "traffic": None,
+                         "note": "algorithmic bytes = 4 B per 44.1 kHz input sample; the fp64 y / corr round trips of the scan "
+                                 "kernels are what the time goes to (roofline_scan of the headline line)"},
+            "cpu_baseline": {"value": 60.0 / cpu_s, "unit": "audio-s/s", "cores": os.cpu_count() or 1, "kind": "port",
+                             "sample": f"first 60 s of the same recording through the oracle verify (scan single-threaded, SCL on all cores), {cpu_s:.1f} s"},
+            "parity": parity}
+    if emit_line:
+        emit(line)
+    return line
 
 
 def main():
@@ -380,8 +539,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--sub-batch", type=int, default=1000)
     ap.add_argument("--cpu-sample", type=int, default=0, help="clips for the cpu_baseline leg (0 = 2 x cores)")
-    ap.add_argument("--workload", default="rx", choices=["rx", "scl", "tx"],
-                    help="rx = configs[1] (the headline); scl = configs[3] microbench; tx = configs[4]")
+    ap.add_argument("--workload", default="rx", choices=["rx", "scl", "tx", "long"],
+                    help="rx = configs[1] (the headline); scl = configs[3] microbench; tx = configs[4]; long = configs[2]")
+    ap.add_argument("--hours", type=float, default=1.0)
+    ap.add_argument("--no-secondary", action="store_true",
+                    help="skip the secondary block (configs[2], [3], [4] lines inside the headline line at N=1)")
     ap.add_argument("--codewords", type=int, default=1_000_000)
     ap.add_argument("--streams", type=int, default=4096)
     args = ap.parse_args()
@@ -393,7 +555,7 @@ def main():
         return
     if args.workload != "rx":
         if rank == 0:
-            (run_scl if args.workload == "scl" else run_tx)(args)
+            {"scl": run_scl, "tx": run_tx, "long": run_long}[args.workload](args)
         return
 
     import torch
@@ -458,7 +620,7 @@ def main():
     assert (v == verdicts).all()
 
     # ---------------- timed: end to end from pinned host memory (H2D of every clip + D2H of verdicts)
-    e2e_steps = max(1, min(args.steps, 2))
+    e2e_steps = args.steps                                  # the same number of steps as the device-resident timing
     host_clips = torch.empty((args.clips, N_SAMPLES), dtype=torch.float32, pin_memory=True)
     host_clips.copy_(clips)
     host_np = host_clips                                    # pinned CPU tensor: verify_batch copies from it in place
@@ -503,6 +665,7 @@ def main():
     sm_mhz = float(peaks.get("sm_max_mhz", 1965.0))
     fp64_lane_rate = 148 * 64 * sm_mhz * 1e6            # DFMA lanes/s
     phi_walk, phi_exec = scl_phi_counts()
+    dram_per_cw, dram_src = scl_measured_traffic()
     kshare = {k: float(np.sum(v_)) for k, v_ in ktimes.items()}
     ksum = sum(kshare.values()) or 1.0
     scan_ms = sum(kshare.get(k, 0.0) for k in ("bandpass", "ncc", "peaks"))
@@ -537,17 +700,18 @@ def main():
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": {"kernel": "scl_list_kernel", "bound": "hbm", "achieved": achieved_gbs, "peak": hbm, "unit": "GB/s",
-                     "frac": achieved_gbs / hbm, "traffic": cw_per_launch * SCL_DRAM_BYTES_PER_CW, "peak_source": peak_kind,
+                     "frac": achieved_gbs / hbm, "traffic": (cw_per_launch * dram_per_cw) if dram_per_cw else None,
+                     "traffic_source": dram_src, "peak_source": peak_kind,
                      "note": "the SCL decoder is FP64-issue bound, not HBM bound; see roofline_issue"},
         "roofline_issue": {"kernel": "scl_list_kernel", "bound": "fp64_issue", "achieved": scl_cw_s, "unit": "codewords/s",
                            "avg_launch_ms": scl_avg_ms, "codewords_per_launch": cw_per_launch,
                            "node_updates_per_s": scl_cw_s * SCL_NODE_UPDATES_PER_CW,
-                           "stated_bound_cw_s": fp64_lane_rate / (phi_walk * 29),
-                           "frac": scl_cw_s / (fp64_lane_rate / (phi_walk * 29)),
+                           "stated_bound_cw_s": fp64_lane_rate / (phi_walk * PHI_FP64_INSTR),
+                           "frac": scl_cw_s / (fp64_lane_rate / (phi_walk * PHI_FP64_INSTR)),
                            "bound_def": f"148 SM x 64 FP64 lanes x sm_max_mhz / ({phi_walk:.0f} phi evaluations of the "
-                                        "leaf-by-leaf walk x 29 FP64 instr)",
+                                        f"leaf-by-leaf walk x {PHI_FP64_INSTR} FP64 instr)",
                            "phi_executed_per_cw": phi_exec,
-                           "fp64_pipe_frac_executed": scl_cw_s * phi_exec * 29 / fp64_lane_rate,
+                           "fp64_pipe_frac_executed": scl_cw_s * phi_exec * PHI_FP64_INSTR / fp64_lane_rate,
                            "note": "rate-0 node sums and the shared first half of each +/- pair cut the executed phi "
                                    "count below the walk's; frac is against the walk (algorithmic work), "
                                    "fp64_pipe_frac_executed against what the kernel really issues"},
@@ -566,6 +730,17 @@ def main():
                          "verdict_agreement": f"{agree_v}/{m}", "scl_attempt_count_agreement": f"{agree_n}/{m}"},
         "host_threads_per_rank": host_threads,
     }
+    if world == 1 and not args.no_secondary:
+        # the other BASELINE configs, each a full line of its own (metric, roofline, cpu_baseline on the same inputs, parity)
+        del clips, host_clips
+        torch.cuda.empty_cache()
+        sec = {}
+        for name, fn in (("configs[2]_long_recording", run_long), ("configs[3]_scl_microbench", run_scl), ("configs[4]_tx", run_tx)):
+            try:
+                sec[name] = fn(args, emit_line=False)
+            except Exception as e:                       # a secondary line must never cost the headline
+                sec[name] = {"error": f"{type(e).__name__}: {e}"}
+        line["secondary"] = sec
     emit(line)
     if world > 1:
         dist.destroy_process_group()

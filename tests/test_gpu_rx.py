@@ -382,6 +382,62 @@ def test_positive_path_matches_reference_golden(env):
             assert ok and not hard.any()                            # True, and not through the fast path
 
 
+def make_long_recording(torch, seconds: float, scale_num: int, scale_den: int, seed: int = 2024):
+    """configs[2] recipe at 48 kHz: watermarked Gaussian host, time-scaled by num/den, white noise at -15 dB SNR."""
+    from echoseal_b200 import rx_gpu, embedder
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    dev = torch.device("cuda", 0)
+    key = bench.bench_key(seed)
+    g = torch.Generator(device=dev).manual_seed(seed)
+    n48 = int(seconds * 48000 * scale_den / scale_num) + 4096
+    host = 0.05 * torch.randn((1, n48), device=dev, generator=g)
+    wm = embedder.EmbedderBank([key]).process(host)
+    stretched = rx_gpu.resample(wm, scale_den, scale_num)[:, : int(seconds * 48000)]
+    p = float((stretched.double() ** 2).mean())
+    noisy = stretched + torch.randn(stretched.shape, device=dev, generator=g) * np.sqrt(p * 10 ** 1.5)
+    return key, noisy[0].contiguous().cpu().numpy().astype(np.float32)
+
+
+def compare_with_oracle(res, audio48: np.ndarray, key: bytes):
+    """RxResult of WatermarkDetector.verify vs oracle.detector_oracle on the same 48 kHz samples
+    (rtwm/detector.py:44-152): threshold statistics, the <= 25 sync offsets per band, attempted (offset, counter)
+    lists, number of SCL decodes, verdict.  Returns a summary dict; asserts nothing."""
+    from oracle import detector_oracle as do
+    ok, det = do.verify(audio48, key, list_size=8, return_details=True)
+    out = {"oracle_verdict": bool(ok), "oracle_scl_decodes": int(det["n_scl"]), "bands": []}
+    for bi, band in enumerate(do.BAND_PLAN):
+        sc = do.scan_band(audio48, band)
+        got_pk = [int(p) for p in res.peaks[bi, :int(res.npeaks[bi])]]
+        out["bands"].append({
+            "band": bi, "corr_len": int(sc["corr"].size),
+            "med_err": abs(float(res.stats[bi, 0]) - sc["med"]), "mad_err": abs(float(res.stats[bi, 1]) - sc["mad"]),
+            "thr_err": abs(float(res.stats[bi, 2]) - sc["thr"]), "thr": sc["thr"],
+            "sync_offsets_equal": got_pk == sc["peaks"][:25], "npeaks": len(got_pk),
+            "attempts_equal": [(int(s_), int(c)) for s_, c in det["attempts"].get(bi, [])] == res.attempts[bi],
+            "attempts": len(res.attempts[bi])})
+    return out
+
+
+def test_long_recording_matches_oracle(env):
+    """configs[2] semantics on a recording long enough (correlation row >= 2^21 = rx_gpu.K3_LONG_MIN) that the
+    multi-CTA peak selection es_rx_peaks_long is what runs: 50 s at 48 kHz, time-scaled x1.05, -15 dB SNR.
+    Thresholds, the 25 sync offsets per band, attempt lists (400-try budget) and the verdict against the oracle."""
+    torch, rx_gpu, detector, clips, taps = env
+    key, audio = make_long_recording(torch, 50.0, 21, 20)
+    assert audio.size - 62 >= rx_gpu.K3_LONG_MIN
+    rx = detector.WatermarkDetector(key, list_size=8)
+    ok = rx.verify(audio, 48000)
+    r = rx.last_result
+    cmp_ = compare_with_oracle(r, audio, key)
+    print(cmp_)
+    assert ok == cmp_["oracle_verdict"] and r.n_scl == cmp_["oracle_scl_decodes"]
+    for b in cmp_["bands"]:
+        assert b["corr_len"] >= rx_gpu.K3_LONG_MIN
+        assert b["med_err"] < 1e-7 and b["mad_err"] < 1e-7 and b["thr_err"] < 1e-7
+        assert b["sync_offsets_equal"] and b["attempts_equal"]
+
+
 def test_full_size_batch_properties(env):
     """BASELINE configs[1] at full size (10 000 x 3 s clips, one key per clip): size-independent properties of
     the whole RX path.  (i) permutation equivariance: verifying the batch in another clip order and with another

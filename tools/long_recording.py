@@ -72,12 +72,25 @@ def main():
         if rank != 0:
             dist.destroy_process_group()
             return
+    oracle = None
+    if os.environ.get("ES_LONG_ORACLE") == "1":
+        # the CPU oracle on the SAME 48 kHz samples the detector scanned (its own resampler output; the resampler has
+        # its own parity test): thresholds, sync offsets, attempt lists, verdict at full size
+        sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+        from test_gpu_rx import compare_with_oracle
+        a48 = rx._resample(audio, 44100)
+        a48 = a48.cpu().numpy() if isinstance(a48, torch.Tensor) else np.asarray(a48)
+        t4 = time.perf_counter()
+        oracle = compare_with_oracle(r, np.ascontiguousarray(a48.reshape(-1), dtype=np.float32), key)
+        oracle["oracle_seconds"] = time.perf_counter() - t4
+        oracle["verdict_equal"] = oracle["oracle_verdict"] == bool(ok)
+        oracle["scl_decodes_equal"] = oracle["oracle_scl_decodes"] == int(r.n_scl)
     print(json.dumps({"workload": f"configs[2]: {hours} h 44.1 kHz recording, time-scale x{num}/{den}, -15 dB SNR",
                       "samples_44k1": int(audio.size), "verdict": bool(ok), "verify_seconds": dt,
                       "audio_seconds_per_second": audio.size / 44100 / dt, "scl_decodes": int(r.n_scl),
                       "attempts_per_band": [len(a) for a in r.attempts], "npeaks": [int(v) for v in r.npeaks],
                       "thr": [float(v) for v in r.stats[:, 2]], "kernel_ms": kt, "generate_seconds": t_gen,
-                      "band_sharded": sharded}))
+                      "band_sharded": sharded, "oracle_comparison": oracle}))
     if world > 1:
         dist.destroy_process_group()
 
