@@ -12,6 +12,7 @@
 #include <openssl/sha.h>
 #include <stdint.h>
 #include <string.h>
+#include <stdlib.h>
 #include <math.h>
 #include <atomic>
 #include <thread>
@@ -19,6 +20,7 @@
 #include <mutex>
 #include <condition_variable>
 #include <vector>
+#include <unistd.h>
 #include <algorithm>
 
 namespace {
@@ -95,6 +97,7 @@ struct KeyCtx {
     HmacKey band;                 // band key = the raw 32-byte master key (rtwm/detector.py:31)
     uint8_t hdr_pn[16];           // pn_bits(0, 128) packed
     std::vector<uint8_t> hop;     // band index per counter, grown on demand
+    EVP_CIPHER_CTX* aes_tpl = nullptr;   // AES-128-ECB context keyed with prng_sub: copied (not re-keyed) per use
 };
 
 struct Feeder {
@@ -107,7 +110,16 @@ struct Feeder {
 // detached and never torn down (no static-destruction order to get wrong); one parallel region runs at a time.
 class WorkPool {
 public:
-    static WorkPool& get() { static WorkPool* p = new WorkPool(); return *p; }
+    // one pool per PROCESS: after fork() the child owns no worker threads (only the forking thread survives), so a pool
+    // inherited from the parent would wait for helpers that do not exist; the child gets a fresh one (the old is leaked)
+    static WorkPool& get()
+    {
+        static std::atomic<WorkPool*> p{nullptr};
+        static std::atomic<long> owner{0};
+        const long me = (long)getpid();
+        if (owner.load() != me || !p.load()) { p.store(new WorkPool()); owner.store(me); }
+        return *p.load();
+    }
     void run(int n, int nthreads, const std::function<void(int)>& fn)
     {
         std::lock_guard<std::mutex> region(region_mu_);
@@ -182,6 +194,9 @@ struct AesEcb {
         EVP_EncryptInit_ex(ctx, cipher_aes_ecb(), nullptr, key, nullptr);
         EVP_CIPHER_CTX_set_padding(ctx, 0);
     }
+    // a context that takes its key schedule from a keyed template: EVP_CIPHER_CTX_copy instead of a key expansion
+    AesEcb() { ctx = EVP_CIPHER_CTX_new(); }
+    void rekey_from(const EVP_CIPHER_CTX* tpl) { EVP_CIPHER_CTX_copy(ctx, tpl); }
     ~AesEcb() { EVP_CIPHER_CTX_free(ctx); }
     void pn(uint64_t ctr, uint8_t out[PN_BYTES])
     {
@@ -220,6 +235,10 @@ static void derive_key(const uint8_t key32[32], KeyCtx& k)
     aes.pn(0, pn);
     memcpy(k.hdr_pn, pn, 16);
     k.hop.clear();
+    if (k.aes_tpl) EVP_CIPHER_CTX_free(k.aes_tpl);
+    k.aes_tpl = EVP_CIPHER_CTX_new();
+    EVP_EncryptInit_ex(k.aes_tpl, cipher_aes_ecb(), nullptr, k.prng_sub, nullptr);
+    EVP_CIPHER_CTX_set_padding(k.aes_tpl, 0);
 }
 
 static void grow_hop(KeyCtx& k, size_t hi)
@@ -270,12 +289,25 @@ void* es_host_keys_new(const uint8_t* keys /*[nkeys][32]*/, int nkeys, int nthre
 {
     Feeder* f = new Feeder();
     f->keys.resize((size_t)std::max(0, nkeys));
-    f->nthreads = nthreads > 0 ? nthreads : (int)std::max(1u, std::thread::hardware_concurrency());
+    if (nthreads <= 0) {
+        // default: the host cores divided among the ranks of this node (torchrun exports LOCAL_WORLD_SIZE), so that N
+        // ranks on one box do not each start a full set of workers
+        int ranks = 1;
+        if (const char* e = getenv("LOCAL_WORLD_SIZE")) ranks = std::max(1, atoi(e));
+        nthreads = (int)std::max(1u, std::thread::hardware_concurrency() / (unsigned)ranks);
+    }
+    f->nthreads = nthreads;
     parallel_for(nkeys, f->nthreads, [&](int i) { derive_key(keys + 32 * (size_t)i, f->keys[(size_t)i]); });
     return f;
 }
 
-void es_host_keys_free(void* h) { delete (Feeder*)h; }
+void es_host_keys_free(void* h)
+{
+    Feeder* f = (Feeder*)h;
+    if (!f) return;
+    for (auto& k : f->keys) if (k.aes_tpl) EVP_CIPHER_CTX_free(k.aes_tpl);
+    delete f;
+}
 
 int es_host_threads(void* h) { return ((Feeder*)h)->nthreads; }
 
@@ -461,18 +493,20 @@ int es_host_tx_prepare(void* h, const int32_t* key_idx, const uint32_t* ctr, con
     const int nchunks = (F + chunk - 1) / chunk;
     parallel_for(nchunks, f->nthreads, [&](int cidx) {
         EVP_CIPHER_CTX* ctx = EVP_CIPHER_CTX_new();
+        AesEcb aes;                                   // one AES context per chunk of frames, keyed by copy per frame
+        int last_k = -1;
         const int i1 = std::min(F, (cidx + 1) * chunk);
         for (int i = cidx * chunk; i < i1; ++i) {
             const int kidx = key_idx ? key_idx[i] : 0;
             if (kidx < 0 || (size_t)kidx >= f->keys.size()) { bad = 1; continue; }
             const KeyCtx& k = f->keys[(size_t)kidx];
+            if (kidx != last_k) { aes.rekey_from(k.aes_tpl); last_k = kidx; }
             uint8_t meta[27];
             memcpy(meta, "ESAL", 4);
             meta[4] = (uint8_t)(ctr[i] >> 24); meta[5] = (uint8_t)(ctr[i] >> 16); meta[6] = (uint8_t)(ctr[i] >> 8); meta[7] = (uint8_t)ctr[i];
             memcpy(meta + 8, session_nonce + 8 * (size_t)i, 8);
             memcpy(meta + 16, rnd + 23 * (size_t)i, 11);
             if (!aead_seal(ctx, k.aead_key, rnd + 23 * (size_t)i + 11, meta, payload + 55 * (size_t)i)) bad = 1;
-            AesEcb aes(k.prng_sub);
             aes.pn((uint64_t)ctr[i], pn + (size_t)PN_BYTES * (size_t)i);
             memcpy(hdr_pn + 16 * (size_t)i, k.hdr_pn, 16);
             uint8_t msg[4] = {meta[4], meta[5], meta[6], meta[7]}, d[32];

@@ -30,7 +30,16 @@ __constant__ double c_bp_a[NBANDS][9];
 __constant__ double c_tpl[NBANDS][PRE_L];
 __constant__ float c_mf[NBANDS][MAXH];
 __constant__ int c_mf_len[NBANDS];
-static int g_rx_ready = 0;
+// per-device: what the device's constant tables hold (content hash) and which kernels have their attributes set
+struct RxDev { int ready = 0; bool oddz = false; unsigned long long sig = 0; int cfg[8] = {0}; };
+static RxDev g_rxdev[ES_MAX_DEVICES];
+#define g_rx_ready (g_rxdev[current_device()].ready)
+static unsigned long long fnv1a(unsigned long long h, const void* p, size_t n)
+{
+    const unsigned char* b = (const unsigned char*)p;
+    for (size_t i = 0; i < n; ++i) { h ^= b[i]; h *= 1099511628211ull; }
+    return h;
+}
 
 // ---------------------------------------------------------------------------------------------
 // K1: band-pass.  One LANE per (clip, chunk), all four bands: direct-form II transposed, the operation order
@@ -51,7 +60,7 @@ struct BpWarpShared {
     float xin[2][32][BP_STEP + 1];
     double yout[NBANDS][32][9];             // half a step (8 samples) of the four bands
 };
-static bool g_bp_oddz = false;
+#define g_bp_oddz (g_rxdev[current_device()].oddz)
 
 template <bool ODDZ>
 __global__ void __launch_bounds__(BP_WARPS * 32, BP_MIN_CTAS) bandpass_kernel(const float* __restrict__ x, int nclips, int n,
@@ -1442,6 +1451,16 @@ int es_rx_set_filters(const double* bp_b /*[4][9]*/, const double* bp_a /*[4][9]
 {
     for (int b = 0; b < NBANDS; ++b)
         if (mf_len[b] < 1 || mf_len[b] > MAXH) { set_error("es_rx_set_filters: mf_len[%d]=%d out of range", b, mf_len[b]); return ES_EINVAL; }
+    RxDev& RD = g_rxdev[current_device()];
+    unsigned long long sig = 1469598103934665603ull;
+    sig = fnv1a(sig, bp_b, sizeof(double) * NBANDS * 9); sig = fnv1a(sig, bp_a, sizeof(double) * NBANDS * 9);
+    sig = fnv1a(sig, tpl, sizeof(double) * NBANDS * PRE_L); sig = fnv1a(sig, mf, sizeof(float) * NBANDS * MAXH);
+    sig = fnv1a(sig, mf_len, sizeof(int) * NBANDS);
+    if (RD.ready) {
+        if (RD.sig == sig) return ES_OK;                 // this device already holds exactly these tables: nothing to upload
+        ES_CUDA_OK(cudaDeviceSynchronize());             // different filters / taps: nothing in flight may still read the old ones
+    }
+    RD.sig = sig;
     ES_CUDA_OK(cudaMemcpyToSymbol(c_bp_b, bp_b, sizeof(double) * NBANDS * 9));
     ES_CUDA_OK(cudaMemcpyToSymbol(c_bp_a, bp_a, sizeof(double) * NBANDS * 9));
     ES_CUDA_OK(cudaMemcpyToSymbol(c_tpl, tpl, sizeof(double) * NBANDS * PRE_L));
@@ -1480,7 +1499,7 @@ int es_rx_ncc(const double* y, int nclips, int n, double* corr, void* stream)
     if (nclips <= 0 || nc <= 0) return ES_OK;
     const int ntiles = (nc + NCC_TILE - 1) / NCC_TILE;
     const size_t smem = 2 * (size_t)(ncc_pad(NCC_IN) + 1) * sizeof(double);
-    static int configured = 0;
+    int& configured = g_rxdev[current_device()].cfg[0];
     if (!configured) {
         ES_CUDA_OK(cudaFuncSetAttribute(ncc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = 1;
@@ -1497,7 +1516,7 @@ void es_rx_peaks_force_general(int on) { g_peaks_general = on ? 1 : 0; }
 int es_rx_peaks(const double* corr, int nclips, int nc, int32_t* peaks, int32_t* npeaks, double* stats, void* stream)
 {
     if (nclips <= 0) return ES_OK;
-    static int configured = 0;
+    int& configured = g_rxdev[current_device()].cfg[1];
     if (!configured) {
         ES_CUDA_OK(cudaFuncSetAttribute(peaks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PeakShared)));
         ES_CUDA_OK(cudaFuncSetAttribute(peaks2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PkUnion)));

@@ -212,6 +212,9 @@ constexpr int SCL_S = 6;   // first LLR-tree level kept in shared memory
 #define ES_SCL_TMA_F ES_SCL_TMA
 #endif
 constexpr int RING_STAGES = 2;      // the passes toggle between two stages (st ^= 1)
+#ifndef ES_SCL_RING_ALIAS
+#define ES_SCL_RING_ALIAS 1  // stage 1 lives in the rows of level 7 (dead while any DRAM-level pass runs: those rewrite levels <= 6,
+#endif                       // and levels 7..8 are recomputed after them); buys the shared memory for 20 warps per SM
 constexpr int RING_STAGE_ROWS = 8;
 constexpr int RING_STAGE_BYTES = RING_STAGE_ROWS * 256;
 
@@ -227,7 +230,8 @@ template <int S> struct SclLayout {
     static constexpr int BROWS_G = 24;                                   // beta words of levels 1..2 in global memory
     static constexpr int SNAP_BYTES = 32 * 32;                           // per-lane (metric, bptr, ord|active) + prune margin at bit 512
     static constexpr int ABYTES = (AROWS * 256 > 32 * 128) ? AROWS * 256 : 32 * 128;   // alpha rows; also holds the root partial sums
-    static constexpr int RING_BYTES = RING_STAGES * RING_STAGE_BYTES;     // TMA staging ring of the DRAM-level passes
+    static constexpr int RING_BYTES = (ES_SCL_RING_ALIAS ? 1 : RING_STAGES) * RING_STAGE_BYTES;   // TMA staging ring of the DRAM-level passes
+    static constexpr int L7_OFF = ((1 << (11 - S)) - (1 << 4)) * 256;     // rows of level 7 inside the alpha area (8 rows = one stage)
     static constexpr int RING_OFF = ABYTES + BROWS_S * 128 + SNAP_BYTES;
     static constexpr int BAR_OFF = RING_OFF + RING_BYTES;                 // one 8-byte mbarrier per stage
     static constexpr int WARP_BYTES = BAR_OFF + 16;
@@ -271,7 +275,14 @@ struct Lane {
     __device__ __forceinline__ double* ga() const { return gw + gbase(); }      // global alpha rows (+gbase)
     __device__ __forceinline__ double* g0() const { return gw + SclLY::G_ROWS * 32 + (lane >> 3); }   // level-0 copy [k][4]
     __device__ __forceinline__ uint32_t tab() const { return smem_base(); }     // phi tables
-    __device__ __forceinline__ uint32_t ring() const { return wsm + SclLY::RING_OFF; }   // stage st at + st * RING_STAGE_BYTES
+    __device__ __forceinline__ uint32_t ring(int st) const                      // shared-window address of stage st
+    {
+#if ES_SCL_RING_ALIAS
+        return wsm + (st ? (uint32_t)SclLY::L7_OFF : (uint32_t)SclLY::RING_OFF);
+#else
+        return wsm + SclLY::RING_OFF + (uint32_t)st * RING_STAGE_BYTES;
+#endif
+    }
     __device__ __forceinline__ uint32_t rbar() const { return wsm + SclLY::BAR_OFF; }    // its mbarrier at + 8 * st
 };
 
@@ -384,7 +395,7 @@ __device__ __forceinline__ void ring_issue(const Lane& L, int st, const void* sr
 {
     const uint32_t bar = L.rbar() + 8u * st;
     mbar_expect_tx(bar, bytes);
-    bulk_g2s(L.ring() + (uint32_t)st * RING_STAGE_BYTES, src, bytes, bar);
+    bulk_g2s(L.ring(st), src, bytes, bar);
 }
 
 // All lanes hold the eight values of the current stage in registers: the stage may be refilled.  A plain
@@ -428,7 +439,7 @@ __device__ __forceinline__ size_t pass_wait(Lane& L, const PassSrc& ps, int c, i
     if (TMA) {
         mbar_wait(L.rbar() + 8u * st, (L.rphase >> st) & 1u);
         L.rphase ^= 1u << st;
-        return (size_t)(L.ring() + (uint32_t)st * RING_STAGE_BYTES + ps.col);
+        return (size_t)(L.ring(st) + ps.col);
     }
     return reinterpret_cast<size_t>(ps.base + (size_t)c * 8u * ps.rs + ps.col);
 }

@@ -15,7 +15,8 @@ constexpr int TX_SYM_WORDS = 38;          // 1216 sign bits per frame
 // this translation unit's copy of the polar code layout (filled by es_polar_set_code via tx_set_code)
 __device__ uint16_t d_datapos[1024];     // global memory: read with per-lane indices (a constant-bank read would serialise)
 __constant__ int c_K;
-static int g_tx_code_ready = 0;
+static int g_tx_code_ready_dev[ES_MAX_DEVICES] = {0};
+#define g_tx_code_ready (g_tx_code_ready_dev[current_device()])
 
 int tx_set_code(const uint16_t* pos, int K)
 {
@@ -28,7 +29,9 @@ int tx_set_code(const uint16_t* pos, int K)
 __constant__ double c_tx_b[4][9];
 __constant__ double c_tx_a[4][9];
 __constant__ uint32_t c_pre_words[2];     // 63 preamble sign bits (bit i = chip i is +1)
-static int g_tx_ready = 0;
+struct TxDev { int ready = 0; unsigned long long sig = 0; };
+static TxDev g_txdev[ES_MAX_DEVICES];
+#define g_tx_ready (g_txdev[current_device()].ready)
 
 __device__ __forceinline__ uint32_t tx_xform_word(uint32_t x)
 {
@@ -223,6 +226,18 @@ int es_tx_set_filters(const double* bp_b /*[4][9]*/, const double* bp_a /*[4][9]
 {
     uint32_t w[2] = {0, 0};
     for (int i = 0; i < TX_PRE; ++i) if (preamble_bits[i]) w[i >> 5] |= 1u << (i & 31);
+    TxDev& TD = g_txdev[current_device()];
+    unsigned long long sig = 1469598103934665603ull;
+    {
+        const unsigned char* parts[3] = {(const unsigned char*)bp_b, (const unsigned char*)bp_a, (const unsigned char*)w};
+        const size_t lens[3] = {sizeof(double) * 36, sizeof(double) * 36, sizeof(w)};
+        for (int p = 0; p < 3; ++p) for (size_t i = 0; i < lens[p]; ++i) { sig ^= parts[p][i]; sig *= 1099511628211ull; }
+    }
+    if (TD.ready) {
+        if (TD.sig == sig) return ES_OK;
+        ES_CUDA_OK(cudaDeviceSynchronize());
+    }
+    TD.sig = sig;
     ES_CUDA_OK(cudaMemcpyToSymbol(c_tx_b, bp_b, sizeof(double) * 36));
     ES_CUDA_OK(cudaMemcpyToSymbol(c_tx_a, bp_a, sizeof(double) * 36));
     ES_CUDA_OK(cudaMemcpyToSymbol(c_pre_words, w, sizeof(w)));

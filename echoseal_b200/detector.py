@@ -8,8 +8,8 @@ and the ChaCha20-Poly1305 tag check stay on the host as producers / consumers of
 inputs / outputs (BASELINE.json north_star).  There is no CPU fallback.
 
 Deviations from the reference, on purpose:
-  * `list_size` defaults to 8 (north_star fixes SCL-8; the reference class default of 256 is
-    unusable — 33 s per failing decode) and must be <= 8.
+  * `list_size` defaults to 8 (north_star fixes SCL-8; the reference class default of 256 costs 33 s per
+    failing decode); larger values are accepted and served with 8 paths (polar_gpu.effective_list_size).
   * nothing is printed.
 """
 from __future__ import annotations
@@ -144,8 +144,7 @@ def verify_batch(keys, audio, *, fs_target: int = 48_000, list_size: int = 8, mf
     while the GPU decodes k."""
     if not torch.cuda.is_available():
         raise RuntimeError("echoseal_b200 needs a CUDA device (no CPU fallback)")
-    if not (1 <= int(list_size) <= 8):
-        raise ValueError("list_size must be in 1..8 on the B200 path (north_star: SCL-8)")
+    list_size = polar_gpu.effective_list_size(list_size)
     is_tensor = isinstance(audio, torch.Tensor) and audio.is_cuda
     host_audio = None
     if not is_tensor:
@@ -330,9 +329,7 @@ class WatermarkDetector:
         self.session_nonce: bytes | None = None
         self._band_key = getattr(self.sec, "band_key", key32)      # rtwm/detector.py:31 (quirk 9)
         self._mf_cache = {}
-        self._list_size = int(list_size)
-        if not (1 <= self._list_size <= 8):
-            raise ValueError("list_size must be in 1..8 on the B200 path (north_star: SCL-8)")
+        self._list_size = polar_gpu.effective_list_size(list_size)     # ValueError below 1; above 8: SCL-8 and a warning
         self._aead = getattr(self.sec, "_aead", None)
         self._pre_sy = 2.0 * PRE_BITS.astype(np.float32) - 1.0
         self._hdr_pn_bits = self.sec.pn_bits(0, HDR_L)

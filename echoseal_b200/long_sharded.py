@@ -17,7 +17,14 @@ them with torch.distributed (NCCL), `run_simulated` runs W virtual ranks in lock
 
 Filtering a segment from zero state 768 samples early differs from filtering the whole recording by < 4e-13 of the
 peak (the same bound as between the chunks of K1 on one GPU), so statistics agree to ~1e-12 and the sync offsets
-are equal unless a correlation value sits within that distance of the threshold or of a neighbour."""
+are equal unless a correlation value sits within that distance of the threshold or of a neighbour.
+
+When to use it: NOT for speed at BASELINE sizes.  A whole hour of audio is one 0.09-0.12 s pass on one B200
+(bench.py --workload long); on 2 GPUs the time split took 0.49 s (profiles/r01_config3_long_x105_2gpu_sharded.json),
+dominated by the host-side phase sequencing and by every rank resampling the recording.  It exists for recordings
+that do not fit one GPU's memory (the four fp64 band signals cost 64 B per 48 kHz sample: ~47 min of audio per
+10 GB) and as the one place of the path with a real exchange step.  Recordings shorter than one frame return False
+without touching the ranks."""
 from __future__ import annotations
 import ctypes as C
 import numpy as np
@@ -171,6 +178,10 @@ def run_simulated(det, signal48: np.ndarray, world: int, dev=None):
     """W virtual ranks in lock-step on one GPU.  Returns (verdict, per-rank result dicts)."""
     dev = dev if dev is not None else torch.device("cuda", torch.cuda.current_device())
     signal48 = np.asarray(signal48, np.float32).reshape(-1)
+    if signal48.size < 63 + 1215:
+        # shorter than one frame after the template: the reference returns False without scanning (rtwm/detector.py:72-73,
+        # :112-113); the rank programs need at least one correlation index per rank
+        return False, [dict(verdict=False) for _ in range(world)]
     outs = [dict() for _ in range(world)]
     gens = [_rank_program(det, signal48, r, world, dev, outs[r]) for r in range(world)]
     reqs = [next(g) for g in gens]
@@ -206,6 +217,8 @@ def verify_recording_time_sharded(det, audio, fs_in: int, device=None) -> bool:
     if isinstance(signal, torch.Tensor):
         signal = signal.detach().cpu().numpy()
     signal = np.asarray(signal, np.float32).reshape(-1)
+    if signal.size < 63 + 1215:
+        return False                                  # every rank sees the same audio and returns the same answer
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return run_simulated(det, signal, 1, dev)[0]
     world, rank = dist.get_world_size(), dist.get_rank()

@@ -1,7 +1,7 @@
 """B200-native drop-in for rtwm/polar_fast.py and rtwm/fastpolar.PolarCode: same names, arguments,
 return types and error behaviour (rtwm/polar_fast.py:26-87, rtwm/fastpolar.py:193-359); the arithmetic
 runs in the sm_100a kernels (es_polar_encode / es_scl_hard / es_scl_list).  `decode_batch` is additive.
-list_size must be <= 8 on this path (north_star: SCL-8)."""
+list_size above 8 is served with SCL-8 (north_star) and a one-time warning (polar_gpu.effective_list_size)."""
 from __future__ import annotations
 from typing import Callable, Optional, Tuple
 import numpy as np
@@ -33,8 +33,7 @@ def _check_code(N: int, K: int, list_size: int, crc_size: int):
         raise ValueError(f"Q_Nmax must have {N} entries (has 1024)")
     if crc_size != 8 or K % 8:
         raise ValueError("the B200 path implements CRC-8 and byte-aligned K only")
-    if list_size > 8:
-        raise ValueError("list_size must be <= 8 on the B200 path (north_star: SCL-8)")
+    return polar_gpu.effective_list_size(list_size)
 
 
 def select(hard_payload, hard_crc, path_payload, path_crc, npaths, validator=None):
@@ -68,7 +67,7 @@ def select(hard_payload, hard_crc, path_payload, path_crc, npaths, validator=Non
 def decode_batch(llr, *, K: int = K_DEFAULT, list_size: int = 8, skip_list_on_hard_crc: bool = True):
     """llr float32[n,1024] (numpy or CUDA tensor) -> list of (payload bytes, ok) with validator=None
     semantics (hard-decision fast path first, rtwm/fastpolar.py:269-276)."""
-    _check_code(1024, K, list_size, 8)
+    list_size = _check_code(1024, K, list_size, 8)
     dev = _dev()
     t = llr if isinstance(llr, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(llr, np.float32))
     t = t.to(device=dev, dtype=torch.float32).contiguous()
@@ -85,7 +84,7 @@ def decode_batch(llr, *, K: int = K_DEFAULT, list_size: int = 8, skip_list_on_ha
 def encode(payload: bytes, *, N: int = N_DEFAULT, K: int = K_DEFAULT, list_size: int = 8, crc_size: int = 8,
            debug: bool = False) -> np.ndarray:
     """rtwm/polar_fast.py:26-53 -> uint8[1024] code bits"""
-    _check_code(N, K, list_size, crc_size)
+    list_size = _check_code(N, K, list_size, crc_size)
     info_bytes = (K - crc_size) // 8
     if len(payload) != info_bytes:
         raise ValueError(f"payload must be {info_bytes} bytes (got {len(payload)})")
@@ -98,7 +97,7 @@ def decode(llr: np.ndarray, *, N: int = N_DEFAULT, K: int = K_DEFAULT, list_size
            return_ok: bool = False, debug: bool = False,
            validator: Optional[Callable[[bytes], bool]] = None) -> Optional[bytes] | Tuple[bytes, bool]:
     """rtwm/polar_fast.py:55-87"""
-    _check_code(N, K, list_size, crc_size)
+    list_size = _check_code(N, K, list_size, crc_size)
     llr = np.asarray(llr)
     if llr.ndim != 1 or llr.size != N:
         raise ValueError(f"LLR length {llr.size} != N {N}")
@@ -120,7 +119,7 @@ class PolarCode:
     """rtwm/fastpolar.py:193-359: encode(info_bits) -> uint8[N]; decode(llr, validator) -> (uint8[K-8], ok)."""
 
     def __init__(self, N: int, K: int, list_size: int = 8, crc_size: int = 8, debug: bool = False):
-        _check_code(N, K, list_size, crc_size)
+        list_size = _check_code(N, K, list_size, crc_size)
         self.N, self.K, self.list_size, self.crc_size, self.debug = N, K, list_size, crc_size, debug
         from .polar_tables import frozen_mask, data_positions
         self.frozen = frozen_mask(N, K)

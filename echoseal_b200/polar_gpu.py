@@ -11,6 +11,27 @@ from .polar_tables import frozen_mask
 
 _code_key = None
 _scratch = {}
+MAX_LIST = 8
+_warned_list = set()
+
+
+def effective_list_size(list_size: int) -> int:
+    """The list the kernels run: min(list_size, 8).  The reference accepts any list_size >= 1 (its constructor default is
+    256, rtwm/detector.py:27; its own quick test uses 32); the B200 path implements SCL-8 (north_star), so a larger
+    request is served with 8 paths and a one-time warning instead of an error.  Verdict parity with the reference at
+    list_size > 8 therefore holds for every frame SCL-8 recovers; a frame only a longer list would recover comes
+    back False / None here (INTEGRATION.md)."""
+    L = int(list_size)
+    if L < 1:
+        raise ValueError("list_size must be >= 1")
+    if L > MAX_LIST:
+        if L not in _warned_list:
+            import warnings
+            warnings.warn(f"list_size={L}: the B200 path decodes with SCL-{MAX_LIST}; larger lists are clamped", RuntimeWarning,
+                          stacklevel=3)
+            _warned_list.add(L)
+        return MAX_LIST
+    return L
 
 
 def set_code(N_: int = 1024, K: int = 448):
