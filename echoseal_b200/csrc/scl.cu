@@ -234,7 +234,8 @@ template <int S> struct SclLayout {
     static constexpr int L7_OFF = ((1 << (11 - S)) - (1 << 4)) * 256;     // rows of level 7 inside the alpha area (8 rows = one stage)
     static constexpr int RING_OFF = ABYTES + BROWS_S * 128 + SNAP_BYTES;
     static constexpr int BAR_OFF = RING_OFF + RING_BYTES;                 // one 8-byte mbarrier per stage
-    static constexpr int WARP_BYTES = BAR_OFF + 16;
+    static constexpr int STASH_OFF = BAR_OFF + 16;                        // 48 bytes per lane: decode state parked across the LLR update
+    static constexpr int WARP_BYTES = STASH_OFF + 32 * 48;
     static constexpr int TAB_BYTES = PHI_TAB_DOUBLES * 8;
     static constexpr size_t G_ROWS = 1024 - (1 << (11 - S));           // global alpha rows, levels 1..S-1
     static constexpr size_t G_DOUBLES = G_ROWS * 32 + 1024 * 4 + BROWS_G * 16;   // + level-0 copy [1024][4] + beta rows
@@ -321,27 +322,38 @@ template <int S> __device__ __forceinline__ double* elem_ptr(const Lane& L, int 
     return L.ga() + (lvl_row0(lv) + ipos(lv, k)) * 32 + slot;
 }
 
-// f-combine of a whole shared-memory node: dst[k*32] = f(a[k*32], b[k*32]), k < count, count even.
-// Two elements per trip = four independent phi chains.
-__device__ __noinline__ void f_loop(const double* a, const double* b, double* dst, int count, uint32_t tab)
+// f-combine of a whole shared-memory node (32-bit shared-window addresses, 256-byte element pitch):
+// dst[k] = f(a[k], b[k]), k < count, count even.  Two elements per trip = four independent phi chains.
+__device__ __forceinline__ void sts_f64(uint32_t addr, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory"); }
+__device__ __noinline__ void f_loop(uint32_t a, uint32_t b, uint32_t dst, int count, uint32_t tab)
 {
 #pragma unroll 1
     for (int k = 0; k + 2 <= count; k += 2) {
-        const double a0 = a[k * 32], b0 = b[k * 32], a1 = a[(k + 1) * 32], b1 = b[(k + 1) * 32];
+        const double a0 = lds_f64(a + k * 256), b0 = lds_f64(b + k * 256), a1 = lds_f64(a + k * 256 + 256), b1 = lds_f64(b + k * 256 + 256);
         double r0, r1;
         fcomb2(a0, b0, a1, b1, tab, r0, r1);
-        dst[k * 32] = r0;
-        dst[(k + 1) * 32] = r1;
+        sts_f64(dst + k * 256, r0);
+        sts_f64(dst + k * 256 + 256, r1);
     }
 }
 
+// shared-window address of element 0 of the shared-memory level lv (>= S) in `slot`
+template <int S> __device__ __forceinline__ uint32_t slvl_a(const Lane& L, int lv, int slot)
+{
+    return L.wsm + (uint32_t)(((1 << (11 - S)) - (1 << (11 - lv))) * 256 + (L.gbase() + slot) * 8);
+}
+
+// f node of the shared-memory level lv (S < lv <= 8) from level lv-1.  coop (bit 0): one path, slot 0, one element
+// pair per lane; otherwise the lane's own slot, the whole node.
 template <int S>
-__device__ __forceinline__ void f_level(Lane& L, int lv)   // S < lv <= 8: parent (level lv-1 >= S) in own slot
+__device__ __forceinline__ void f_level(Lane& L, int lv, bool coop)
 {
     const int s = 1 << (10 - lv);
-    const double* src = slvl<S>(L, lv - 1, L.p());
-    f_loop(src, src + s * 32, slvl<S>(L, lv, L.p()), s, L.tab());
-    L.ptr = (L.ptr & ~(7u << (3 * (lv - 1)))) | ((uint32_t)L.p() << (3 * (lv - 1)));
+    const int slot = coop ? 0 : L.p();
+    const uint32_t off = coop ? (uint32_t)(2 * L.p() * 256) : 0u;
+    const uint32_t src = slvl_a<S>(L, lv - 1, slot) + off;
+    f_loop(src, src + s * 256, slvl_a<S>(L, lv, slot) + off, coop ? ((2 * L.p() < s) ? 2 : 0) : s, L.tab());
+    L.ptr = (L.ptr & ~(7u << (3 * (lv - 1)))) | ((uint32_t)slot << (3 * (lv - 1)));
 }
 
 // g over one shared-memory level l0 (S..8): dst[k] = par[k+s] +- par[k], sign from the left-child partial sums in the
@@ -610,44 +622,36 @@ __device__ __forceinline__ void pass_f(Lane& L, int lv, bool coop)
     L.ptr = (L.ptr & ~(7u << (3 * (lv - 1)))) | ((uint32_t)(coop ? 0 : L.p()) << (3 * (lv - 1)));
 }
 
-// bit 0: only one path exists; the 8 lanes of the codeword share the work, everything goes to slot 0
-template <int S>
-__device__ __forceinline__ void spine(Lane& L)
-{
-#pragma unroll 1
-    for (int lv = 1; lv <= S; ++lv) {
-        pass_f<S>(L, lv, true);
-        __syncwarp();
-    }
-#pragma unroll 1
-    for (int lv = S + 1; lv <= 8; ++lv) {     // 8 and 4 elements: one pair per lane
-        const int s = 1 << (10 - lv);
-        const double* src = slvl<S>(L, lv - 1, 0) + 2 * L.p() * 32;
-        f_loop(src, src + s * 32, slvl<S>(L, lv, 0) + 2 * L.p() * 32, (2 * L.p() < s) ? 2 : 0, L.tab());
-        __syncwarp();
-    }
-    L.ptr = 0;
-}
-
-// levels 1..8 for the quad starting at bit i (i % 4 == 0, i > 0): one g node, then f nodes down to level `last`.
+// levels 1..8 for the quad starting at bit i (i % 4 == 0): one g node, then f nodes down to level `last`.
+// Bit 0 has no g node and only one path: the 8 lanes of the codeword share the f chain of slot 0 (coop).
 // Levels 9 and 10 never touch memory: the quad routine in the kernel keeps them in registers.
 template <int S>
 __device__ __forceinline__ void llr_update8(Lane& L, int i, int last)   // l0 <= last <= 8
 {
-    const int l0 = 11 - __ffs(i);    // <= 8
-    int lv;
-    if (l0 < S) {
-        const bool fuse = last > l0;
-        pass_gf<S>(L, l0, fuse);
-        lv = l0 + (fuse ? 2 : 1);
-#pragma unroll 1
-        for (; lv <= last && lv <= S; ++lv) pass_f<S>(L, lv, false);
-    } else {
-        g_level<S>(L, l0);
-        lv = l0 + 1;
+    const bool coop = (i == 0);
+    int lv = 1;
+    if (!coop) {
+        const int l0 = 11 - __ffs(i);    // <= 8
+        if (l0 < S) {
+            const bool fuse = last > l0;
+            pass_gf<S>(L, l0, fuse);
+            lv = l0 + (fuse ? 2 : 1);
+        } else {
+            g_level<S>(L, l0);
+            lv = l0 + 1;
+        }
     }
 #pragma unroll 1
-    for (; lv <= last; ++lv) f_level<S>(L, lv);
+    for (; lv <= last && lv <= S; ++lv) {
+        pass_f<S>(L, lv, coop);
+        if (coop) __syncwarp();
+    }
+#pragma unroll 1
+    for (; lv <= last; ++lv) {
+        f_level<S>(L, lv, coop);
+        if (coop) __syncwarp();
+    }
+    if (coop) L.ptr = 0;
 }
 
 // Rate-0 node: all `count` (multiple of 4) bits below the node are frozen, so every path's decisions there
@@ -883,7 +887,7 @@ __global__ void __maxnreg__(ES_SCL_MAXNREG) scl_list_kernel(SclParams P)
 #pragma unroll 1
     for (int grp = blockIdx.x * W + warp; grp < ((P.nunits + 3) >> 2); grp += gridDim.x * W) {
         const int j = grp * 4 + (L.lane >> 3);
-        const bool valid = j < P.nunits;
+        bool valid = j < P.nunits;
         const int jj = valid ? j : (P.nunits - 1);
         int w = P.pair ? 2 * jj : (P.index ? P.index[jj] : jj);
         {   // level 0: widen this warp's 4 rows to double, [position][4] (quarter-interleaved like the levels below).  Always +row: f(-a,-b) = f(a,b), so the first
@@ -901,8 +905,6 @@ __global__ void __maxnreg__(ES_SCL_MAXNREG) scl_list_kernel(SclParams P)
         __syncwarp();
 
         int qfirst = 0;
-        spine<S>(L);              // bit 0 (quad 0 is never a rate-0 node)
-        __syncwarp();
 #pragma unroll 1
         for (int pass = 0; ; ++pass) {
 #pragma unroll 1
@@ -922,8 +924,29 @@ __global__ void __maxnreg__(ES_SCL_MAXNREG) scl_list_kernel(SclParams P)
             // rate-0 nodes: the first quad adds the whole node's penalty, every quad feeds zeros upward
             const int r0 = c_r0[q];
             const int last = (r0 == 0) ? 8 : (9 - r0);
-            if (r0 != 255 && q != 0) {
+            if (r0 != 255) {                       // (quad 0 is never a rate-0 node)
+                // The update below is where the register pressure peaks (pass state + four interleaved phi chains):
+                // the words it does not touch wait in shared memory meanwhile.
+                const uint32_t stash = L.wsm + (uint32_t)LY::STASH_OFF + (uint32_t)L.lane * 48u;
+                asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(stash), "d"(L.m), "d"(L.mg_gap) : "memory");
+                asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(stash + 16u), "d"(L.mg_den),
+                             "d"(__hiloint2double((int)L.bs, L.ord)) : "memory");
+                asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(stash + 32u), "r"(w),
+                             "r"((valid ? 1 : 0) | (pass << 1) | (qfirst << 2) | ((int)L.active << 10) | ((int)L.neg << 11)) : "memory");
                 llr_update8<S>(L, i, last);
+                {
+                    int t2;
+                    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(w), "=r"(t2) : "r"(stash + 32u) : "memory");
+                    valid = (t2 & 1) != 0; pass = (t2 >> 1) & 1; qfirst = (t2 >> 2) & 255;
+                    L.active = ((t2 >> 10) & 1) != 0; L.neg = ((t2 >> 11) & 1) != 0;
+                }
+                {
+                    double t;
+                    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(L.m), "=d"(L.mg_gap) : "r"(stash) : "memory");
+                    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(L.mg_den), "=d"(t) : "r"(stash + 16u) : "memory");
+                    L.bs = (uint32_t)__double2hiint(t);
+                    L.ord = __double2loint(t);
+                }
                 __syncwarp();
             }
             Carry cy; cy.qb = 0;
