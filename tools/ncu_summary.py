@@ -19,8 +19,49 @@ STALLS = ['stall_barrier', 'stall_branch_resolving', 'stall_dispatch', 'stall_dr
           'stall_math', 'stall_membar', 'stall_mio', 'stall_misc', 'stall_no_inst', 'stall_not_selected',
           'stall_selected', 'stall_short_sb', 'stall_sleep', 'stall_tex', 'stall_wait']
 
+def traffic(rep, codewords):
+    """--traffic N: DRAM bytes per codeword of the (single) captured launch -> JSON on stdout"""
+    import json
+    rows = page(rep, "raw")
+    hdr, units, vals = rows[0], rows[1], rows[2]
+    ci = {h: i for i, h in enumerate(hdr)}
+    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    rd = float(vals[ci["dram__bytes_read.sum"]]) * scale[units[ci["dram__bytes_read.sum"]]]
+    wr = float(vals[ci["dram__bytes_write.sum"]]) * scale[units[ci["dram__bytes_write.sum"]]]
+    print(json.dumps({"dram_bytes_per_codeword": (rd + wr) / codewords, "dram_bytes_read": rd, "dram_bytes_write": wr,
+                      "codewords": codewords, "kernel": vals[ci["Kernel Name"]],
+                      "source": "ncu --set full --clock-control none, tools/scl_prof.sh (5th scl_list launch of tools/scl_perf.py "
+                                f"{codewords} 8: detector pairing)"}))
+
+
+def all_kernels(rep):
+    """--all: one block of headline metrics per captured launch"""
+    rows = page(rep, "raw")
+    hdr, units = rows[0], rows[1]
+    ci = {h: i for i, h in enumerate(hdr)}
+    extra = ['dram__throughput.avg.pct_of_peak_sustained_elapsed', 'l1tex__t_sector_hit_rate.pct', 'launch__grid_size',
+             'launch__block_size', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
+             'smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio',
+             'smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio',
+             'smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio']
+    for vals in rows[2:]:
+        print(f"### {vals[ci['Kernel Name']]}  grid {vals[ci['launch__grid_size']]} x block {vals[ci['launch__block_size']]}")
+        for h, u, v in zip(hdr, units, vals):
+            try:
+                big = float(v or 0) > 0.15
+            except ValueError:
+                big = False
+            if h in KEYS or h in extra[:2] or h in extra[4:5] or ('issue_stalled' in h and 'per_issue_active' in h and big):
+                print(f"  {h:86s} {u:14s} {v}")
+        print()
+
+
 def main():
     rep = sys.argv[1]
+    if len(sys.argv) > 3 and sys.argv[2] == "--traffic":
+        return traffic(rep, int(sys.argv[3]))
+    if len(sys.argv) > 2 and sys.argv[2] == "--all":
+        return all_kernels(rep)
     rows = page(rep, "raw")
     hdr, units, vals = rows[0], rows[1], rows[2]
     for h, u, v in zip(hdr, units, vals):
