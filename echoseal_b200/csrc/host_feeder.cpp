@@ -97,7 +97,6 @@ struct KeyCtx {
     HmacKey band;                 // band key = the raw 32-byte master key (rtwm/detector.py:31)
     uint8_t hdr_pn[16];           // pn_bits(0, 128) packed
     std::vector<uint8_t> hop;     // band index per counter, grown on demand
-    EVP_CIPHER_CTX* aes_tpl = nullptr;   // AES-128-ECB context keyed with prng_sub: copied (not re-keyed) per use
 };
 
 struct Feeder {
@@ -194,9 +193,14 @@ struct AesEcb {
         EVP_EncryptInit_ex(ctx, cipher_aes_ecb(), nullptr, key, nullptr);
         EVP_CIPHER_CTX_set_padding(ctx, 0);
     }
-    // a context that takes its key schedule from a keyed template: EVP_CIPHER_CTX_copy instead of a key expansion
-    AesEcb() { ctx = EVP_CIPHER_CTX_new(); }
-    void rekey_from(const EVP_CIPHER_CTX* tpl) { EVP_CIPHER_CTX_copy(ctx, tpl); }
+    // a context bound to AES-128-ECB once; rekey() only expands a key (no reference traffic on the shared cipher object)
+    AesEcb()
+    {
+        ctx = EVP_CIPHER_CTX_new();
+        EVP_EncryptInit_ex(ctx, cipher_aes_ecb(), nullptr, nullptr, nullptr);
+        EVP_CIPHER_CTX_set_padding(ctx, 0);
+    }
+    void rekey(const uint8_t key[16]) { EVP_EncryptInit_ex(ctx, nullptr, nullptr, key, nullptr); }
     ~AesEcb() { EVP_CIPHER_CTX_free(ctx); }
     void pn(uint64_t ctr, uint8_t out[PN_BYTES])
     {
@@ -235,10 +239,6 @@ static void derive_key(const uint8_t key32[32], KeyCtx& k)
     aes.pn(0, pn);
     memcpy(k.hdr_pn, pn, 16);
     k.hop.clear();
-    if (k.aes_tpl) EVP_CIPHER_CTX_free(k.aes_tpl);
-    k.aes_tpl = EVP_CIPHER_CTX_new();
-    EVP_EncryptInit_ex(k.aes_tpl, cipher_aes_ecb(), nullptr, k.prng_sub, nullptr);
-    EVP_CIPHER_CTX_set_padding(k.aes_tpl, 0);
 }
 
 static void grow_hop(KeyCtx& k, size_t hi)
@@ -255,23 +255,41 @@ static void grow_hop(KeyCtx& k, size_t hi)
     }
 }
 
+// A ChaCha20-Poly1305 context bound to its cipher ONCE (encrypt or decrypt side); every message then only sets key and
+// nonce.  Passing the cipher to EVP_*Init_ex per message takes and drops a reference on the shared cipher object - an
+// atomic on one cache line from every worker thread, which is what kept the feeder from scaling past a few threads.
+struct Aead {
+    EVP_CIPHER_CTX* ctx = nullptr;
+    int enc = -1;
+    ~Aead() { if (ctx) EVP_CIPHER_CTX_free(ctx); }
+    bool bind(int want_enc)
+    {
+        if (ctx && enc == want_enc) return true;
+        if (!ctx) ctx = EVP_CIPHER_CTX_new();
+        if (EVP_CipherInit_ex(ctx, cipher_chacha(), nullptr, nullptr, nullptr, want_enc) != 1) return false;
+        EVP_CIPHER_CTX_ctrl(ctx, EVP_CTRL_AEAD_SET_IVLEN, 12, nullptr);
+        enc = want_enc;
+        return true;
+    }
+};
+
 // ChaCha20-Poly1305 open of nonce(12) | ct(27) | tag(16) (rtwm/crypto.py:39-43)
-static bool aead_open(EVP_CIPHER_CTX* ctx, const uint8_t key[32], const uint8_t blob[55], uint8_t pt[27])
+static bool aead_open(Aead& A, const uint8_t key[32], const uint8_t blob[55], uint8_t pt[27])
 {
     int ol = 0, fl = 0;
-    if (EVP_DecryptInit_ex(ctx, cipher_chacha(), nullptr, nullptr, nullptr) != 1) return false;
-    EVP_CIPHER_CTX_ctrl(ctx, EVP_CTRL_AEAD_SET_IVLEN, 12, nullptr);
+    if (!A.bind(0)) return false;
+    EVP_CIPHER_CTX* ctx = A.ctx;
     if (EVP_DecryptInit_ex(ctx, nullptr, nullptr, key, blob) != 1) return false;
     if (EVP_DecryptUpdate(ctx, pt, &ol, blob + 12, 27) != 1) return false;
     EVP_CIPHER_CTX_ctrl(ctx, EVP_CTRL_AEAD_SET_TAG, 16, (void*)(blob + 39));
     return EVP_DecryptFinal_ex(ctx, pt + ol, &fl) == 1;
 }
 
-static bool aead_seal(EVP_CIPHER_CTX* ctx, const uint8_t key[32], const uint8_t nonce[12], const uint8_t pt[27], uint8_t blob[55])
+static bool aead_seal(Aead& A, const uint8_t key[32], const uint8_t nonce[12], const uint8_t pt[27], uint8_t blob[55])
 {
     int ol = 0, fl = 0;
-    if (EVP_EncryptInit_ex(ctx, cipher_chacha(), nullptr, nullptr, nullptr) != 1) return false;
-    EVP_CIPHER_CTX_ctrl(ctx, EVP_CTRL_AEAD_SET_IVLEN, 12, nullptr);
+    if (!A.bind(1)) return false;
+    EVP_CIPHER_CTX* ctx = A.ctx;
     if (EVP_EncryptInit_ex(ctx, nullptr, nullptr, key, nonce) != 1) return false;
     memcpy(blob, nonce, 12);
     if (EVP_EncryptUpdate(ctx, blob + 12, &ol, pt, 27) != 1) return false;
@@ -305,7 +323,6 @@ void es_host_keys_free(void* h)
 {
     Feeder* f = (Feeder*)h;
     if (!f) return;
-    for (auto& k : f->keys) if (k.aes_tpl) EVP_CIPHER_CTX_free(k.aes_tpl);
     delete f;
 }
 
@@ -449,7 +466,7 @@ int es_host_rx_validate(void* h, const int32_t* key_idx, int nb,
         int64_t boff[4];
         int64_t o = item_offset[ci];
         for (int b = 0; b < 4; ++b) { boff[b] = o; o += band_count[ci * 4 + b]; }
-        EVP_CIPHER_CTX* ctx = nullptr;
+        Aead ctx;
         uint8_t* ns = nonce_state + 9 * (size_t)ci;
         for (int oi = 0; oi < 4 && !verdict[ci]; ++oi) {
             const int b = order[oi];
@@ -461,7 +478,6 @@ int es_host_rx_validate(void* h, const int32_t* key_idx, int nb,
                 for (const int64_t* p = p0; p < p1; ++p) {
                     const uint8_t* blob = hit_payload + 55 * (size_t)(p - hit_cw);
                     uint8_t pt[27 + 16];
-                    if (!ctx) ctx = EVP_CIPHER_CTX_new();
                     if (!aead_open(ctx, k.aead_key, blob, pt)) continue;
                     if (memcmp(pt, "ESAL", 4) != 0) continue;
                     const uint32_t ec = ((uint32_t)pt[4] << 24) | ((uint32_t)pt[5] << 16) | ((uint32_t)pt[6] << 8) | pt[7];
@@ -476,7 +492,6 @@ int es_host_rx_validate(void* h, const int32_t* key_idx, int nb,
                 }
             }
         }
-        if (ctx) EVP_CIPHER_CTX_free(ctx);
     });
     return 0;
 }
@@ -492,15 +507,15 @@ int es_host_tx_prepare(void* h, const int32_t* key_idx, const uint32_t* ctr, con
     const int chunk = 64;
     const int nchunks = (F + chunk - 1) / chunk;
     parallel_for(nchunks, f->nthreads, [&](int cidx) {
-        EVP_CIPHER_CTX* ctx = EVP_CIPHER_CTX_new();
-        AesEcb aes;                                   // one AES context per chunk of frames, keyed by copy per frame
+        Aead ctx;                                     // one AEAD and one AES context per chunk of frames
+        AesEcb aes;
         int last_k = -1;
         const int i1 = std::min(F, (cidx + 1) * chunk);
         for (int i = cidx * chunk; i < i1; ++i) {
             const int kidx = key_idx ? key_idx[i] : 0;
             if (kidx < 0 || (size_t)kidx >= f->keys.size()) { bad = 1; continue; }
             const KeyCtx& k = f->keys[(size_t)kidx];
-            if (kidx != last_k) { aes.rekey_from(k.aes_tpl); last_k = kidx; }
+            if (kidx != last_k) { aes.rekey(k.prng_sub); last_k = kidx; }
             uint8_t meta[27];
             memcpy(meta, "ESAL", 4);
             meta[4] = (uint8_t)(ctr[i] >> 24); meta[5] = (uint8_t)(ctr[i] >> 16); meta[6] = (uint8_t)(ctr[i] >> 8); meta[7] = (uint8_t)ctr[i];
@@ -514,7 +529,6 @@ int es_host_tx_prepare(void* h, const int32_t* key_idx, const uint32_t* ctr, con
             band[i] = d[0] & 3;
             ctr_lo16[i] = (int32_t)(ctr[i] & 0xFFFF);
         }
-        EVP_CIPHER_CTX_free(ctx);
     });
     return bad ? -1 : 0;
 }
