@@ -50,6 +50,14 @@ __device__ __forceinline__ void phi_lds2(uint32_t addr, double& a, double& b)
 #define PHI_HI(x) ((uint32_t)__double2hiint(x))
 #define PHI_LO(x) ((uint32_t)__double2loint(x))
 #define PHI_HILO(hi, lo) __hiloint2double((int)(hi), (int)(lo))
+// hi + ((k div 64) << 20) as shift + multiply-add (two instructions; the compiler's own form is shift, mask, add)
+__device__ __forceinline__ uint32_t phi_expadd(uint32_t hi, int32_t k)
+{
+    uint32_t r;
+    asm("{\n.reg .s32 t;\nshr.s32 t, %1, 6;\nmad.lo.s32 %0, t, 1048576, %2;\n}" : "=r"(r) : "r"(k), "r"(hi));
+    return r;
+}
+#define PHI_EXPADD(hi, k) phi_expadd((hi), (k))
 #else
 #include <math.h>
 typedef const double* phi_tab_t;
@@ -61,6 +69,7 @@ static inline double PHI_U2D(uint64_t u) { double x; memcpy(&x, &u, 8); return x
 #define PHI_HI(x) ((uint32_t)(PHI_D2U(x) >> 32))
 #define PHI_LO(x) ((uint32_t)PHI_D2U(x))
 #define PHI_HILO(hi, lo) PHI_U2D(((uint64_t)(uint32_t)(hi) << 32) | (uint32_t)(lo))
+#define PHI_EXPADD(hi, k) ((uint32_t)(hi) + (uint32_t)(((k) >> 6) * 0x100000))
 #endif
 
 // scalar coefficients.  On the device they are read from __constant__ memory so that they are free
@@ -106,10 +115,11 @@ PHI_FN double phi_fast(double d, phi_tab_t tab)
     q = PHI_FMA(r, q, PHI_K(5));
     q = PHI_FMA(r, q, 0.5);
     const double p = PHI_FMA(r * r, q, r);                    // exp(r) - 1
-    const double th = PHI_LD(tab, PHI_OFF_EXP + (ki & 63));
-    const double tm = PHI_FMA(th, p, th);                     // 2^(j/64) * exp(r), in (0.99, 1.99)
-    // t = tm * 2^(k div 64): (ki & ~63) << 14 is (k div 64) << 20, added to the exponent field (>= -93: no underflow)
-    const double t = PHI_HILO(PHI_HI(tm) + (((uint32_t)ki & ~63u) << 14), PHI_LO(tm));
+    const double th0 = PHI_LD(tab, PHI_OFF_EXP + (ki & 63));
+    // th = 2^(j/64) * 2^(k div 64): (k div 64) << 20 goes into the exponent field of the table value (>= -93: never
+    // subnormal, so the scaling is exact and commutes with the fma below), off the critical path of the polynomial
+    const double th = PHI_HILO(PHI_EXPADD(PHI_HI(th0), ki), PHI_LO(th0));
+    const double t = PHI_FMA(th, p, th);                      // exp(-d)
     // ---- log1p(t), 0 <= t <= 1
     const double u = 1.0 + t;
     const int i = (int)(PHI_HI(u) >> 11) - 0x7fe00;           // 0..511, 512 iff u == 2.0
@@ -120,6 +130,14 @@ PHI_FN double phi_fast(double d, phi_tab_t tab)
     w = PHI_FMA(rr, w, PHI_K(7));
     w = PHI_FMA(rr, w, -0.5);
     return lc + PHI_FMA(rr * rr, w, rr);
+}
+
+// psi(x) = |x|/2 + phi(|x|) = ln(2 cosh(x/2)).  The decoder's f = logaddexp(a,b) - logaddexp(0,a+b) equals
+// psi(a-b) - psi(a+b) (max(a,b) - max(0,a+b) = (|a-b| - |a+b|)/2), so no max/select terms travel with phi.
+PHI_FN double psi_fast(double x, phi_tab_t tab)
+{
+    const double ax = PHI_HILO(PHI_HI(x) & 0x7fffffffu, PHI_LO(x));
+    return PHI_FMA(ax, 0.5, phi_fast(x, tab));
 }
 
 // fill `tab` (PHI_TAB_DOUBLES doubles) from the generated bit patterns in phi_tables.h

@@ -54,59 +54,53 @@ static CodeDev g_code[ES_MAX_DEVICES];
 // interleaved evaluations.  The kernel is instruction-cache sensitive: with phi
 // inlined, every phi-heavy loop cost 4 KB of SASS and the hot code sat on the 32 KB edge.  ptxas
 // allocates registers across these calls (no marshalling: a call costs CALL + RET + one MOV).
-// Each routine returns mx_j + phi(d_j): the callers' "max" terms ride along, so that nothing but the results is live
-// in the caller across the call.
+// f = logaddexp(a,b) - logaddexp(0,a+b) (rtwm/fastpolar.py:18-23) is evaluated as psi(a-b) - psi(a+b) with
+// psi(x) = |x|/2 + phi(|x|) (phi_impl.h): max(a,b) - max(0,a+b) = (|a-b| - |a+b|)/2, so no max/select terms travel
+// with phi and the routines take one operand per evaluation.
 struct D4 { double a, b, c, d; };
 struct D2 { double a, b; };
 
-__device__ __noinline__ D4 lse4(double m0, double d0, double m1, double d1, double m2, double d2, double m3, double d3,
-                                uint32_t tab)
+// The routines take the shared-window address of the phi tables from the CTA's dynamic shared memory base themselves
+// (a uniform register: the table reads are [index + base] with no address add per evaluation).
+__device__ __forceinline__ uint32_t smem_base();
+__device__ __noinline__ D4 psi4(double x0, double x1, double x2, double x3)
 {
+    const uint32_t tab = smem_base();
     D4 r;
-    r.a = m0 + phi_fast(d0, tab); r.b = m1 + phi_fast(d1, tab); r.c = m2 + phi_fast(d2, tab); r.d = m3 + phi_fast(d3, tab);
+    r.a = psi_fast(x0, tab); r.b = psi_fast(x1, tab); r.c = psi_fast(x2, tab); r.d = psi_fast(x3, tab);
     return r;
 }
-__device__ __noinline__ D2 phi2(double d0, double d1, uint32_t tab)
+__device__ __noinline__ D2 phi2(double d0, double d1)
 {
+    const uint32_t tab = smem_base();
     D2 r;
     r.a = phi_fast(d0, tab); r.b = phi_fast(d1, tab);
     return r;
 }
-__device__ __noinline__ double phi1(double d0, uint32_t tab) { return phi_fast(d0, tab); }
+__device__ __noinline__ double phi1(double d0) { return phi_fast(d0, smem_base()); }
 
-// numpy's npy_logaddexp: x==y -> x+ln2 ; else max + log1p(exp(-|x-y|)).  x == y needs no special case here:
-// phi_fast(0) == ln2 exactly (table entry 256).  f = logaddexp(a,b) - logaddexp(0,a+b) for two element pairs
-// at once (four independent phi chains).
-#ifndef ES_SCL_F2FN
-#define ES_SCL_F2FN 0       // f of two element pairs as ONE out-of-line routine taking the four operands (0: through lse4)
-#endif
-#if ES_SCL_F2FN
-__device__ __noinline__ D2 f2_fn(double a0, double b0, double a1, double b1, uint32_t tab)
-{
-    const double d0 = a0 - b0, s0 = a0 + b0, d1 = a1 - b1, s1 = a1 + b1;
-    const double A0 = ((d0 > 0.0) ? a0 : b0) + phi_fast(d0, tab);              // phi takes |d| itself
-    const double B0 = (((0.0 - s0) > 0.0) ? 0.0 : s0) + phi_fast(s0, tab);
-    const double A1 = ((d1 > 0.0) ? a1 : b1) + phi_fast(d1, tab);
-    const double B1 = (((0.0 - s1) > 0.0) ? 0.0 : s1) + phi_fast(s1, tab);
-    D2 r;
-    r.a = A0 - B0;
-    r.b = A1 - B1;
-    return r;
-}
-#endif
+// f of two element pairs at once (four independent phi chains).  x == y needs no special case (numpy's npy_logaddexp
+// has one): phi_fast(0) == ln2 exactly (table entry 256).
 __device__ __forceinline__ void fcomb2(double a0, double b0, double a1, double b1, uint32_t tab, double& r0, double& r1)
 {
-#if ES_SCL_F2FN
-    const D2 R = f2_fn(a0, b0, a1, b1, tab);
-    r0 = R.a;
-    r1 = R.b;
-#else
-    const double d0 = a0 - b0, s0 = a0 + b0, d1 = a1 - b1, s1 = a1 + b1;
-    const D4 P = lse4((d0 > 0.0) ? a0 : b0, d0, ((0.0 - s0) > 0.0) ? 0.0 : s0, s0,
-                      (d1 > 0.0) ? a1 : b1, d1, ((0.0 - s1) > 0.0) ? 0.0 : s1, s1, tab);     // phi takes |d| itself
+    const D4 P = psi4(a0 - b0, a0 + b0, a1 - b1, a1 + b1);
     r0 = P.a - P.b;
     r1 = P.c - P.d;
+}
+// the same with the four chains inlined into the caller's loop (the passes over the DRAM-resident levels: no call, so
+// the loads, stores and g arithmetic of the loop schedule into the latency gaps of the chains)
+#ifndef ES_SCL_PHI_INL
+#define ES_SCL_PHI_INL 0
 #endif
+__device__ __forceinline__ void fcomb2_inl(double a0, double b0, double a1, double b1, uint32_t tab, double& r0, double& r1)
+{
+#if !ES_SCL_PHI_INL
+    fcomb2(a0, b0, a1, b1, tab, r0, r1);
+    return;
+#endif
+    const double p0 = psi_fast(a0 - b0, tab), p1 = psi_fast(a0 + b0, tab), p2 = psi_fast(a1 - b1, tab), p3 = psi_fast(a1 + b1, tab);
+    r0 = p0 - p1;
+    r1 = p2 - p3;
 }
 
 // same value as f(a, b), also handing out the two phi terms: fm = phi(|a-b|), fp = phi(|a+b|).
@@ -115,12 +109,10 @@ __device__ __forceinline__ void fcomb2(double a0, double b0, double a1, double b
 __device__ __forceinline__ double fcomb_parts(double a, double b, uint32_t tab, double& fm, double& fp)
 {
     const double d = a - b, s = a + b;
-    const D2 P = phi2(d, s, tab);
+    const D2 P = phi2(d, s);
     fm = P.a;
     fp = P.b;
-    const double A = ((d > 0.0) ? a : b) + fm;
-    const double B = (((0.0 - s) > 0.0) ? 0.0 : s) + fp;
-    return A - B;
+    return __fma_rn(fabs(d), 0.5, fm) - __fma_rn(fabs(s), 0.5, fp);
 }
 
 // g = b + (1-2u) a (rtwm/fastpolar.py:26-29): (1-2u)*a is exact, so flipping the sign bit of a is the same number
@@ -236,7 +228,8 @@ template <int S> struct SclLayout {
     static constexpr int BAR_OFF = RING_OFF + RING_BYTES;                 // one 8-byte mbarrier per stage
     static constexpr int STASH_OFF = BAR_OFF + 16;                        // 48 bytes per lane: decode state parked across the LLR update
     static constexpr int WARP_BYTES = STASH_OFF + 32 * 48;
-    static constexpr int TAB_BYTES = PHI_TAB_DOUBLES * 8;
+    static constexpr int NTH_OFF = PHI_TAB_DOUBLES * 8;                  // [mask 256][n 8] bytes: position of the n-th set bit
+    static constexpr int TAB_BYTES = NTH_OFF + 2048;
     static constexpr size_t G_ROWS = 1024 - (1 << (11 - S));           // global alpha rows, levels 1..S-1
     static constexpr size_t G_DOUBLES = G_ROWS * 32 + 1024 * 4 + BROWS_G * 16;   // + level-0 copy [1024][4] + beta rows
 };
@@ -396,10 +389,20 @@ __device__ __noinline__ void negate_level0(double* l0)
 // passes over the DRAM-resident levels (0..S-1).  Lane 0 streams the source node into the warp's ring with
 // cp.async.bulk (TMA), one 8-row chunk per stage and two stages ahead, completion on one mbarrier per stage;
 // every lane reads its own (codeword, slot) column of the landed rows.  Results go straight to their level
-// (each store instruction writes one full 256-byte row).
+// (each store instruction writes one full 256-byte row).  The row pitch RS of the source is a template
+// parameter (256 bytes; 32 for level 0, [position][codeword]) so that the eight loads of a chunk are one address
+// plus immediates; the four phi chains of a chunk are inlined (fcomb2_inl), so nothing is called inside the loops.
 // ---------------------------------------------------------------------------------------------
 #ifndef ES_SCL_DBG_VERIFY
 #define ES_SCL_DBG_VERIFY 0
+#endif
+#ifndef ES_SCL_PASS_INLINE
+#define ES_SCL_PASS_INLINE 0     // the two ring passes inlined into the kernel body (single call site each)
+#endif
+#if ES_SCL_PASS_INLINE
+#define ES_PASS_INLINE __forceinline__
+#else
+#define ES_PASS_INLINE __noinline__
 #endif
 
 // lane 0: queue one stage
@@ -424,134 +427,126 @@ __device__ __forceinline__ int hi4(double a, double b, double c, double d)
     return __double2hiint(a) ^ __double2hiint(b) ^ __double2hiint(c) ^ __double2hiint(d);
 }
 
-// the eight rows of chunk c of a source node (row pitch rs bytes, this lane's column at byte offset col)
-struct PassSrc {
-    const unsigned char* base;    // row 0 of the node, warp-uniform
-    uint32_t rs, col;
-    int nch;
-};
+// Ring state of one pass.  Every pass consumes an even number of chunks, so both stages always sit at the same
+// mbarrier parity between passes: one bit (ph) is carried from pass to pass.
+template <int RS> struct Ring {
+    const unsigned char* next;   // global address of the next chunk to queue (warp-uniform)
+    uint32_t col0, col1;         // shared-window address of this lane's column in stage 0 / 1
+    uint32_t bar;                // mbarrier of stage 0 (stage 1: + 8)
+    uint32_t ph;                 // parity the next wait has to see
+    int st;                      // stage of the next chunk
+    int left;                    // chunks not queued yet
 
-template <bool TMA>
-__device__ __forceinline__ void pass_begin(Lane& L, const PassSrc& ps)
-{
-    if (TMA) {
+    __device__ __forceinline__ void begin(const Lane& L, const unsigned char* base, uint32_t col, int nch, uint32_t ph0)
+    {
+        col0 = L.ring(0) + col; col1 = L.ring(1) + col; bar = L.rbar(); ph = ph0; st = 0;
         fence_proxy_async();      // the node was written with ordinary stores (this warp, earlier passes)
         __syncwarp();
         if (L.lane == 0) {
-            ring_issue(L, 0, ps.base, 8u * ps.rs);
-            if (ps.nch > 1) ring_issue(L, 1, ps.base + 8u * ps.rs, 8u * ps.rs);
+            ring_issue(L, 0, base, 8u * RS);
+            ring_issue(L, 1, base + 8u * RS, 8u * RS);
         }
         __syncwarp();
+        next = base + 16u * RS;
+        left = nch - 2;
     }
-}
-// wait for chunk c (stage st); returns the address this lane's column of row 0 is read from
-template <bool TMA>
-__device__ __forceinline__ size_t pass_wait(Lane& L, const PassSrc& ps, int c, int st)
-{
-    if (TMA) {
-        mbar_wait(L.rbar() + 8u * st, (L.rphase >> st) & 1u);
-        L.rphase ^= 1u << st;
-        return (size_t)(L.ring(st) + ps.col);
+    // wait for the next chunk; returns the shared-window address of this lane's column of its row 0
+    __device__ __forceinline__ uint32_t wait()
+    {
+        mbar_wait(bar + 8u * (uint32_t)st, ph);
+        return st ? col1 : col0;
     }
-    return reinterpret_cast<size_t>(ps.base + (size_t)c * 8u * ps.rs + ps.col);
-}
-// rows i0 .. i0+3 of the chunk
-template <bool TMA>
-__device__ __forceinline__ void pass_ld4(size_t at, const PassSrc& ps, int i0, double& a, double& b, double& c, double& d)
-{
-    if (TMA) {
-        const uint32_t sb = (uint32_t)at + (uint32_t)i0 * ps.rs;
-        a = lds_f64(sb); b = lds_f64(sb + ps.rs); c = lds_f64(sb + 2 * ps.rs); d = lds_f64(sb + 3 * ps.rs);
-    } else {
-        const unsigned char* src = reinterpret_cast<const unsigned char*>(at) + (size_t)i0 * ps.rs;
-        a = *reinterpret_cast<const double*>(src); b = *reinterpret_cast<const double*>(src + ps.rs);
-        c = *reinterpret_cast<const double*>(src + 2 * ps.rs); d = *reinterpret_cast<const double*>(src + 3 * ps.rs);
-    }
-}
-// every lane holds the values of the stage in registers (w covers the loads not consumed yet): refill it
-template <bool TMA>
-__device__ __forceinline__ void pass_refill(Lane& L, const PassSrc& ps, int c, int& st, int w)
-{
-    if (TMA) {
+    // every lane holds the values of the stage in registers (w covers the loads not consumed yet): refill it
+    __device__ __forceinline__ void refill(const Lane& L, int w)
+    {
         ring_release(w);
-        if (L.lane == 0 && c + RING_STAGES < ps.nch)
-            ring_issue(L, st, ps.base + (size_t)(c + RING_STAGES) * 8u * ps.rs, 8u * ps.rs);
+        if (L.lane == 0 && left > 0) ring_issue(L, st, next, 8u * RS);
+        next += 8u * RS;
+        --left;
+        ph ^= (uint32_t)st;
         st ^= 1;
     }
+};
+template <int RS> __device__ __forceinline__ void ring_ld4(uint32_t at, int i0, double& a, double& b, double& c, double& d)
+{
+    a = lds_f64(at + (uint32_t)(i0 * RS)); b = lds_f64(at + (uint32_t)((i0 + 1) * RS));
+    c = lds_f64(at + (uint32_t)((i0 + 2) * RS)); d = lds_f64(at + (uint32_t)((i0 + 3) * RS));
 }
 
 // g node of level l0 (1..S-1) from its parent (slot ps of level l0-1; level 0 = the channel LLRs), fused with the
 // f node of level l0+1 below it when do_f: chunk c holds the parent elements k, k+h, k+s, k+s+h for k = 2c, 2c+1
 // and gives g[k], g[k+h] (stored: the g node of level l0+1 needs them later) and f(g[k], g[k+h]) — the g node is
 // never read back for its f child.
-template <int S>
-__device__ __forceinline__ void pass_gf_body(Lane& L, int l0, bool do_f)
+template <int S, int RS>
+__device__ __forceinline__ uint32_t pass_gf_body(const Lane& L, int l0, bool do_f)
 {
     const int s = 1 << (10 - l0), h = s >> 1;
-    PassSrc src;
-    src.nch = h >> 1;
-    if (l0 == 1) {
-        src.base = reinterpret_cast<const unsigned char*>(L.gw + SclLY::G_ROWS * 32);
-        src.rs = 32u;
-        src.col = (uint32_t)(L.lane >> 3) * 8u;
-    } else {
-        src.base = reinterpret_cast<const unsigned char*>(L.gw + (size_t)lvl_row0(l0 - 1) * 32);
-        src.rs = 256u;
-        src.col = (uint32_t)(L.gbase() + ((L.ptr >> (3 * (l0 - 2))) & 7)) * 8u;
-    }
-    // running output pointers: g[k] sits at position 8c (c < half) or 8(c-half)+1, with g[k+1] +4 rows and g[k+h] +2
-    // rows; f[k] at k (shared memory, natural order) or at its interleaved position, which advances by 8 rows per
-    // chunk inside a quarter of nch/4... (recomputed per chunk: two shifts)
-    double* gd = L.ga() + lvl_row0(l0) * 32 + L.p();
-    double* const gd_odd = gd + 32;
-    double* fdst = (l0 + 1 >= S) ? slvl<S>(L, l0 + 1, L.p()) : L.ga() + lvl_row0(l0 + 1) * 32 + L.p();
-    const int lqf = (l0 + 1 >= S) ? -1 : 8 - (l0 + 1);          // f node: natural order in shared memory
+    const int nch = h >> 1;
+    Ring<RS> R;
+    if (RS == 32) R.begin(L, reinterpret_cast<const unsigned char*>(L.gw + SclLY::G_ROWS * 32), (uint32_t)(L.lane >> 3) * 8u, nch, L.rphase);
+    else R.begin(L, reinterpret_cast<const unsigned char*>(L.gw + (size_t)lvl_row0(l0 - 1) * 32),
+                 (uint32_t)(L.gbase() + ((L.ptr >> (3 * (l0 - 2))) & 7)) * 8u, nch, L.rphase);
+    // outputs, as running pointers.  g[k] sits at row 8c (c < nch/2) or 8(c - nch/2) + 1, g[k+h] 2 rows, g[k+1] 4 rows,
+    // g[k+1+h] 6 rows further.  f[k]: natural order in shared memory (row k, f[k+1] one row further), or quarter-
+    // interleaved in global memory: quarter j = c / (nch/4), row 8(c mod nch/4) + j, f[k+1] four rows further.
+    double* const gbase = L.ga() + lvl_row0(l0) * 32 + L.p();
+    double* gd = gbase;
+    const bool nat = (l0 + 1 >= S);
+    double* const fbase = nat ? slvl<S>(L, l0 + 1, L.p()) : L.ga() + lvl_row0(l0 + 1) * 32 + L.p();
+    double* fd = fbase;
+    const int fstep = nat ? 2 * 32 : 8 * 32, f1 = nat ? 32 : 4 * 32;
+    const int lnq = 31 - __clz(nch) - 2;                      // log2(nch / 4) >= 1
+    const int bmask = ((lnq < 4) ? (1 << lnq) : 16) - 1;      // chunks between two looks at the block below
     // left-child partial sums of the g node: bit k of the lane's beta words; 32 consecutive k per word, h is a
     // multiple of 16: the two words in use are reloaded every 16 chunks only
     const uint32_t* bw = beta_rows(L, l0) + L.gbase() + ((L.bptr >> (3 * (l0 - 1))) & 7);
     uint32_t w0 = 0, w1 = 0;
-    pass_begin<ES_SCL_TMA_GF != 0>(L, src);
-    int st = 0;
-    const int half = src.nch >> 1;
+    const uint32_t tab = L.tab();
 #pragma unroll 1
-    for (int c = 0; c < src.nch; ++c) {
-        double v[8];     // A(k) A(k+h) B(k) B(k+h) A(k+1) A(k+1+h) B(k+1) B(k+1+h)
+    for (int c = 0; c < nch; ++c) {
+        double v0, v1, v2, v3, v4, v5, v6, v7;     // A(k) A(k+h) B(k) B(k+h) A(k+1) A(k+1+h) B(k+1) B(k+1+h)
         {
-            const size_t at = pass_wait<ES_SCL_TMA_GF != 0>(L, src, c, st);
-            pass_ld4<ES_SCL_TMA_GF != 0>(at, src, 0, v[0], v[1], v[2], v[3]);
-            pass_ld4<ES_SCL_TMA_GF != 0>(at, src, 4, v[4], v[5], v[6], v[7]);
-            pass_refill<ES_SCL_TMA_GF != 0>(L, src, c, st, hi4(v[0], v[1], v[2], v[3]) ^ hi4(v[4], v[5], v[6], v[7]));
+            const uint32_t at = R.wait();
+            ring_ld4<RS>(at, 0, v0, v1, v2, v3);
+            ring_ld4<RS>(at, 4, v4, v5, v6, v7);
+            R.refill(L, hi4(v0, v1, v2, v3) ^ hi4(v4, v5, v6, v7));
         }
-        const int k = 2 * c;
-        if ((c & 15) == 0) {
-            w0 = bw[(k >> 5) * 32];
-            w1 = bw[((k + h) >> 5) * 32] >> (h & 31);         // h = 16 (level 5): the upper half of the same word
+        if ((c & bmask) == 0) {
+            if ((c & 15) == 0) {
+                const int k = 2 * c;
+                w0 = bw[(k >> 5) * 32];
+                w1 = bw[((k + h) >> 5) * 32] >> (h & 31);         // h = 16 (level 5): the upper half of the same word
+            }
+            if ((c & ((1 << lnq) - 1)) == 0) {
+                const int j = c >> lnq;
+                if (!nat) fd = fbase + j * 32;
+                if (j == 2) gd = gbase + 32;
+            }
         }
-        if (c == half) gd = gd_odd;
-        const double g0 = gcomb(v[0], v[2], w0 & 1u), gh0 = gcomb(v[1], v[3], w1 & 1u);
-        const double g1 = gcomb(v[4], v[6], (w0 >> 1) & 1u), gh1 = gcomb(v[5], v[7], (w1 >> 1) & 1u);
+        const double g0 = gcomb(v0, v2, w0 & 1u), gh0 = gcomb(v1, v3, w1 & 1u);
+        const double g1 = gcomb(v4, v6, (w0 >> 1) & 1u), gh1 = gcomb(v5, v7, (w1 >> 1) & 1u);
         w0 >>= 2; w1 >>= 2;
         gd[0] = g0; gd[2 * 32] = gh0; gd[4 * 32] = g1; gd[6 * 32] = gh1;
         gd += 8 * 32;
         if (do_f) {
             double r0, r1;
-            fcomb2(g0, gh0, g1, gh1, L.tab(), r0, r1);
-            double* fd = fdst + ((lqf < 0) ? k : (((k & ((1 << lqf) - 1)) << 2) | (k >> lqf))) * 32;
-            fd[0] = r0; fd[((lqf < 0) ? 1 : 4) * 32] = r1;
+            fcomb2_inl(g0, gh0, g1, gh1, tab, r0, r1);
+            fd[0] = r0; fd[f1] = r1;
+            fd += fstep;
         }
     }
+    return R.ph;
 }
 
 // Out of line on purpose (one copy, and its working set does not add to the register pressure of the
 // decode loop): only the words the pass needs travel; the caller re-points the level's slot.
 template <int S>
-__device__ __noinline__ uint32_t pass_gf_fn(uint32_t wsm, double* gw, int lane, uint32_t rphase, uint32_t ptr, uint32_t bptr,
+__device__ ES_PASS_INLINE uint32_t pass_gf_fn(uint32_t wsm, double* gw, int lane, uint32_t rphase, uint32_t ptr, uint32_t bptr,
                                             int l0, bool do_f)
 {
     Lane T;
     T.wsm = wsm; T.gw = gw; T.lane = lane; T.rphase = rphase; T.ptr = ptr; T.bptr = bptr;
-    pass_gf_body<S>(T, l0, do_f);
-    return T.rphase;
+    return (l0 == 1) ? pass_gf_body<S, 32>(T, l0, do_f) : pass_gf_body<S, 256>(T, l0, do_f);
 }
 template <int S>
 __device__ __forceinline__ void pass_gf(Lane& L, int l0, bool do_f)
@@ -562,63 +557,86 @@ __device__ __forceinline__ void pass_gf(Lane& L, int l0, bool do_f)
     L.ptr = ptr;
 }
 
-// f node of level lv (1..S) from the node of level lv-1: chunk c holds the source elements r, r+q, r+2q, r+3q for
-// r = 2c, 2c+1 (q = quarter of the source node) and gives f[r], f[r+q], f[r+1], f[r+1+q].
-//   coop = false: every lane walks the whole node of its own slot (written by the pass above it), staged through the ring;
-//   coop = true (bit 0, one path): the 8 lanes of a codeword share the chunks of slot 0, read straight from memory.
+// f node of level lv (3..S) from the node of level lv-1 in the lane's own slot (written by the pass above it): chunk c
+// holds the source elements r, r+q, r+2q, r+3q for r = 2c, 2c+1 (q = quarter of the source node) and gives f[r],
+// f[r+q], f[r+1], f[r+1+q].
 template <int S>
-__device__ __forceinline__ void pass_f_body(Lane& L, int lv, bool coop)
+__device__ ES_PASS_INLINE uint32_t pass_f_fn(uint32_t wsm, double* gw, int lane, uint32_t rphase, int lv)
 {
+    Lane L;
+    L.wsm = wsm; L.gw = gw; L.lane = lane;
     const int s = 1 << (10 - lv), q = s >> 1;
-    const int slot = coop ? 0 : L.p();
-    PassSrc src;
-    src.nch = s >> 2;
-    if (lv == 1) {
-        src.base = reinterpret_cast<const unsigned char*>(L.gw + SclLY::G_ROWS * 32);
-        src.rs = 32u;
-        src.col = (uint32_t)(L.lane >> 3) * 8u;
-    } else {
-        src.base = reinterpret_cast<const unsigned char*>(L.gw + (size_t)lvl_row0(lv - 1) * 32);
-        src.rs = 256u;
-        src.col = (uint32_t)(L.gbase() + slot) * 8u;
-    }
+    const int nch = s >> 2;
+    Ring<256> R;
+    R.begin(L, reinterpret_cast<const unsigned char*>(gw + (size_t)lvl_row0(lv - 1) * 32), (uint32_t)lane * 8u, nch, rphase);
+    // f[r]: natural order in shared memory (row r; f[r+q] q rows, f[r+1] one row further) or quarter-interleaved in
+    // global memory: row 8c (c < nch/2) or 8(c - nch/2) + 1, f[r+q] two rows, f[r+1] four rows further
     const bool nat = lv >= S;
-    double* fdst = nat ? slvl<S>(L, lv, slot) : L.ga() + lvl_row0(lv) * 32 + slot;
-    const bool tma = (ES_SCL_TMA_F != 0) && !coop;
-    if (tma) pass_begin<true>(L, src);
-    int st = 0;
-    const int half = src.nch >> 1;
-    const int cstep = coop ? 8 : 1;
+    double* const fbase = nat ? slvl<S>(L, lv, L.p()) : L.ga() + lvl_row0(lv) * 32 + L.p();
+    double* fd = fbase;
+    const int fstep = nat ? 2 * 32 : 8 * 32, dq = nat ? q * 32 : 2 * 32, d1 = nat ? 32 : 4 * 32;
+    const int half = nat ? -1 : (nch >> 1);
+    const uint32_t tab = L.tab();
 #pragma unroll 1
-    for (int c = coop ? L.p() : 0; c < src.nch; c += cstep) {
-        // rows of the chunk: e(r) e(r+q) e(r+2q) e(r+3q) | e(r+1) e(r+1+q) e(r+1+2q) e(r+1+3q); one call per half,
-        // the second half loaded after the first call so that nothing of it is live across that call
-        double* fd = nat ? fdst + 2 * c * 32 : fdst + ((c < half) ? 8 * c : 8 * (c - half) + 1) * 32;   // f[r]
-        const int dq = nat ? q * 32 : 2 * 32, d1 = nat ? 32 : 4 * 32;                                        // f[r+q], f[r+1]
+    for (int c = 0; c < nch; ++c) {
+        // rows of the chunk: e(r) e(r+q) e(r+2q) e(r+3q) | e(r+1) e(r+1+q) e(r+1+2q) e(r+1+3q)
         double v0, v1, v2, v3, r0, r1;
-        const size_t at = tma ? pass_wait<true>(L, src, c, st) : pass_wait<false>(L, src, c, st);
-        if (tma) pass_ld4<true>(at, src, 0, v0, v1, v2, v3); else pass_ld4<false>(at, src, 0, v0, v1, v2, v3);
-        fcomb2(v0, v2, v1, v3, L.tab(), r0, r1);               // f[r], f[r+q]
+        const uint32_t at = R.wait();
+        if (c == half) fd = fbase + 32;
+        ring_ld4<256>(at, 0, v0, v1, v2, v3);
+        fcomb2_inl(v0, v2, v1, v3, tab, r0, r1);               // f[r], f[r+q]
         fd[0] = r0; fd[dq] = r1;
-        if (tma) pass_ld4<true>(at, src, 4, v0, v1, v2, v3); else pass_ld4<false>(at, src, 4, v0, v1, v2, v3);
-        if (tma) pass_refill<true>(L, src, c, st, hi4(v0, v1, v2, v3));
-        fcomb2(v0, v2, v1, v3, L.tab(), r0, r1);               // f[r+1], f[r+1+q]
+        ring_ld4<256>(at, 4, v0, v1, v2, v3);
+        R.refill(L, hi4(v0, v1, v2, v3));
+        fcomb2_inl(v0, v2, v1, v3, tab, r0, r1);               // f[r+1], f[r+1+q]
         fd[d1] = r0; fd[d1 + dq] = r1;
+        fd += fstep;
     }
+    return R.ph;
 }
 
+// The bit-0 spine (one path): f node of level lv (1..S) from level lv-1, the 8 lanes of a codeword sharing the chunks
+// of slot 0, read straight from memory.  Runs once per decode.
 template <int S>
-__device__ __noinline__ uint32_t pass_f_fn(uint32_t wsm, double* gw, int lane, uint32_t rphase, int lv, bool coop)
+__device__ __noinline__ void pass_f_coop_fn(uint32_t wsm, double* gw, int lane, int lv)
 {
-    Lane T;
-    T.wsm = wsm; T.gw = gw; T.lane = lane; T.rphase = rphase;
-    pass_f_body<S>(T, lv, coop);
-    return T.rphase;
+    Lane L;
+    L.wsm = wsm; L.gw = gw; L.lane = lane;
+    const int s = 1 << (10 - lv), q = s >> 1;
+    const int nch = s >> 2;
+    const unsigned char* base;
+    uint32_t rs, col;
+    if (lv == 1) {
+        base = reinterpret_cast<const unsigned char*>(gw + SclLY::G_ROWS * 32);
+        rs = 32u;
+        col = (uint32_t)(lane >> 3) * 8u;
+    } else {
+        base = reinterpret_cast<const unsigned char*>(gw + (size_t)lvl_row0(lv - 1) * 32);
+        rs = 256u;
+        col = (uint32_t)L.gbase() * 8u;
+    }
+    const bool nat = lv >= S;
+    double* fdst = nat ? slvl<S>(L, lv, 0) : L.ga() + lvl_row0(lv) * 32;
+    const int half = nch >> 1;
+#pragma unroll 1
+    for (int c = L.p(); c < nch; c += 8) {
+        double* fd = nat ? fdst + 2 * c * 32 : fdst + ((c < half) ? 8 * c : 8 * (c - half) + 1) * 32;   // f[r]
+        const int dq = nat ? q * 32 : 2 * 32, d1 = nat ? 32 : 4 * 32;                                        // f[r+q], f[r+1]
+        const unsigned char* src = base + (size_t)c * 8u * rs + col;
+        double v[8], r0, r1;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = *reinterpret_cast<const double*>(src + (size_t)i * rs);
+        fcomb2(v[0], v[2], v[1], v[3], L.tab(), r0, r1);       // f[r], f[r+q]
+        fd[0] = r0; fd[dq] = r1;
+        fcomb2(v[4], v[6], v[5], v[7], L.tab(), r0, r1);       // f[r+1], f[r+1+q]
+        fd[d1] = r0; fd[d1 + dq] = r1;
+    }
 }
 template <int S>
 __device__ __forceinline__ void pass_f(Lane& L, int lv, bool coop)
 {
-    L.rphase = pass_f_fn<S>(L.wsm, L.gw, L.lane, L.rphase, lv, coop);
+    if (coop) pass_f_coop_fn<S>(L.wsm, L.gw, L.lane, lv);
+    else L.rphase = pass_f_fn<S>(L.wsm, L.gw, L.lane, L.rphase, lv);
     L.ptr = (L.ptr & ~(7u << (3 * (lv - 1)))) | ((uint32_t)(coop ? 0 : L.p()) << (3 * (lv - 1)));
 }
 
@@ -668,11 +686,11 @@ __device__ __noinline__ double r0_sum(const double* a, int lq, int count, uint32
     for (int k = 0; k < count; k += 4) {
         const double* e = a + ((lq < 0) ? k : (((k & ((1 << lq) - 1)) << 2) | (k >> lq))) * 32;
         const double a0 = e[0], a1 = e[step], a2 = e[2 * step], a3 = e[3 * step];
-        const D4 P = lse4(fmax(a0, 0.0), a0, fmax(a1, 0.0), a1, fmax(a2, 0.0), a2, fmax(a3, 0.0), a3, tab);   // phi takes |a| itself
-        s0 += P.a;
-        s1 += P.b;
-        s2 += P.c;
-        s3 += P.d;
+        const D4 P = psi4(a0, a1, a2, a3);            // ln(1 + e^a) = a/2 + psi(a)
+        s0 += __fma_rn(a0, 0.5, P.a);
+        s1 += __fma_rn(a1, 0.5, P.b);
+        s2 += __fma_rn(a2, 0.5, P.c);
+        s3 += __fma_rn(a3, 0.5, P.d);
     }
     return (s0 + s1) + (s2 + s3);
 }
@@ -696,9 +714,42 @@ struct Carry { double c0, c1, c2, c3; uint32_t qb; };
 // pen0/pen1 = penalties of deciding 0 / 1 (rtwm/fastpolar.py:32-40).  Metrics are non-negative finite
 // doubles, so their bit patterns order like unsigned integers; the reference's stable tie-break
 // (candidate index 2*ord+bit) folds into the comparison as  (kj < k) + (kj == k && c) == (kj < k + c).
-#ifndef ES_SCL_RANK_FP
-#define ES_SCL_RANK_FP 1     // candidate ranking with FP64 compares (2 DSETP per pair) instead of 64-bit integer compares
+#ifndef ES_SCL_NTH_LUT
+#define ES_SCL_NTH_LUT 1     // clone-source lookup (n-th set bit of the clone mask) from a 2 KB shared table
 #endif
+#ifndef ES_SCL_LOCKSTEP
+#define ES_SCL_LOCKSTEP 0    // n > 0 (power of two): CTA barrier every n quads
+#endif
+#ifndef ES_SCL_RANK_KEY
+#define ES_SCL_RANK_KEY 1    // 1: unique 64-bit integer keys exchanged through shared memory; 0: FP64 compares over shuffles
+#endif
+// general ranking of the 16 candidates of a codeword by (metric, path order, bit): the reference's stable tie-break
+// (candidate index 2*ord+bit) makes "<" a "<=" against later candidates
+__device__ __forceinline__ void rank_ties_body(double k0, double k1, int ord, int& r0, int& r1)
+{
+    const unsigned full = 0xffffffffu;
+    r0 = 0; r1 = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const double k0j = __shfl_sync(full, k0, j, 8);
+        const double k1j = __shfl_sync(full, k1, j, 8);
+        const int oj = __shfl_sync(full, ord, j, 8);
+        const bool lt = oj < ord, le = oj <= ord;
+        r0 += (int)((k0j < k0) || (lt && k0j == k0)) + (int)((k1j < k0) || (lt && k1j == k0));
+        r1 += (int)((k0j < k1) || (le && k0j == k1)) + (int)((k1j < k1) || (lt && k1j == k1));
+    }
+}
+// The same order as ONE unsigned 64-bit key per candidate.  A path metric is a sum of penalties that are each 0 or
+// >= 2^-54 (phi_fast is exactly 0 or >= 2^-53; |leaf| is only added on top of phi), so it is 0 or >= 2^-54 and < 2^64: its
+// exponent field spans fewer than 128 values above 960 and the bit pattern, rebased there, leaves four low bits for the
+// candidate index.  Keys are unique, so the rank is a plain count of smaller keys.
+__device__ __forceinline__ unsigned long long rank_key(double m, uint32_t cand)
+{
+    uint32_t hi = (uint32_t)__double2hiint(m), lo = (uint32_t)__double2loint(m);
+    hi = max(hi, 0x3C000000u) - 0x3C000000u;                    // exact zero stays zero (its low word is zero)
+    return ((((unsigned long long)hi << 32) | lo) << 4) | cand;
+}
+
 // carry: the quad-local values have to follow a clone only after an EVEN leaf (the odd leaf right after it reads
 // c0, c1 and - a clone always took bit 1 - c2); after an odd leaf nothing of them is read again.
 template <bool MG>
@@ -707,33 +758,28 @@ __device__ __forceinline__ int info_step(Lane& L, int list_size, double pen0, do
     const unsigned full = 0xffffffffu;
     const double m0 = L.m + pen0, m1 = L.m + pen1;
     int r0 = 0, r1 = 0;
-#if ES_SCL_RANK_FP
-    // metrics are non-negative finite doubles; candidates of inactive lanes are +inf: never "before" anything.
-    // The reference's stable tie-break (candidate index 2*ord+bit) makes "<" a "<=" against later candidates.
-    const double k0 = L.active ? m0 : CUDART_INF, k1 = L.active ? m1 : CUDART_INF;
+#if ES_SCL_RANK_KEY
+    {
+        const unsigned long long k0 = L.active ? rank_key(m0, 2u * (uint32_t)L.ord) : ~0ull;
+        const unsigned long long k1 = L.active ? rank_key(m1, 2u * (uint32_t)L.ord + 1u) : ~0ull;
+        // exchange through the warp's stash area (idle outside the LLR update): 16 bytes per lane, broadcast reads
+        const uint32_t xa = L.wsm + (uint32_t)SclLY::STASH_OFF;
+        asm volatile("st.shared.v2.u64 [%0], {%1, %2};" ::"r"(xa + (uint32_t)L.lane * 16u), "l"(k0), "l"(k1) : "memory");
+        __syncwarp();
+        const uint32_t xg = xa + (uint32_t)L.gbase() * 16u;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const double k0j = __shfl_sync(full, k0, j, 8);
-        const double k1j = __shfl_sync(full, k1, j, 8);
-        const int oj = __shfl_sync(full, L.ord, j, 8);
-        const bool lt = oj < L.ord, le = oj <= L.ord;
-        r0 += (int)((k0j < k0) || (lt && k0j == k0)) + (int)((k1j < k0) || (lt && k1j == k0));
-        r1 += (int)((k0j < k1) || (le && k0j == k1)) + (int)((k1j < k1) || (lt && k1j == k1));
+        for (int j = 0; j < 8; ++j) {
+            unsigned long long k0j, k1j;
+            asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(k0j), "=l"(k1j) : "r"(xg + 16u * j) : "memory");
+            r0 += (int)(k0j < k0) + (int)(k1j < k0);
+            r1 += (int)(k0j < k1) + (int)(k1j < k1);
+        }
     }
 #else
-    // bit patterns of non-negative doubles order like unsigned integers; the tie-break folds into the comparison as
-    // (kj < k) + (kj == k && c) == (kj < k + c)
-    const unsigned long long k0 = L.active ? (unsigned long long)__double_as_longlong(m0) : ~0ull;
-    const unsigned long long k1 = L.active ? (unsigned long long)__double_as_longlong(m1) : ~0ull;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const unsigned long long k0j = __shfl_sync(full, k0, j, 8);
-        const unsigned long long k1j = __shfl_sync(full, k1, j, 8);
-        const int oj = __shfl_sync(full, L.ord, j, 8);
-        const unsigned long long lt = (oj < L.ord) ? 1ull : 0ull, le = (oj <= L.ord) ? 1ull : 0ull;
-        const unsigned long long a0 = k0 + lt, a1 = k1 + le, a2 = k1 + lt;
-        r0 += (k0j < a0) + (k1j < a0);
-        r1 += (k0j < a1) + (k1j < a2);
+    {
+        // metrics are non-negative finite doubles; candidates of inactive lanes are +inf: never "before" anything.
+        const double k0 = L.active ? m0 : CUDART_INF, k1 = L.active ? m1 : CUDART_INF;
+        rank_ties_body(k0, k1, L.ord, r0, r1);
     }
 #endif
     if (MG) {
@@ -757,7 +803,16 @@ __device__ __forceinline__ int info_step(Lane& L, int list_size, double pen0, do
     // clone source for free lanes (j-th free lane takes the j-th clone)
     const int jfree = __popc(fm & ((1u << L.p()) - 1u));
     const bool take = !(s0 || s1) && (jfree < __popc(cm));
+#if ES_SCL_NTH_LUT
+    int src = L.p();
+    if (take) {
+        uint32_t v;
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(smem_base() + (uint32_t)SclLY::NTH_OFF + cm * 8u + (uint32_t)jfree) : "memory");
+        src = (int)v;
+    }
+#else
     const int src = take ? nth_set8(cm, jfree) : L.p();
+#endif
     const double cm1 = __shfl_sync(full, m1, src, 8);
     const int cr1 = __shfl_sync(full, r1, src, 8);
     const uint32_t cptr = __shfl_sync(full, L.ptr, src, 8);
@@ -863,6 +918,7 @@ __global__ void __maxnreg__(ES_SCL_MAXNREG) scl_list_kernel(SclParams P)
     {
         double* st = reinterpret_cast<double*>(smem_raw);
         for (int q = threadIdx.x; q < PHI_TAB_DOUBLES; q += W * 32) st[q] = P.phi_tab[q];
+        for (int q = threadIdx.x; q < 2048; q += W * 32) smem_raw[LY::NTH_OFF + q] = (unsigned char)nth_set8((uint32_t)(q >> 3), q & 7);
     }
     const int warp = threadIdx.x >> 5;
     Lane L;
@@ -885,7 +941,12 @@ __global__ void __maxnreg__(ES_SCL_MAXNREG) scl_list_kernel(SclParams P)
 #define gscr (L.gw)
 
 #pragma unroll 1
+#if ES_SCL_LOCKSTEP
+    for (int grp0 = blockIdx.x * W; grp0 < ((P.nunits + 3) >> 2); grp0 += gridDim.x * W) {
+        const int grp = grp0 + warp;                   // every warp of the CTA runs every trip (surplus warps redo the last unit, unwritten)
+#else
     for (int grp = blockIdx.x * W + warp; grp < ((P.nunits + 3) >> 2); grp += gridDim.x * W) {
+#endif
         const int j = grp * 4 + (L.lane >> 3);
         bool valid = j < P.nunits;
         const int jj = valid ? j : (P.nunits - 1);
@@ -910,6 +971,9 @@ __global__ void __maxnreg__(ES_SCL_MAXNREG) scl_list_kernel(SclParams P)
 #pragma unroll 1
         for (int q = qfirst; q < 256; ++q) {
             const int i = q << 2;
+#if ES_SCL_LOCKSTEP
+            if ((q & (ES_SCL_LOCKSTEP - 1)) == 0) __syncthreads();   // all warps of the CTA in the same loops: one hot code region per SM
+#endif
             if (q == 128 && P.pair && pass == 0) {
                 // bit 512: everything the second half reads from the first half is the level-1 partial sums
                 // (global rows, never rewritten) plus these per-lane words
@@ -977,7 +1041,7 @@ __global__ void __maxnreg__(ES_SCL_MAXNREG) scl_list_kernel(SclParams P)
                     }
                     // even leaf: f of the pair; its two phi terms are the odd leaf's penalty terms
                     leaf = fcomb_parts(x0, x1, L.tab(), fm, fp);
-                    ph = phi1(leaf, L.tab());
+                    ph = phi1(leaf);
                     cy.c0 = x0; cy.c1 = x1; cy.c2 = fm; cy.c3 = fp;
                 } else {
                     // odd leaf: g of the pair
