@@ -141,6 +141,26 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
                      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     } while (!ok);
 }
+#ifndef ES_SCL_L2HINT
+#define ES_SCL_L2HINT 1      // 1: levels 1..2 (written once, read once, far apart) travel evict_first; 2: also levels 3..5 evict_last
+#endif
+__device__ __forceinline__ uint64_t l2_policy(int kind)     // 0 normal, 1 evict_first, 2 evict_last
+{
+    uint64_t p;
+    if (kind == 1) asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    else if (kind == 2) asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    else asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void bulk_g2s_hint(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t pol)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void stg_hint(double* p, double v, uint64_t pol)
+{
+    asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(pol) : "memory");
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar)
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -406,11 +426,15 @@ __device__ __noinline__ void negate_level0(double* l0)
 #endif
 
 // lane 0: queue one stage
-__device__ __forceinline__ void ring_issue(const Lane& L, int st, const void* src, uint32_t bytes)
+__device__ __forceinline__ void ring_issue(const Lane& L, int st, const void* src, uint32_t bytes, uint64_t pol)
 {
     const uint32_t bar = L.rbar() + 8u * st;
     mbar_expect_tx(bar, bytes);
+#if ES_SCL_L2HINT
+    bulk_g2s_hint(L.ring(st), src, bytes, bar, pol);
+#else
     bulk_g2s(L.ring(st), src, bytes, bar);
+#endif
 }
 
 // All lanes hold the eight values of the current stage in registers: the stage may be refilled.  A plain
@@ -436,15 +460,20 @@ template <int RS> struct Ring {
     uint32_t ph;                 // parity the next wait has to see
     int st;                      // stage of the next chunk
     int left;                    // chunks not queued yet
+    uint64_t pol;                // L2 policy of the source node (ES_SCL_L2HINT)
 
-    __device__ __forceinline__ void begin(const Lane& L, const unsigned char* base, uint32_t col, int nch, uint32_t ph0)
+    __device__ __forceinline__ void begin(const Lane& L, const unsigned char* base, uint32_t col, int nch, uint32_t ph0, int srclvl)
     {
+        pol = 0;
+#if ES_SCL_L2HINT
+        pol = l2_policy((srclvl >= 1 && srclvl <= 2) ? 1 : ((ES_SCL_L2HINT >= 2 && srclvl >= 3) ? 2 : 0));
+#endif
         col0 = L.ring(0) + col; col1 = L.ring(1) + col; bar = L.rbar(); ph = ph0; st = 0;
         fence_proxy_async();      // the node was written with ordinary stores (this warp, earlier passes)
         __syncwarp();
         if (L.lane == 0) {
-            ring_issue(L, 0, base, 8u * RS);
-            ring_issue(L, 1, base + 8u * RS, 8u * RS);
+            ring_issue(L, 0, base, 8u * RS, pol);
+            ring_issue(L, 1, base + 8u * RS, 8u * RS, pol);
         }
         __syncwarp();
         next = base + 16u * RS;
@@ -460,7 +489,7 @@ template <int RS> struct Ring {
     __device__ __forceinline__ void refill(const Lane& L, int w)
     {
         ring_release(w);
-        if (L.lane == 0 && left > 0) ring_issue(L, st, next, 8u * RS);
+        if (L.lane == 0 && left > 0) ring_issue(L, st, next, 8u * RS, pol);
         next += 8u * RS;
         --left;
         ph ^= (uint32_t)st;
@@ -483,9 +512,13 @@ __device__ __forceinline__ uint32_t pass_gf_body(const Lane& L, int l0, bool do_
     const int s = 1 << (10 - l0), h = s >> 1;
     const int nch = h >> 1;
     Ring<RS> R;
-    if (RS == 32) R.begin(L, reinterpret_cast<const unsigned char*>(L.gw + SclLY::G_ROWS * 32), (uint32_t)(L.lane >> 3) * 8u, nch, L.rphase);
+    if (RS == 32) R.begin(L, reinterpret_cast<const unsigned char*>(L.gw + SclLY::G_ROWS * 32), (uint32_t)(L.lane >> 3) * 8u, nch, L.rphase, 0);
     else R.begin(L, reinterpret_cast<const unsigned char*>(L.gw + (size_t)lvl_row0(l0 - 1) * 32),
-                 (uint32_t)(L.gbase() + ((L.ptr >> (3 * (l0 - 2))) & 7)) * 8u, nch, L.rphase);
+                 (uint32_t)(L.gbase() + ((L.ptr >> (3 * (l0 - 2))) & 7)) * 8u, nch, L.rphase, l0 - 1);
+#if ES_SCL_L2HINT
+    const uint64_t gpol = l2_policy((l0 <= 2) ? 1 : ((ES_SCL_L2HINT >= 2) ? 2 : 0));
+    const uint64_t fpol = l2_policy((l0 + 1 <= 2) ? 1 : ((ES_SCL_L2HINT >= 2) ? 2 : 0));
+#endif
     // outputs, as running pointers.  g[k] sits at row 8c (c < nch/2) or 8(c - nch/2) + 1, g[k+h] 2 rows, g[k+1] 4 rows,
     // g[k+1+h] 6 rows further.  f[k]: natural order in shared memory (row k, f[k+1] one row further), or quarter-
     // interleaved in global memory: quarter j = c / (nch/4), row 8(c mod nch/4) + j, f[k+1] four rows further.
@@ -526,12 +559,20 @@ __device__ __forceinline__ uint32_t pass_gf_body(const Lane& L, int l0, bool do_
         const double g0 = gcomb(v0, v2, w0 & 1u), gh0 = gcomb(v1, v3, w1 & 1u);
         const double g1 = gcomb(v4, v6, (w0 >> 1) & 1u), gh1 = gcomb(v5, v7, (w1 >> 1) & 1u);
         w0 >>= 2; w1 >>= 2;
+#if ES_SCL_L2HINT
+        stg_hint(gd, g0, gpol); stg_hint(gd + 2 * 32, gh0, gpol); stg_hint(gd + 4 * 32, g1, gpol); stg_hint(gd + 6 * 32, gh1, gpol);
+#else
         gd[0] = g0; gd[2 * 32] = gh0; gd[4 * 32] = g1; gd[6 * 32] = gh1;
+#endif
         gd += 8 * 32;
         if (do_f) {
             double r0, r1;
             fcomb2_inl(g0, gh0, g1, gh1, tab, r0, r1);
-            fd[0] = r0; fd[f1] = r1;
+#if ES_SCL_L2HINT
+            if (!nat) { stg_hint(fd, r0, fpol); stg_hint(fd + f1, r1, fpol); }
+            else
+#endif
+            { fd[0] = r0; fd[f1] = r1; }
             fd += fstep;
         }
     }
@@ -568,7 +609,7 @@ __device__ ES_PASS_INLINE uint32_t pass_f_fn(uint32_t wsm, double* gw, int lane,
     const int s = 1 << (10 - lv), q = s >> 1;
     const int nch = s >> 2;
     Ring<256> R;
-    R.begin(L, reinterpret_cast<const unsigned char*>(gw + (size_t)lvl_row0(lv - 1) * 32), (uint32_t)lane * 8u, nch, rphase);
+    R.begin(L, reinterpret_cast<const unsigned char*>(gw + (size_t)lvl_row0(lv - 1) * 32), (uint32_t)lane * 8u, nch, rphase, lv - 1);
     // f[r]: natural order in shared memory (row r; f[r+q] q rows, f[r+1] one row further) or quarter-interleaved in
     // global memory: row 8c (c < nch/2) or 8(c - nch/2) + 1, f[r+q] two rows, f[r+1] four rows further
     const bool nat = lv >= S;
