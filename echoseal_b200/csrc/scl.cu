@@ -63,11 +63,95 @@ struct D2 { double a, b; };
 // The routines take the shared-window address of the phi tables from the CTA's dynamic shared memory base themselves
 // (a uniform register: the table reads are [index + base] with no address add per evaluation).
 __device__ __forceinline__ uint32_t smem_base();
+// N evaluations of psi_fast step by step in lock-step (the operation sequence of phi_impl.h per element, bit for bit):
+// written interleaved so that the schedule does not depend on how ptxas happens to merge N separate call chains.
+#ifndef ES_SCL_F_PSI
+#define ES_SCL_F_PSI 1       // 1: f = psi(a-b) - psi(a+b); 0: the reference's two logaddexp terms with their own rounding points (15 % slower)
+#endif
+// PSI: out = |x|/2 + phi(|x|); otherwise out = mx + phi(|x|), the reference's logaddexp term (max + log1p(exp(-|d|))).
+template <int N, bool PSI>
+__device__ __forceinline__ void psi_lockstep(const double (&x)[N], const double (&mx)[N], double (&out)[N], uint32_t tab)
+{
+    const double SHIFT = 6755399441055744.0;
+    double dd[N], ax[N], kd[N], r[N], q[N], p[N], th[N], t[N], u[N], ic[N], lc[N], rr[N], w[N];
+    int32_t ki[N];
+#pragma unroll
+    for (int c = 0; c < N; ++c) {
+        uint32_t dhi = PHI_HI(x[c]) & 0x7fffffffu;
+        ax[c] = PHI_HILO(dhi, PHI_LO(x[c]));
+        dhi = dhi < 0x40500000u ? dhi : 0x40500000u;
+        dd[c] = PHI_HILO(dhi, PHI_LO(x[c]));
+    }
+#pragma unroll
+    for (int c = 0; c < N; ++c) kd[c] = PHI_FMA(-dd[c], PHI_K(0), SHIFT);
+#pragma unroll
+    for (int c = 0; c < N; ++c) { ki[c] = (int32_t)PHI_LO(kd[c]); kd[c] -= SHIFT; }
+#pragma unroll
+    for (int c = 0; c < N; ++c) r[c] = PHI_FMA(kd[c], -PHI_K(1), -dd[c]);
+#pragma unroll
+    for (int c = 0; c < N; ++c) r[c] = PHI_FMA(kd[c], -PHI_K(2), r[c]);
+#pragma unroll
+    for (int c = 0; c < N; ++c) { const double th0 = PHI_LD(tab, PHI_OFF_EXP + (ki[c] & 63)); th[c] = PHI_HILO(PHI_EXPADD(PHI_HI(th0), ki[c]), PHI_LO(th0)); }
+#pragma unroll
+    for (int c = 0; c < N; ++c) q[c] = PHI_FMA(r[c], PHI_K(3), PHI_K(4));
+#pragma unroll
+    for (int c = 0; c < N; ++c) q[c] = PHI_FMA(r[c], q[c], PHI_K(5));
+#pragma unroll
+    for (int c = 0; c < N; ++c) q[c] = PHI_FMA(r[c], q[c], 0.5);
+#pragma unroll
+    for (int c = 0; c < N; ++c) p[c] = PHI_FMA(r[c] * r[c], q[c], r[c]);
+#pragma unroll
+    for (int c = 0; c < N; ++c) t[c] = PHI_FMA(th[c], p[c], th[c]);
+#pragma unroll
+    for (int c = 0; c < N; ++c) u[c] = 1.0 + t[c];
+#pragma unroll
+    for (int c = 0; c < N; ++c) { const int i = (int)(PHI_HI(u[c]) >> 11) - 0x7fe00; PHI_LD2(tab, PHI_OFF_LOGP, i, ic[c], lc[c]); }
+#pragma unroll
+    for (int c = 0; c < N; ++c) rr[c] = PHI_FMA(u[c], ic[c], -1.0);
+#pragma unroll
+    for (int c = 0; c < N; ++c) w[c] = PHI_FMA(rr[c], PHI_K(6), -0.25);
+#pragma unroll
+    for (int c = 0; c < N; ++c) w[c] = PHI_FMA(rr[c], w[c], PHI_K(7));
+#pragma unroll
+    for (int c = 0; c < N; ++c) w[c] = PHI_FMA(rr[c], w[c], -0.5);
+#pragma unroll
+    for (int c = 0; c < N; ++c) {
+        const double ph = lc[c] + PHI_FMA(rr[c] * rr[c], w[c], rr[c]);
+        out[c] = PSI ? PHI_FMA(ax[c], 0.5, ph) : mx[c] + ph;
+    }
+}
 __device__ __noinline__ D4 psi4(double x0, double x1, double x2, double x3)
 {
-    const uint32_t tab = smem_base();
+    const double x[4] = {x0, x1, x2, x3};
+    double o[4];
+    psi_lockstep<4, true>(x, x, o, smem_base());
     D4 r;
-    r.a = psi_fast(x0, tab); r.b = psi_fast(x1, tab); r.c = psi_fast(x2, tab); r.d = psi_fast(x3, tab);
+    r.a = o[0]; r.b = o[1]; r.c = o[2]; r.d = o[3];
+    return r;
+}
+// f of two element pairs in the reference's own form, numpy's npy_logaddexp terms max + log1p(exp(-|x-y|)) for (a,b) and
+// (0,a+b) with the reference's rounding points (rtwm/fastpolar.py:18-23): operands in, results out, nothing else live
+// across the call.  x == y needs no special case: phi_fast(0) == ln2 exactly (table entry 256).
+__device__ __noinline__ D2 f2(double a0, double b0, double a1, double b1)
+{
+    const double d0 = a0 - b0, s0 = a0 + b0, d1 = a1 - b1, s1 = a1 + b1;
+    const double x[4] = {d0, s0, d1, s1};
+    const double m[4] = {(d0 > 0.0) ? a0 : b0, ((0.0 - s0) > 0.0) ? 0.0 : s0, (d1 > 0.0) ? a1 : b1, ((0.0 - s1) > 0.0) ? 0.0 : s1};
+    double o[4];
+    psi_lockstep<4, false>(x, m, o, smem_base());
+    D2 r;
+    r.a = o[0] - o[1];
+    r.b = o[2] - o[3];
+    return r;
+}
+// four phi evaluations (the rate-0 node sums)
+__device__ __noinline__ D4 phi4(double x0, double x1, double x2, double x3)
+{
+    const double x[4] = {x0, x1, x2, x3}, z[4] = {0.0, 0.0, 0.0, 0.0};
+    double o[4];
+    psi_lockstep<4, false>(x, z, o, smem_base());
+    D4 r;
+    r.a = o[0]; r.b = o[1]; r.c = o[2]; r.d = o[3];
     return r;
 }
 __device__ __noinline__ D2 phi2(double d0, double d1)
@@ -83,9 +167,15 @@ __device__ __noinline__ double phi1(double d0) { return phi_fast(d0, smem_base()
 // has one): phi_fast(0) == ln2 exactly (table entry 256).
 __device__ __forceinline__ void fcomb2(double a0, double b0, double a1, double b1, uint32_t tab, double& r0, double& r1)
 {
+#if ES_SCL_F_PSI
     const D4 P = psi4(a0 - b0, a0 + b0, a1 - b1, a1 + b1);
     r0 = P.a - P.b;
     r1 = P.c - P.d;
+#else
+    const D2 Q = f2(a0, b0, a1, b1);
+    r0 = Q.a;
+    r1 = Q.b;
+#endif
 }
 // the same with the four chains inlined into the caller's loop (the passes over the DRAM-resident levels: no call, so
 // the loads, stores and g arithmetic of the loop schedule into the latency gaps of the chains)
@@ -112,7 +202,13 @@ __device__ __forceinline__ double fcomb_parts(double a, double b, uint32_t tab, 
     const D2 P = phi2(d, s);
     fm = P.a;
     fp = P.b;
+#if ES_SCL_F_PSI
     return __fma_rn(fabs(d), 0.5, fm) - __fma_rn(fabs(s), 0.5, fp);
+#else
+    const double A = ((d > 0.0) ? a : b) + fm;
+    const double B = (((0.0 - s) > 0.0) ? 0.0 : s) + fp;
+    return A - B;
+#endif
 }
 
 // g = b + (1-2u) a (rtwm/fastpolar.py:26-29): (1-2u)*a is exact, so flipping the sign bit of a is the same number
@@ -727,11 +823,19 @@ __device__ __noinline__ double r0_sum(const double* a, int lq, int count, uint32
     for (int k = 0; k < count; k += 4) {
         const double* e = a + ((lq < 0) ? k : (((k & ((1 << lq) - 1)) << 2) | (k >> lq))) * 32;
         const double a0 = e[0], a1 = e[step], a2 = e[2 * step], a3 = e[3 * step];
+#if ES_SCL_F_PSI
         const D4 P = psi4(a0, a1, a2, a3);            // ln(1 + e^a) = a/2 + psi(a)
         s0 += __fma_rn(a0, 0.5, P.a);
         s1 += __fma_rn(a1, 0.5, P.b);
         s2 += __fma_rn(a2, 0.5, P.c);
         s3 += __fma_rn(a3, 0.5, P.d);
+#else
+        const D4 P = phi4(a0, a1, a2, a3);            // ln(1 + e^a) = max(a, 0) + phi(|a|)
+        s0 += P.a + fmax(a0, 0.0);
+        s1 += P.b + fmax(a1, 0.0);
+        s2 += P.c + fmax(a2, 0.0);
+        s3 += P.d + fmax(a3, 0.0);
+#endif
     }
     return (s0 + s1) + (s2 + s3);
 }

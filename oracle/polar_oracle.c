@@ -69,7 +69,7 @@ static inline double np_logaddexp(double x, double y)
 
 static inline double f_comb(double a, double b)
 {
-#ifdef ORACLE_PHI_FAST
+#if defined(ORACLE_PHI_FAST) && defined(ORACLE_F_PSI)
     /* device model: the kernel's form of the same quantity, psi(a-b) - psi(a+b) with psi(x) = |x|/2 + phi(|x|)
      * (max(a,b) - max(0,a+b) = (|a-b| - |a+b|)/2); echoseal_b200/csrc/scl.cu fcomb2 */
     return psi_fast(a - b, g_phi_tab) - psi_fast(a + b, g_phi_tab);
@@ -254,7 +254,11 @@ int es_oracle_scl_decode(const double *llr, const uint8_t *frozen, int K, int L,
                     sc_step_llr_to(&P[p], llr, i, lv);
                     const double *a = &P[p].alpha[AOFF(lv)];
                     double acc[4] = {0.0, 0.0, 0.0, 0.0};
+#ifdef ORACLE_F_PSI
                     for (int k = 0; k < s; k++) acc[k & 3] += fma(a[k], 0.5, psi_fast(a[k], g_phi_tab));   /* ln(1 + e^a) = a/2 + psi(a) */
+#else
+                    for (int k = 0; k < s; k++) acc[k & 3] += phi(fabs(a[k])) + fmax(a[k], 0.0);
+#endif
                     P[p].metric += (acc[0] + acc[1]) + (acc[2] + acc[3]);
                     for (int k = 0; k < s; k++) sc_extend(&P[p], i + k, 0);
                 }

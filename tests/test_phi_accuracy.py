@@ -67,3 +67,34 @@ def test_monotone_on_a_fine_grid(lib):
     d = np.linspace(0, 40, 400001)
     fast, _ = _run(lib, d)
     assert (np.diff(fast) < 3e-16).all()
+
+
+def test_f_as_psi_difference_matches_the_reference_form(lib):
+    """The kernel forms f = logaddexp(a,b) - logaddexp(0,a+b) (rtwm/fastpolar.py:18-23) as psi(a-b) - psi(a+b) with
+    psi(x) = |x|/2 + phi(|x|).  Against mpmath on LLR-like operands the absolute error stays within a few ulp of the larger
+    operand — the error class of the reference's own two-logaddexp form — and psi is even, so f(-a,-b) == f(a,b) and
+    f(-a,b) == -f(a,b) hold bit for bit."""
+    import mpmath as mp
+    mp.mp.prec = 120
+    rng = np.random.default_rng(1)
+    a = np.concatenate([rng.uniform(-12, 12, 3000), rng.uniform(-60, 60, 1500), rng.uniform(-1e3, 1e3, 500)])
+    b = np.concatenate([rng.uniform(-12, 12, 3000), rng.uniform(-60, 60, 1500), rng.uniform(-1e3, 1e3, 500)])
+
+    def psi(x):
+        x = np.ascontiguousarray(x, np.float64); o = np.empty_like(x)
+        lib.psi_fast_array(x.ctypes.data_as(C.c_void_p), o.ctypes.data_as(C.c_void_p), C.c_int(x.size))
+        return o
+    f = psi(a - b) - psi(a + b)
+    ref_form = np.logaddexp(a, b) - np.logaddexp(0.0, a + b)
+    worst = worst_ref = 0.0
+    for x, y, v, r in zip(a, b, f, ref_form):
+        X, Y = mp.mpf(float(x)), mp.mpf(float(y))
+        ex = mp.log((mp.exp(X) + mp.exp(Y)) / (1 + mp.exp(X + Y))) if abs(x) + abs(y) < 600 else None
+        if ex is None:
+            continue
+        ulp = np.spacing(max(abs(x), abs(y), 1.0))
+        worst = max(worst, abs(float(mp.mpf(float(v)) - ex)) / ulp)
+        worst_ref = max(worst_ref, abs(float(mp.mpf(float(r)) - ex)) / ulp)
+    print(f"f as psi difference: max error {worst:.2f} ulp of the larger operand; numpy two-logaddexp form: {worst_ref:.2f}")
+    assert worst < 4.0
+    assert (psi(-(a - b)) == psi(a - b)).all()

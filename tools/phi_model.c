@@ -16,3 +16,4 @@ void phi_libm_array(const double* d, double* out, int n)
 {
     for (int k = 0; k < n; k++) out[k] = log1p(exp(-d[k]));
 }
+void psi_fast_array(const double* d, double* out, int n) { if (!g_init) { phi_fill_table(g_tab); g_init = 1; } for (int i = 0; i < n; ++i) out[i] = psi_fast(d[i], g_tab); }
