@@ -234,6 +234,194 @@ __global__ void __launch_bounds__(256, 4) ncc_kernel(const double* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------
+// K1+K2 fused (es_rx_scan): band-pass and normalised correlation in one pass; the filtered signal never leaves the SM.
+// One WARP per (clip, band, 32 consecutive chunks), one lane per chunk, as in K1: the lane runs the order-8 recurrence over
+// its chunk (768-sample zero-state warm-up, same chunk grid as K1, so the samples are bit-identical to K1's) and keeps
+// the last 64..96 filtered samples of its chunk in a shared-memory history [slot][lane]; after every 8 new samples it
+// forms the 8 correlations that have become complete (their 63-sample windows end inside the new samples) exactly like
+// K2: 8 consecutive outputs from a 70-sample register window, shared energy core + head/tail squares.  A chunk's last
+// 62 windows reach into the next chunk: the lane simply filters 64 samples further (its own recurrence: those samples
+// differ from the neighbour's by the 4e-13 warm-up truncation at most).  Input rows arrive by 16-byte cp.async
+// (zero-filled outside the clip), double-buffered; results leave through a transposing tile, 128-byte row segments.
+// Per sample and band: 4 B read (x, once per band, L2-served for three of them) + 8 B written, against K1+K2's 8 + 16.
+// ---------------------------------------------------------------------------------------------
+constexpr int SC_L = 96;                     // history slots per lane
+constexpr int SC_KEEP = 64;                  // slots carried over when the history wraps (>= 62)
+constexpr int SC_XP = 20;                    // floats per input row in shared memory (16 + pad: conflict-free 16-byte reads)
+constexpr int SC_EXTRA = 64;                 // samples filtered beyond the chunk for its last windows
+struct ScanShared {
+    double ring[SC_L][32];
+    double out[32][17];
+    float xin[2][32][SC_XP];
+};
+
+template <bool ODDZ, bool ALIGNED>
+__global__ void __launch_bounds__(32) scan_kernel(const float* __restrict__ x, int nclips, int n, long long x_stride,
+                                                  double* __restrict__ corr, long long corr_pitch, int ch, int groups)
+{
+    extern __shared__ __align__(16) unsigned char scan_raw[];
+    ScanShared& S = *reinterpret_cast<ScanShared*>(scan_raw);
+    const int lane = threadIdx.x;
+    const long long wid = blockIdx.x;                    // ((clip * groups) + grp) * 4 + band: the four bands of a chunk group are neighbours (x from L2)
+    const int band = (int)(wid & 3);
+    const int grp = (int)((wid >> 2) % groups);
+    const long long clip = (wid >> 2) / groups;
+    const int nc = n - (PRE_L - 1);
+    const float* xs = x + clip * x_stride;
+    double* cs = corr + (clip * NBANDS + band) * corr_pitch;
+    const int chunk0 = grp * 32;
+    const long long c0 = (long long)(chunk0 + lane) * ch;          // first sample of this lane's chunk
+    double bb[5], aa[8];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) bb[i] = c_bp_b[band][2 * i];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) aa[i] = -c_bp_a[band][i + 1];
+    double bo[4] = {0.0, 0.0, 0.0, 0.0};
+    if (!ODDZ) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) bo[i] = c_bp_b[band][2 * i + 1];
+    }
+    double z[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) z[i] = 0.0;
+
+    const int nstages = (BP_WARM + ch + SC_EXTRA) / 16;            // ch % 16 == 0
+    auto fetch = [&](int sg) {
+        const long long g0 = c0 - BP_WARM + 16LL * sg;              // multiple of 16
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&S.xin[sg & 1][lane][0]);
+        if (ALIGNED) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const long long g = g0 + 4 * i;
+                long long left = (long long)n - g;                  // samples of the clip at and after g
+                const int bytes = (g < 0 || left <= 0) ? 0 : (left >= 4 ? 16 : (int)left * 4);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + 16 * i), "l"(xs + (bytes ? g : 0)), "r"(bytes));
+            }
+        } else {
+#pragma unroll 4
+            for (int i = 0; i < 16; ++i) {
+                const long long g = g0 + i;
+                const bool in = (g >= 0 && g < n);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + 4 * i), "l"(xs + (in ? g : 0)), "r"(in ? 4 : 0));
+            }
+        }
+        asm volatile("cp.async.commit_group;");
+    };
+    fetch(0);
+    int w = 0;                    // history write position
+    int t = -BP_WARM;             // time of the next sample, relative to the chunk start
+    int R = 0;                    // next correlation index, relative to the chunk start
+#pragma unroll 1
+    for (int sg = 0; sg < nstages; ++sg) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        if (sg + 1 < nstages) fetch(sg + 1);
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            const float4 xa = *reinterpret_cast<const float4*>(&S.xin[sg & 1][lane][8 * half]);
+            const float4 xb = *reinterpret_cast<const float4*>(&S.xin[sg & 1][lane][8 * half + 4]);
+            const float xv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+            double yv[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                // direct form II transposed, the operation order of K1 / scipy's lfilter
+                const double xn = (double)xv[q];
+                const double yn = fma(bb[0], xn, z[0]);
+#pragma unroll
+                for (int i = 0; i < 7; ++i) {
+                    const double zi = (i & 1) ? fma(bb[(i + 1) >> 1], xn, z[i + 1]) : (ODDZ ? z[i + 1] : fma(bo[i >> 1], xn, z[i + 1]));
+                    z[i] = fma(aa[i], yn, zi);
+                }
+                z[7] = fma(aa[7], yn, bb[4] * xn);
+                yv[q] = yn;
+            }
+            if (t >= 0) {
+                if (w == SC_L) {          // history full: carry the last SC_KEEP samples to the front
+#pragma unroll 8
+                    for (int k = 0; k < SC_KEEP; ++k) S.ring[k][lane] = S.ring[SC_L - SC_KEEP + k][lane];
+                    w = SC_KEEP;
+                }
+#pragma unroll
+                for (int q = 0; q < 8; ++q) S.ring[w + q][lane] = yv[q];
+                w += 8;
+            }
+            t += 8;
+            if (t >= R + 72 && R < ch) {
+                // correlations R .. R+7 of this chunk: windows y[R+q .. R+q+62], history slots w-72 .. w-3
+                const double* hv = &S.ring[w - 72][lane];
+#define SC_V(m) hv[(m) * 32]
+                double d[8], win[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) d[q] = 0.0;
+#pragma unroll
+                for (int q = 0; q < 7; ++q) win[q] = SC_V(q);
+                double core = 0.0;                          // sum of v[m]^2, m = 7..62: common to the 8 windows
+#pragma unroll
+                for (int k = 0; k < PRE_L; ++k) {
+                    win[(k + 7) & 7] = SC_V(k + 7);
+                    const double wk = c_tpl[band][k];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) d[q] = fma(win[(k + q) & 7], wk, d[q]);
+                    if (k >= 7) { const double v = win[k & 7]; core = fma(v, v, core); }
+                }
+                double head[8], tail[8];
+                head[7] = 0.0;
+#pragma unroll
+                for (int q = 6; q >= 0; --q) { const double v = SC_V(q); head[q] = fma(v, v, head[q + 1]); }
+                tail[0] = 0.0;
+#pragma unroll
+                for (int q = 1; q < 8; ++q) { const double v = SC_V(PRE_L - 1 + q); tail[q] = fma(v, v, tail[q - 1]); }
+#undef SC_V
+                const int o8 = R & 8;                       // two tiles per output row of 16
+#pragma unroll
+                for (int q = 0; q < 8; ++q) S.out[lane][o8 + q] = d[q] / (sqrt((head[q] + core) + tail[q]) + 1e-12);
+                if (o8) {
+                    __syncwarp();
+                    const int col = lane & 15;
+                    const long long r0 = (long long)(R - 8 + col);      // index inside the chunk
+#pragma unroll 4
+                    for (int r = lane >> 4; r < 32; r += 2) {
+                        const long long i = (long long)(chunk0 + r) * ch + r0;
+                        if (i < nc) cs[i] = S.out[r][col];
+                    }
+                    __syncwarp();
+                }
+                R += 8;
+            }
+        }
+    }
+}
+
+// Band-passed samples of the candidate frames only (K4's input once the scan no longer writes y): thread per
+// (clip, band, peak slot), the recurrence from 768 samples before the frame (zero state; exact from the clip start).
+__global__ void __launch_bounds__(32) frame_bandpass_kernel(const float* __restrict__ x, int n, long long x_stride,
+                                                            const int32_t* __restrict__ peaks, const int32_t* __restrict__ npeaks,
+                                                            double* __restrict__ yfr /*[clips][4][25][FRAME_LEN]*/)
+{
+    const int cb = blockIdx.x, slot = threadIdx.x;
+    if (slot >= PEAK_LIMIT || slot >= npeaks[cb]) return;
+    const int band = cb & 3;
+    const long long clip = cb >> 2;
+    const int start = peaks[(long long)cb * PEAK_LIMIT + slot];
+    if (start < 0 || start + FRAME_LEN > n) return;
+    const float* xs = x + clip * x_stride;
+    double* out = yfr + ((long long)cb * PEAK_LIMIT + slot) * FRAME_LEN;
+    double z[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) z[i] = 0.0;
+    const int t0 = max(0, start - BP_WARM);
+#pragma unroll 1
+    for (int j = t0; j < start + FRAME_LEN; ++j) {
+        const double xn = (double)__ldg(xs + j);
+        const double yn = fma(c_bp_b[band][0], xn, z[0]);
+#pragma unroll
+        for (int i = 0; i < 7; ++i) z[i] = fma(-c_bp_a[band][i + 1], yn, fma(c_bp_b[band][i + 1], xn, z[i + 1]));
+        z[7] = fma(-c_bp_a[band][8], yn, c_bp_b[band][8] * xn);
+        if (j >= start) out[j - start] = yn;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // K3: exact order statistics + NMS.  One CTA of 1024 threads per (clip, band).
 // ---------------------------------------------------------------------------------------------
 constexpr int PK_THREADS = 512;        // two CTAs (rows) per SM: one row's serial decisions overlap the other's streaming passes
@@ -1135,7 +1323,7 @@ __device__ __forceinline__ void conv_block(const double* __restrict__ sig, int n
     }
 }
 
-__global__ void __launch_bounds__(FR_THREADS) frames_kernel(const double* __restrict__ y, int n,
+__global__ void __launch_bounds__(FR_THREADS) frames_kernel(const double* __restrict__ y, int n, int framed,
                                                             const int32_t* __restrict__ peaks,
                                                             const int32_t* __restrict__ npeaks,
                                                             const uint8_t* __restrict__ hdr_pn /*[clips][16]*/,
@@ -1153,7 +1341,8 @@ __global__ void __launch_bounds__(FR_THREADS) frames_kernel(const double* __rest
                         llr_best_s[pidx] = 0; hdr_best_s[pidx] = 0; }
         return;
     }
-    const double* ys = y + (long long)cb * n + start;
+    // framed: y holds the band-passed samples of the candidate frames only, [clip][band][slot][FRAME_LEN] (frame_bandpass_kernel)
+    const double* ys = framed ? y + pidx * FRAME_LEN : y + (long long)cb * n + start;
     for (int t = tid; t < FRAME_LEN; t += FR_THREADS) S.frame[t] = (double)(float)ys[t];   // frame.astype(float32)
     __syncthreads();
     const int nh = c_mf_len[band];
@@ -1492,6 +1681,43 @@ int es_rx_bandpass(const float* x, int nclips, int n, long long x_stride, double
     return ES_OK;
 }
 
+int es_rx_scan(const float* x, int nclips, int n, long long x_stride, double* corr, void* stream)
+{
+    if (!g_rx_ready) { set_error("es_rx_scan: call es_rx_set_filters first"); return ES_ENOTREADY; }
+    const int nc = n - (PRE_L - 1);
+    if (nclips <= 0 || nc <= 0) return ES_OK;
+    // the chunk grid of es_rx_bandpass (a function of n only)
+    int groups = (int)(((long long)n + 16LL * BP_CHUNK) / (32LL * BP_CHUNK));
+    if (groups < 1) groups = 1;
+    int ch = (int)(((long long)n + 32LL * groups - 1) / (32LL * groups));
+    ch = (ch + 15) & ~15;
+    const long long blocks = (long long)nclips * groups * NBANDS;
+    if (blocks > 0x7fffffffLL) { set_error("es_rx_scan: %lld warps exceed the grid", blocks); return ES_EINVAL; }
+    const bool aligned = ((reinterpret_cast<uintptr_t>(x) & 15u) == 0) && ((x_stride & 3) == 0);
+    const int variant = (g_bp_oddz ? 2 : 0) | (aligned ? 1 : 0);
+    int& configured = g_rxdev[current_device()].cfg[4];
+    if (!configured) {
+        const void* fns[4] = {(const void*)scan_kernel<false, false>, (const void*)scan_kernel<false, true>,
+                              (const void*)scan_kernel<true, false>, (const void*)scan_kernel<true, true>};
+        for (int i = 0; i < 4; ++i) {
+            ES_CUDA_OK(cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanShared)));
+            ES_CUDA_OK(cudaFuncSetAttribute(fns[i], cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        }
+        configured = 1;
+    }
+    const unsigned grid = (unsigned)blocks;
+    const size_t smem = sizeof(ScanShared);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (variant) {
+    case 0: scan_kernel<false, false><<<grid, 32, smem, st>>>(x, nclips, n, x_stride, corr, nc, ch, groups); break;
+    case 1: scan_kernel<false, true><<<grid, 32, smem, st>>>(x, nclips, n, x_stride, corr, nc, ch, groups); break;
+    case 2: scan_kernel<true, false><<<grid, 32, smem, st>>>(x, nclips, n, x_stride, corr, nc, ch, groups); break;
+    default: scan_kernel<true, true><<<grid, 32, smem, st>>>(x, nclips, n, x_stride, corr, nc, ch, groups); break;
+    }
+    ES_CUDA_OK(cudaGetLastError());
+    return ES_OK;
+}
+
 int es_rx_ncc(const double* y, int nclips, int n, double* corr, void* stream)
 {
     if (!g_rx_ready) { set_error("es_rx_ncc: call es_rx_set_filters first"); return ES_ENOTREADY; }
@@ -1664,7 +1890,21 @@ int es_rx_frames(const double* y, int nclips, int n, const int32_t* peaks, const
     if (!g_rx_ready) { set_error("es_rx_frames: call es_rx_set_filters first"); return ES_ENOTREADY; }
     if (nclips <= 0) return ES_OK;
     dim3 grid(PEAK_LIMIT, nclips * NBANDS);
-    frames_kernel<<<grid, FR_THREADS, 0, (cudaStream_t)stream>>>(y, n, peaks, npeaks, hdr_pn, mf_aligned, llr_best_s, hdr_out, hdr_best_s);
+    frames_kernel<<<grid, FR_THREADS, 0, (cudaStream_t)stream>>>(y, n, 0, peaks, npeaks, hdr_pn, mf_aligned, llr_best_s, hdr_out, hdr_best_s);
+    ES_CUDA_OK(cudaGetLastError());
+    return ES_OK;
+}
+
+int es_rx_frames_x(const float* x, int nclips, int n, long long x_stride, const int32_t* peaks, const int32_t* npeaks,
+                   const uint8_t* hdr_pn, double* yframes, float* mf_aligned, int32_t* llr_best_s, float* hdr_out,
+                   int32_t* hdr_best_s, void* stream)
+{
+    if (!g_rx_ready) { set_error("es_rx_frames_x: call es_rx_set_filters first"); return ES_ENOTREADY; }
+    if (nclips <= 0) return ES_OK;
+    frame_bandpass_kernel<<<nclips * NBANDS, 32, 0, (cudaStream_t)stream>>>(x, n, x_stride, peaks, npeaks, yframes);
+    ES_CUDA_OK(cudaGetLastError());
+    dim3 grid(PEAK_LIMIT, nclips * NBANDS);
+    frames_kernel<<<grid, FR_THREADS, 0, (cudaStream_t)stream>>>(yframes, n, 1, peaks, npeaks, hdr_pn, mf_aligned, llr_best_s, hdr_out, hdr_best_s);
     ES_CUDA_OK(cudaGetLastError());
     return ES_OK;
 }

@@ -90,6 +90,44 @@ def ncc(y: torch.Tensor) -> torch.Tensor:
 K3_LONG_MIN = 1 << 21      # correlation length from which the multi-CTA form of K3 is used
 
 
+def scan(x: torch.Tensor) -> torch.Tensor:
+    """Band-pass + normalised correlation in one pass (K1+K2 fused, es_rx_scan): float32 [B, n] -> corr float64
+    [B, 4, n-62]; the filtered signal is never written (rtwm/detector.py:59-60,75-79)."""
+    B, n = x.shape
+    nc = n - (PRE_L - 1)
+    if x.stride(1) != 1:
+        x = x.contiguous()
+    N.require_cuda(x if x.is_contiguous() else x[:1, :1])      # rows may be a strided view of a wider buffer (x_stride)
+    corr = torch.empty((B, 4, max(nc, 0)), dtype=torch.float64, device=x.device)
+    if nc > 0:
+        with N.timed("scan"):
+            N.check(N.lib().es_rx_scan(N.ptr(x), C.c_int(B), C.c_int(n), C.c_longlong(x.stride(0)), N.ptr(corr),
+                                       N.stream_ptr()), "es_rx_scan")
+    return corr
+
+
+def frames_x(x: torch.Tensor, pk: torch.Tensor, npk: torch.Tensor, hdr_pn: torch.Tensor):
+    """Per-peak front end (K4) from the audio itself: the candidate frames are band-passed on their own
+    (es_rx_frames_x), then decoded exactly as frames() does.  Same outputs as frames()."""
+    B, n = x.shape
+    if x.stride(1) != 1:
+        x = x.contiguous()
+    N.require_cuda(x if x.is_contiguous() else x[:1, :1], pk, npk, hdr_pn)
+    dev = x.device
+    out = dict(
+        mf_aligned=torch.empty((B, 4, PEAK_LIMIT, NPAY), dtype=torch.float32, device=dev),
+        llr_best_s=torch.zeros((B, 4, PEAK_LIMIT), dtype=torch.int32, device=dev),
+        hdr=torch.zeros((B, 4, PEAK_LIMIT, 4), dtype=torch.float32, device=dev),
+        hdr_best_s=torch.zeros((B, 4, PEAK_LIMIT), dtype=torch.int32, device=dev),
+    )
+    yfr = torch.empty((B, 4, PEAK_LIMIT, FRAME_LEN), dtype=torch.float64, device=dev)
+    with N.timed("frames"):
+        N.check(N.lib().es_rx_frames_x(N.ptr(x), C.c_int(B), C.c_int(n), C.c_longlong(x.stride(0)), N.ptr(pk), N.ptr(npk),
+                                       N.ptr(hdr_pn), N.ptr(yfr), N.ptr(out["mf_aligned"]), N.ptr(out["llr_best_s"]),
+                                       N.ptr(out["hdr"]), N.ptr(out["hdr_best_s"]), N.stream_ptr()), "es_rx_frames_x")
+    return out
+
+
 def peaks_force_general(on: bool):
     """Test hook: route every row of K3 through the general multi-pass form (same results as the two-pass form)."""
     N.lib().es_rx_peaks_force_general(C.c_int(1 if on else 0))

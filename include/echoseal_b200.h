@@ -71,6 +71,10 @@ int es_rx_bandpass(const float* x /*[clips][x_stride]*/, int nclips, int n, long
                    double* y /*[clips][4][n]*/, void* stream);
 /* K2: cosine-normalised preamble correlation (rtwm/detector.py:76-79) */
 int es_rx_ncc(const double* y, int nclips, int n, double* corr /*[clips][4][n-62]*/, void* stream);
+/* K1+K2 fused (rtwm/detector.py:59-60,75-79): band-pass and normalised correlation in one pass, the filtered signal
+ * stays on the SM.  Same chunk grid and arithmetic as es_rx_bandpass + es_rx_ncc; windows that cross a chunk boundary see
+ * the filter's 4e-13 warm-up truncation on the far side.  corr f64 [clips][4][n-62]. */
+int es_rx_scan(const float* x /*[clips][x_stride]*/, int nclips, int n, long long x_stride, double* corr, void* stream);
 /* K3: median/MAD threshold, NMS, first 25 peaks, top-5 fallback (rtwm/detector.py:83-99,107-110).
  * stats = med, mad, thr, used_fallback */
 int es_rx_peaks(const double* corr, int nclips, int nc, int32_t* peaks /*[clips][4][25]*/,
@@ -97,6 +101,12 @@ int es_rx_peaks_long_layout(int nclips, int n_range, long long* out /*[14]*/);
 int es_rx_frames(const double* y, int nclips, int n, const int32_t* peaks, const int32_t* npeaks,
                  const uint8_t* hdr_pn /*[clips][16]*/, float* mf_aligned /*[clips][4][25][1024]*/,
                  int32_t* llr_best_s, float* hdr_out /*[clips][4][25][4]*/, int32_t* hdr_best_s, void* stream);
+/* K4 from the audio itself: the candidate frames are band-passed on their own (768-sample zero-state warm-up, exact from
+ * the clip start) into yframes f64 [clips][4][25][1215] (scratch), then decoded as es_rx_frames does. */
+int es_rx_frames_x(const float* x /*[clips][x_stride]*/, int nclips, int n, long long x_stride, const int32_t* peaks,
+                   const int32_t* npeaks, const uint8_t* hdr_pn /*[clips][16]*/, double* yframes,
+                   float* mf_aligned /*[clips][4][25][1024]*/, int32_t* llr_best_s, float* hdr_out /*[clips][4][25][4]*/,
+                   int32_t* hdr_best_s, void* stream);
 /* K5: despread + LLR scaling for (peak, counter) items, both PN variants (rtwm/detector.py:306-314,384-414) */
 int es_rx_llr(const float* mf_aligned, const int32_t* item_peak /*[items]*/, const uint8_t* pn_packed /*[items][152]*/,
               int nitems, float* llr /*[2*items][1024]*/, void* stream);

@@ -544,3 +544,54 @@ def test_time_sharded_recording_equals_single_gpu(env):
     det = detector.WatermarkDetector(keys[2], list_size=8)
     v, outs = long_sharded.run_simulated(det, sig, 2)
     assert outs[0]["overflow"] and v == ref.verify(sig, 48000)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", NAMES)
+def test_fused_scan_vs_oracle_and_staged_kernels(env, name):
+    """es_rx_scan (band-pass + correlation fused, filtered signal never written) and es_rx_frames_x (frames band-passed on
+    their own): correlation within 1e-7 of the oracle (rtwm/detector.py:59-79) and 1e-11 of K2(K1(x)), thresholds and sync
+    offsets equal to the reference golden, K4 outputs equal to the staged path's within float32 rounding."""
+    torch, rx_gpu, detector, clips, taps = env
+    from oracle import detector_oracle as do
+    from oracle import tx_oracle as txo
+    audio, key = clips[name]
+    x = torch.from_numpy(audio[None]).cuda()
+    corr = rx_gpu.scan(x)
+    y = rx_gpu.bandpass(x)
+    corr2 = rx_gpu.ncc(y)
+    assert float((corr - corr2).abs().max()) < 1e-9       # windows across a chunk boundary see the 4e-13 warm-up truncation, amplified where the window energy is small
+    pk, npk, st = rx_gpu.peaks(corr)
+    c_h = corr.cpu().numpy()[0]
+    pk_h, npk_h, st_h = pk.cpu().numpy()[0], npk.cpu().numpy()[0], st.cpu().numpy()[0]
+    for bi, band in enumerate(do.BAND_PLAN):
+        ref = do.scan_band(audio, band)
+        assert np.abs(c_h[bi] - ref["corr"]).max() < 1e-7
+        med, mad, thr, npk_ref, fb = G[f"{name}/b{bi}/stats"]
+        np.testing.assert_allclose(st_h[bi, :3], [med, mad, thr], rtol=1e-7, atol=1e-12)
+        assert [int(v) for v in pk_h[bi, :npk_h[bi]]] == list(G[f"{name}/b{bi}/peaks"])[:25]     # sync offsets: bit-exact
+    hdr_pn = torch.from_numpy(np.packbits(txo.Keys(key).pn_bits(0, 128))[None]).cuda()
+    a = rx_gpu.frames(y, pk, npk, hdr_pn)
+    b = rx_gpu.frames_x(x, pk, npk, hdr_pn)
+    valid = (a["hdr"][..., 0] >= 0)
+    assert bool((valid == (b["hdr"][..., 0] >= 0)).all())
+    assert bool((a["hdr"][..., :2] == b["hdr"][..., :2]).all())                    # header (ok, value)
+    assert bool((a["llr_best_s"] == b["llr_best_s"]).all()) and bool((a["hdr_best_s"] == b["hdr_best_s"]).all())
+    ma, mb = a["mf_aligned"][valid], b["mf_aligned"][valid]
+    if ma.numel():
+        assert float((ma - mb).abs().max()) <= 1e-5 * float(ma.abs().max())
+
+
+@pytest.mark.gpu
+def test_fused_scan_ragged_and_unaligned(env):
+    """Lengths that are not multiples of the chunk / of 4 samples, a strided batch view (rows not 16-byte aligned) and a
+    clip shorter than one chunk: the fused scan equals K2(K1(x)) to 1e-11 everywhere."""
+    torch, rx_gpu, detector, clips, taps = env
+    g = torch.Generator(device="cuda").manual_seed(5)
+    for B, n, pitch in [(3, 144000, 144000), (2, 100003, 100003), (2, 70001, 70005), (1, 1500, 1500), (2, 63, 64), (1, 300000, 300000)]:
+        buf = torch.randn((B, pitch), device="cuda", generator=g) * 0.1
+        x = buf[:, :n]
+        corr = rx_gpu.scan(x)
+        ref = rx_gpu.ncc(rx_gpu.bandpass(x.contiguous()))
+        assert corr.shape == ref.shape
+        assert float((corr - ref).abs().max()) < 1e-11, (B, n, pitch)

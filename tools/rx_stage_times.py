@@ -27,6 +27,12 @@ def main():
         corr = T("ncc", lambda: rx_gpu.ncc(y))
         pk, npk, st = T("peaks", lambda: rx_gpu.peaks(corr))
         fr = T("frames", lambda: rx_gpu.frames(y, pk, npk, hdr_pn))
+        del y
+        corr_f = T("scan (K1+K2 fused)", lambda: rx_gpu.scan(clips))
+        print("   fused vs staged corr max diff", float((corr_f - corr).abs().max()))
+        del corr_f
+        fr2 = T("frames_x", lambda: rx_gpu.frames_x(clips, pk, npk, hdr_pn))
+        del fr2
         pk_h, npk_h, hdr_h = T("d2h peaks/hdr", lambda: (pk.cpu().numpy(), npk.cpu().numpy(), fr["hdr"].cpu().numpy()))
         enum = T("rx_enumerate", lambda: bank.rx_enumerate(kidx, clips.shape[1], pk_h, npk_h, hdr_h))
         I = enum["item_peak"].size
