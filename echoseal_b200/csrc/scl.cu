@@ -37,6 +37,8 @@ __device__ uint16_t d_datapos[1024];     // the same positions in global memory,
 // all-frozen node of 4 << (v-1) bits; 255 = interior quad of such a node
 __constant__ uint8_t c_r0[256];
 __constant__ uint8_t c_crc8[256];        // CRC-8 (poly 0x07, MSB first) of one byte
+__constant__ uint32_t c_cmp[32][5];      // per word of 32 positions: the five move masks that compress its un-frozen bits to the low end
+__constant__ uint32_t c_cnt[32];         // un-frozen positions per word
 
 // what each device's constant tables currently hold (es_polar_set_code)
 struct CodeDev { int ready = 0; int K = 0; uint32_t frozen[32] = {0}; };
@@ -345,7 +347,8 @@ template <int S> struct SclLayout {
     static constexpr int STASH_OFF = BAR_OFF + 16;                        // 48 bytes per lane: decode state parked across the LLR update
     static constexpr int WARP_BYTES = STASH_OFF + 32 * 48;
     static constexpr int NTH_OFF = PHI_TAB_DOUBLES * 8;                  // [mask 256][n 8] bytes: position of the n-th set bit
-    static constexpr int TAB_BYTES = NTH_OFF + 2048;
+    static constexpr int CRC_OFF = NTH_OFF + 2048;                       // CRC-8 byte table
+    static constexpr int TAB_BYTES = CRC_OFF + 256;
     static constexpr size_t G_ROWS = 1024 - (1 << (11 - S));           // global alpha rows, levels 1..S-1
     static constexpr size_t G_DOUBLES = G_ROWS * 32 + 1024 * 4 + BROWS_G * 16;   // + level-0 copy [1024][4] + beta rows
 };
@@ -1064,6 +1067,7 @@ __global__ void __maxnreg__(ES_SCL_MAXNREG) scl_list_kernel(SclParams P)
         double* st = reinterpret_cast<double*>(smem_raw);
         for (int q = threadIdx.x; q < PHI_TAB_DOUBLES; q += W * 32) st[q] = P.phi_tab[q];
         for (int q = threadIdx.x; q < 2048; q += W * 32) smem_raw[LY::NTH_OFF + q] = (unsigned char)nth_set8((uint32_t)(q >> 3), q & 7);
+        for (int q = threadIdx.x; q < 256; q += W * 32) smem_raw[LY::CRC_OFF + q] = c_crc8[q];
     }
     const int warp = threadIdx.x >> 5;
     Lane L;
@@ -1234,18 +1238,38 @@ __global__ void __maxnreg__(ES_SCL_MAXNREG) scl_list_kernel(SclParams P)
         const int K = c_K;
         const int nbytes = (K - 8) >> 3;
         uint8_t* out = P.path_payload + orow * nbytes;
-        uint8_t crcreg = 0, crcbits = 0;
-        uint32_t acc = 0;
+        uint32_t crcreg = 0, crcbits = 0;
+        {
+            // The K un-frozen bits of u-hat in ascending position are the payload + CRC stream, first bit = MSB of byte 0
+            // (rtwm/fastpolar.py:340-349).  Per 32-bit word: compress the un-frozen bits to the low end (five shift steps
+            // with masks precomputed by es_polar_set_code), append them to a 64-bit queue, drain whole bytes.
+            unsigned long long acc = 0;
+            int fill = 0, nb = 0;
+            const uint32_t crc_tab = smem_base() + (uint32_t)LY::CRC_OFF;
 #pragma unroll 1
-        for (int q = 0; q < K; ++q) {
-            const int pos = c_datapos[q];
-            const uint32_t b = (xroot[(pos >> 5) * 32 + L.lane] >> (pos & 31)) & 1u;
-            if (q < K - 8) {
-                acc = (acc << 1) | b;
-                crcreg = crc8_step_bit(crcreg, b);
-                if ((q & 7) == 7 && wr && L.active) out[q >> 3] = (uint8_t)(acc & 0xffu);
-            } else {
-                crcbits = (uint8_t)((crcbits << 1) | b);
+            for (int j = 0; j < 32; ++j) {
+                uint32_t v = xroot[j * 32 + L.lane] & ~c_frozen[j];
+#pragma unroll
+                for (int s5 = 0; s5 < 5; ++s5) {
+                    const uint32_t tt = v & c_cmp[j][s5];
+                    v = (v ^ tt) | (tt >> (1 << s5));
+                }
+                acc |= (unsigned long long)v << fill;
+                fill += c_cnt[j];
+#pragma unroll 1
+                while (fill >= 8) {
+                    const uint32_t byte = __brev((uint32_t)acc) >> 24;
+                    acc >>= 8; fill -= 8;
+                    if (nb < nbytes) {
+                        uint32_t t8;
+                        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(t8) : "r"(crc_tab + (crcreg ^ byte)) : "memory");
+                        crcreg = t8;
+                        if (wr && L.active) out[nb] = (uint8_t)byte;
+                    } else {
+                        crcbits = byte;
+                    }
+                    ++nb;
+                }
             }
         }
         if (wr) {
@@ -1512,6 +1536,25 @@ int es_polar_set_code(const uint8_t* frozen_host, int K)
             tab[v] = r;
         }
         ES_CUDA_OK(cudaMemcpyToSymbol(c_crc8, tab, sizeof(tab)));
+    }
+    {
+        // bit compress by a fixed mask (Hacker's Delight 7-4): move masks per word of 32 positions
+        uint32_t cmp[32][5], cnt[32];
+        for (int j = 0; j < 32; ++j) {
+            uint32_t m = ~words[j];
+            cnt[j] = (uint32_t)__builtin_popcount(m);
+            uint32_t mk = ~m << 1;
+            for (int i = 0; i < 5; ++i) {
+                uint32_t mp = mk ^ (mk << 1);
+                mp ^= mp << 2; mp ^= mp << 4; mp ^= mp << 8; mp ^= mp << 16;
+                const uint32_t mv = mp & m;
+                cmp[j][i] = mv;
+                m = (m ^ mv) | (mv >> (1 << i));
+                mk &= ~mp;
+            }
+        }
+        ES_CUDA_OK(cudaMemcpyToSymbol(c_cmp, cmp, sizeof(cmp)));
+        ES_CUDA_OK(cudaMemcpyToSymbol(c_cnt, cnt, sizeof(cnt)));
     }
     { const int rc = tx_set_code(pos, K); if (rc != ES_OK) return rc; }
     CD.ready = 1;

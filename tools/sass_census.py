@@ -31,7 +31,7 @@ def main():
                 f = sum(v for op, v in c.items() if op in FP64)
                 calls = sum(1 for x in seg if x.startswith("CALL"))
                 role = ""
-                if 70 <= f <= 80 and len(seg) < 200: role = "  <- lse4: four phi evaluations (4 x 18 FP64) + 4 adds"
+                if 70 <= f <= 80 and len(seg) < 200: role = "  <- psi4: four evaluations of psi = |x|/2 + phi(|x|) in lock-step (4 x 19 FP64)"
                 elif 34 <= f <= 38 and len(seg) < 110: role = "  <- phi2: two phi evaluations"
                 elif 17 <= f <= 19 and len(seg) < 60: role = "  <- phi1: one phi evaluation"
                 print(f"  routine {k}: {len(seg):4d} instr, FP64 pipe {f:3d} ({100 * f / len(seg):4.1f}%), calls {calls}{role}")
