@@ -516,7 +516,7 @@ __device__ __noinline__ void negate_level0(double* l0)
 #define ES_SCL_DBG_VERIFY 0
 #endif
 #ifndef ES_SCL_PASS_INLINE
-#define ES_SCL_PASS_INLINE 0     // the two ring passes inlined into the kernel body (single call site each)
+#define ES_SCL_PASS_INLINE 1     // the two ring passes inlined into the kernel body (single call site each)
 #endif
 #if ES_SCL_PASS_INLINE
 #define ES_PASS_INLINE __forceinline__
@@ -818,7 +818,15 @@ __device__ __forceinline__ void llr_update8(Lane& L, int i, int last)   // l0 <=
 // "tie contract").  Four interleaved partial sums over the elements in natural order, combined as
 // (s0 + s1) + (s2 + s3).  a = position 0 of the node in the lane's slot; lq >= 0: quarter-interleaved node
 // with quarters of 2^lq elements (>= 8), lq < 0: natural order.
-__device__ __noinline__ double r0_sum(const double* a, int lq, int count, uint32_t tab)
+#ifndef ES_SCL_R0_INLINE
+#define ES_SCL_R0_INLINE 0
+#endif
+#if ES_SCL_R0_INLINE
+__device__ __forceinline__
+#else
+__device__ __noinline__
+#endif
+double r0_sum(const double* a, int lq, int count, uint32_t tab)
 {
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
     const int step = (lq < 0) ? 32 : 128;
