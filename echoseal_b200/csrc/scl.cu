@@ -1323,14 +1323,24 @@ __device__ __forceinline__ uint32_t warp_transform(uint32_t x, int lane)
 }
 
 // One warp per LLR row.  In neg_mode the row yields two codewords (+row: bit = llr > 0, -row: bit = llr < 0) from
-// one set of loads; all 32 coalesced row loads are issued before the first ballot.
+// one set of loads; all 32 coalesced row loads are issued before the first ballot.  Lane j ends up with word j of u-hat
+// (positions 32j .. 32j+31); its un-frozen bits are compressed to the low end with the five move masks of that word
+// (d_hard_tab, filled by es_polar_set_code) and OR-ed into the K-bit stream at the word's stream offset; lanes then emit
+// four stream bytes each.  CRC-8 is linear: every lane runs its own bytes through the table, advances the result over
+// the payload bytes that follow its group (d_hard_shift: the state after r more zero bytes) and the warp XORs the parts.
+struct HardTab { uint32_t cmp[5]; uint32_t unfrozen; uint32_t cnt; uint32_t off; };
+__device__ HardTab d_hard_tab[32];
+__device__ uint8_t d_hard_shift[32][256];       // [lane][crc state]: the state advanced over the payload bytes after the lane's group
+__device__ uint8_t d_crc8_g[256];               // CRC-8 byte table in global memory (per-lane index)
+
 __global__ void __launch_bounds__(128) scl_hard_kernel(const float* __restrict__ llr, int nrows, int neg_mode,
                                                        uint8_t* __restrict__ hard_payload,
                                                        uint8_t* __restrict__ hard_crc)
 {
+    __shared__ uint32_t sbuf[4][2][34];
     const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+    const int row = blockIdx.x * (blockDim.x >> 5) + wl;
     if (row >= nrows) return;
     const float* src = llr + (size_t)row * 1024;
     const int K = c_K;
@@ -1338,6 +1348,7 @@ __global__ void __launch_bounds__(128) scl_hard_kernel(const float* __restrict__
     float v[32];
 #pragma unroll
     for (int it = 0; it < 32; ++it) v[it] = __ldg(src + it * 32 + lane);
+    const HardTab T = d_hard_tab[lane];
     uint32_t xp = 0, xn = 0;
 #pragma unroll
     for (int it = 0; it < 32; ++it) {
@@ -1346,32 +1357,40 @@ __global__ void __launch_bounds__(128) scl_hard_kernel(const float* __restrict__
         if (lane == it) { xp = bp; xn = bn; }
     }
     const int nvar = neg_mode ? 2 : 1;
+    sbuf[wl][0][lane] = 0; sbuf[wl][1][lane] = 0;
+    if (lane < 2) { sbuf[wl][0][32 + lane] = 0; sbuf[wl][1][32 + lane] = 0; }
+    __syncwarp();
 #pragma unroll 1
     for (int var = 0; var < nvar; ++var) {
         const int w = neg_mode ? (2 * row + var) : row;
-        const uint32_t x = warp_transform(var ? xn : xp, lane);
-        uint8_t* out = hard_payload + (size_t)w * nbytes;
-        uint8_t crcreg = 0, crcbits = 0;
-        const int nchunk = (K + 31) >> 5;
-        for (int c = 0; c < nchunk; ++c) {
-            const int q = c * 32 + lane;
-            const int pos = (q < K) ? d_datapos[q] : 0;             // per-lane index: a constant-bank read would serialise
-            const uint32_t wv = __shfl_sync(full, x, pos >> 5);
-            const uint32_t b = (q < K) ? ((wv >> (pos & 31)) & 1u) : 0u;
-            const uint32_t word = __brev(__ballot_sync(full, b));   // bit q -> MSB-first
+        uint32_t u = warp_transform(var ? xn : xp, lane) & T.unfrozen;
 #pragma unroll
-            for (int bb = 0; bb < 4; ++bb) {
-                const int byte_idx = c * 4 + bb;
-                const uint8_t byte = (uint8_t)(word >> (24 - 8 * bb));
-                if (byte_idx < nbytes) {
-                    if (lane == bb) out[byte_idx] = byte;
-                    crcreg = c_crc8[crcreg ^ byte];                 // uniform index: one constant-cache broadcast
-                } else if (byte_idx == nbytes) {
-                    crcbits = byte;
-                }
-            }
+        for (int s5 = 0; s5 < 5; ++s5) {
+            const uint32_t tt = u & T.cmp[s5];
+            u = (u ^ tt) | (tt >> (1 << s5));
         }
-        if (lane == 0) hard_crc[w] = (crcreg == crcbits) ? 1 : 0;
+        uint32_t* sb = sbuf[wl][var];
+        const unsigned long long piece = (unsigned long long)u << (T.off & 31);
+        if (T.cnt) {
+            atomicOr(&sb[T.off >> 5], (uint32_t)piece);
+            if ((uint32_t)(piece >> 32)) atomicOr(&sb[(T.off >> 5) + 1], (uint32_t)(piece >> 32));
+        }
+        __syncwarp();
+        // stream bit q sits at bit q & 31 of word q >> 5; byte i = bits 8i .. 8i+7, first bit = MSB
+        const uint32_t rev = __brev(sb[lane]);       // byte 4*lane + k = (rev >> (24 - 8k)) & 255
+        uint8_t* out = hard_payload + (size_t)w * nbytes;
+        uint32_t crc = 0, crcbits = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int i = 4 * lane + k;
+            const uint32_t byte = (rev >> (24 - 8 * k)) & 255u;
+            if (i < nbytes) { out[i] = (uint8_t)byte; crc = d_crc8_g[crc ^ byte]; }
+            else if (i == nbytes) crcbits = byte;
+        }
+        crc = d_hard_shift[lane][crc];               // lanes past the payload hold 0 -> 0
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { crc ^= __shfl_xor_sync(full, crc, o); crcbits |= __shfl_xor_sync(full, crcbits, o); }
+        if (lane == 0) hard_crc[w] = (crc == crcbits) ? 1 : 0;
     }
 }
 
@@ -1563,6 +1582,35 @@ int es_polar_set_code(const uint8_t* frozen_host, int K)
         }
         ES_CUDA_OK(cudaMemcpyToSymbol(c_cmp, cmp, sizeof(cmp)));
         ES_CUDA_OK(cudaMemcpyToSymbol(c_cnt, cnt, sizeof(cnt)));
+        // tables of the hard-decision kernel: per word the masks, the stream offset; per lane the CRC-8 state advanced over
+        // the payload bytes that follow the lane's four stream bytes
+        HardTab ht[32];
+        uint32_t off = 0;
+        for (int j = 0; j < 32; ++j) {
+            for (int i = 0; i < 5; ++i) ht[j].cmp[i] = cmp[j][i];
+            ht[j].unfrozen = ~words[j]; ht[j].cnt = cnt[j]; ht[j].off = off;
+            off += cnt[j];
+        }
+        ES_CUDA_OK(cudaMemcpyToSymbol(d_hard_tab, ht, sizeof(ht)));
+        uint8_t tab[256];
+        for (int v = 0; v < 256; ++v) {
+            uint8_t r = (uint8_t)v;
+            for (int t = 0; t < 8; ++t) r = (r & 0x80) ? (uint8_t)((r << 1) ^ 0x07) : (uint8_t)(r << 1);
+            tab[v] = r;
+        }
+        ES_CUDA_OK(cudaMemcpyToSymbol(d_crc8_g, tab, sizeof(tab)));
+        static uint8_t shift[32][256];
+        const int nbytes = (K - 8) / 8;
+        for (int lane = 0; lane < 32; ++lane) {
+            int after = nbytes - (4 * lane + 4);          // payload bytes after this lane's group
+            if (after < 0) after = 0;
+            for (int v = 0; v < 256; ++v) {
+                uint8_t r = (uint8_t)v;
+                for (int z = 0; z < after; ++z) r = tab[r];
+                shift[lane][v] = r;
+            }
+        }
+        ES_CUDA_OK(cudaMemcpyToSymbol(d_hard_shift, shift, sizeof(shift)));
     }
     { const int rc = tx_set_code(pos, K); if (rc != ES_OK) return rc; }
     CD.ready = 1;
