@@ -537,7 +537,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--clips", type=int, default=10_000, help="clips per GPU per step (configs[1]: 10k)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--sub-batch", type=int, default=1000)
+    ap.add_argument("--sub-batch", type=int, default=2000)
     ap.add_argument("--cpu-sample", type=int, default=0, help="clips for the cpu_baseline leg (0 = 2 x cores)")
     ap.add_argument("--workload", default="rx", choices=["rx", "scl", "tx", "long"],
                     help="rx = configs[1] (the headline); scl = configs[3] microbench; tx = configs[4]; long = configs[2]")

@@ -1113,8 +1113,19 @@ __global__ void __maxnreg__(ES_SCL_MAXNREG) scl_list_kernel(SclParams P)
             const int row = P.neg_mode ? (w >> 1) : w;
             const float* src = P.llr + (size_t)row * 1024;
             double* dst = gscr + LY::G_ROWS * 32 + (L.lane >> 3);
+            if ((reinterpret_cast<uintptr_t>(P.llr) & 15u) == 0) {          // 16-byte loads, eight in flight per lane
+                const float4* src4 = reinterpret_cast<const float4*>(src);
+#pragma unroll 8
+                for (int i = 0; i < 32; ++i) {
+                    const int k = 4 * (L.p() + 8 * i);
+                    const float4 v = __ldg(src4 + (k >> 2));
+                    double* d0 = dst + ipos(0, k) * 4;                      // k .. k+3 share their 256-block: positions 4 apart
+                    d0[0] = (double)v.x; d0[16] = (double)v.y; d0[32] = (double)v.z; d0[48] = (double)v.w;
+                }
+            } else {
 #pragma unroll 4
-            for (int k = L.p(); k < 1024; k += 8) dst[ipos(0, k) * 4] = (double)__ldg(src + k);
+                for (int k = L.p(); k < 1024; k += 8) dst[ipos(0, k) * 4] = (double)__ldg(src + k);
+            }
         }
         L.m = 0.0; L.ptr = 0; L.bptr = 0; L.bs = 0; L.ord = 0;
         L.mg_gap = CUDART_INF; L.mg_den = 1.0;
