@@ -1320,6 +1320,268 @@ __global__ void __maxnreg__(ES_SCL_MAXNREG) scl_list_kernel(SclParams P)
 #undef gscr
 
 // ---------------------------------------------------------------------------------------------
+// wide-list decoder: list sizes 9..32 (rtwm/detector.py:27 accepts any list_size; its quick test uses 32).  Same
+// arithmetic and rules as scl_list_kernel (f as a psi difference, rate-0 node sums, the -row variant decoded from +row
+// with the level-1 g node negated, stable ranking by (metric, path order, bit)), in the plain form of the device-
+// arithmetic model (oracle/polar_oracle.c): one WARP per codeword, one lane per path, every tree level in a global
+// scratch [element][lane], bit-by-bit leaves, partial sums as bytes.  Lazy copy as in the fast kernel: every path
+// rewrites a level at the same bit index into its OWN slot, so a clone copies two 64-bit words of per-level slot
+// pointers, its 1024 decision bits and the metric.  Built for exactness, not speed (about a tenth of the SCL-8 rate).
+// ---------------------------------------------------------------------------------------------
+constexpr int WIDE_W = 8;                                  // warps per CTA
+constexpr size_t WIDE_A = 1024u * 32u;                     // doubles: alpha [AOFF(l) + k][lane]
+constexpr size_t WIDE_SCRATCH_BYTES = WIDE_A * 8 + 2 * 1024u * 32u;      // + bl bytes [AOFF(l) + k][lane] + tmp bytes [k][lane]
+
+struct WideParams {
+    const float* llr; int ncw; int neg_mode; int list_size;
+    unsigned char* scratch;
+    const double* phi_tab;
+    uint8_t* path_payload; uint8_t* path_crc; double* path_metric; int32_t* npaths;
+};
+
+__device__ __forceinline__ int wide_aoff(int l) { return 1024 - (1 << (11 - l)); }
+__device__ __forceinline__ int wptr_get(unsigned long long w, int l) { return (int)((w >> (5 * (l - 1))) & 31ull); }
+__device__ __forceinline__ unsigned long long wptr_set(unsigned long long w, int l, int v)
+{
+    return (w & ~(31ull << (5 * (l - 1)))) | ((unsigned long long)v << (5 * (l - 1)));
+}
+
+struct WideLane {
+    double* A; uint8_t* B; uint8_t* T; const float* row; uint32_t* U;      // U: decision bits [word][lane] in shared memory
+    int lane; bool neg;
+    unsigned long long aptr, bptr;
+    double m; int ord; bool active;
+};
+
+// LLR update for bit i down to level `last` (oracle sc_step_llr_to)
+__device__ __noinline__ unsigned long long wide_step(double* A, const uint8_t* B, const float* row, int lane, bool neg,
+                                                    unsigned long long aptr, unsigned long long bptr, int i, int last)
+{
+    const int l0 = (i == 0) ? 0 : 10 - (__ffs(i) - 1);
+    if (l0 >= 1) {
+        const int s = 1 << (10 - l0);
+        const int ps = (l0 == 1) ? 0 : wptr_get(aptr, l0 - 1);
+        const double* par = A + (size_t)wide_aoff(l0 - 1) * 32 + ps;            // unused for l0 == 1
+        double* dst = A + (size_t)wide_aoff(l0) * 32 + lane;
+        const uint8_t* bl = B + (size_t)wide_aoff(l0) * 32 + wptr_get(bptr, l0);
+#pragma unroll 2
+        for (int k = 0; k < s; ++k) {
+            const double a = (l0 == 1) ? (double)__ldg(row + k) : par[(size_t)k * 32];
+            const double b = (l0 == 1) ? (double)__ldg(row + k + s) : par[(size_t)(k + s) * 32];
+            double g = gcomb(a, b, bl[(size_t)k * 32]);
+            if (l0 == 1 && neg) g = -g;
+            dst[(size_t)k * 32] = g;
+        }
+        aptr = wptr_set(aptr, l0, lane);
+    }
+    for (int l = l0 + 1; l <= last; ++l) {
+        const int s = 1 << (10 - l);
+        const int ps = (l == 1) ? 0 : wptr_get(aptr, l - 1);
+        const double* par = A + (size_t)wide_aoff(l - 1) * 32 + ps;
+        double* dst = A + (size_t)wide_aoff(l) * 32 + lane;
+        if (s == 1) {
+            const double a = par[0], b = par[32];
+            const D4 P = psi4(a - b, a + b, a - b, a + b);
+            dst[0] = P.a - P.b;
+        } else {
+#pragma unroll 1
+            for (int k = 0; k < s; k += 2) {
+                const double a0 = (l == 1) ? (double)__ldg(row + k) : par[(size_t)k * 32];
+                const double b0 = (l == 1) ? (double)__ldg(row + k + s) : par[(size_t)(k + s) * 32];
+                const double a1 = (l == 1) ? (double)__ldg(row + k + 1) : par[(size_t)(k + 1) * 32];
+                const double b1 = (l == 1) ? (double)__ldg(row + k + 1 + s) : par[(size_t)(k + 1 + s) * 32];
+                const D4 P = psi4(a0 - b0, a0 + b0, a1 - b1, a1 + b1);
+                dst[(size_t)k * 32] = P.a - P.b;
+                dst[(size_t)(k + 1) * 32] = P.c - P.d;
+            }
+        }
+        aptr = wptr_set(aptr, l, lane);
+    }
+    return aptr;
+}
+
+// partial-sum update after deciding `bit` at position i (oracle sc_extend); returns the new bptr
+__device__ __noinline__ unsigned long long wide_extend(uint8_t* B, uint8_t* T, int lane, unsigned long long bptr, int i, int bit)
+{
+    uint8_t* tmp = T + lane;
+    tmp[0] = (uint8_t)bit;
+    int l = 10, s = 1;
+    while (l > 0 && ((i >> (10 - l)) & 1)) {
+        const uint8_t* left = B + (size_t)wide_aoff(l) * 32 + wptr_get(bptr, l);
+        for (int k = 0; k < s; ++k) {
+            const uint8_t t = tmp[(size_t)k * 32];
+            tmp[(size_t)(k + s) * 32] = t;
+            tmp[(size_t)k * 32] = (uint8_t)(left[(size_t)k * 32] ^ t);
+        }
+        s <<= 1; --l;
+    }
+    if (l > 0) {
+        uint8_t* dst = B + (size_t)wide_aoff(l) * 32 + lane;
+        for (int k = 0; k < s; ++k) dst[(size_t)k * 32] = tmp[(size_t)k * 32];
+        bptr = wptr_set(bptr, l, lane);
+    }
+    return bptr;
+}
+
+__global__ void __launch_bounds__(WIDE_W * 32) scl_wide_kernel(WideParams P)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    using LY = SclLayout<SCL_S>;
+    const unsigned full = 0xffffffffu;
+    {
+        double* st = reinterpret_cast<double*>(smem_raw);
+        for (int q = threadIdx.x; q < PHI_TAB_DOUBLES; q += WIDE_W * 32) st[q] = P.phi_tab[q];
+        for (int q = threadIdx.x; q < 256; q += WIDE_W * 32) smem_raw[LY::CRC_OFF + q] = c_crc8[q];
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t* U = reinterpret_cast<uint32_t*>(smem_raw + LY::TAB_BYTES) + (size_t)warp * 32 * 32;
+    unsigned char* scr = P.scratch + (size_t)(blockIdx.x * WIDE_W + warp) * WIDE_SCRATCH_BYTES;
+    double* A = reinterpret_cast<double*>(scr);
+    uint8_t* B = scr + WIDE_A * 8;
+    uint8_t* T = B + 1024u * 32u;
+    const int Lsz = P.list_size;
+    const int K = c_K;
+    const int nbytes = (K - 8) >> 3;
+#pragma unroll 1
+    for (int w = blockIdx.x * WIDE_W + warp; w < P.ncw; w += gridDim.x * WIDE_W) {
+        const int rowi = P.neg_mode ? (w >> 1) : w;
+        const bool neg = P.neg_mode && (w & 1);
+        const float* row = P.llr + (size_t)rowi * 1024;
+        double m = 0.0;
+        int ord = 0;
+        bool active = (lane == 0);
+        unsigned long long aptr = 0, bptr = 0;
+        for (int j = 0; j < 32; ++j) U[j * 32 + lane] = 0;
+        __syncwarp();
+#pragma unroll 1
+        for (int i = 0; i < 1024; ++i) {
+            const int q = i >> 2;
+            const int r0 = ((i & 3) == 0) ? c_r0[q] : 0;
+            if (r0 != 0 && r0 != 255) {
+                // rate-0 node of s = 4 << (r0-1) bits: sum_k ln(1 + e^{a_k}) over the node, zeros decided
+                const int s = 4 << (r0 - 1);
+                const int lv = 10 - (31 - __clz(s));
+                aptr = wide_step(A, B, row, lane, neg, aptr, bptr, i, lv);
+                const double* a = A + (size_t)wide_aoff(lv) * 32 + wptr_get(aptr, lv);
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll 1
+                for (int k = 0; k < s; k += 4) {
+                    const double a0 = a[(size_t)k * 32], a1 = a[(size_t)(k + 1) * 32], a2 = a[(size_t)(k + 2) * 32], a3 = a[(size_t)(k + 3) * 32];
+                    const D4 Q4 = psi4(a0, a1, a2, a3);
+                    s0 += __fma_rn(a0, 0.5, Q4.a); s1 += __fma_rn(a1, 0.5, Q4.b);
+                    s2 += __fma_rn(a2, 0.5, Q4.c); s3 += __fma_rn(a3, 0.5, Q4.d);
+                }
+                if (active) m += (s0 + s1) + (s2 + s3);
+                for (int k = 0; k < s; ++k) bptr = wide_extend(B, T, lane, bptr, i + k, 0);
+                i += s - 1;
+                continue;
+            }
+            aptr = wide_step(A, B, row, lane, neg, aptr, bptr, i, 10);
+            const double leaf = A[(size_t)wide_aoff(10) * 32 + wptr_get(aptr, 10)];
+            const double al = fabs(leaf);
+            const double ph = phi1(leaf);
+            const bool pref1 = (leaf >= 0.0);
+            const double pen0 = pref1 ? (ph + al) : ph, pen1 = pref1 ? ph : (ph + al);
+            const bool frozen = (c_frozen[i >> 5] >> (i & 31)) & 1u;
+            int bit = 0;
+            if (frozen) {
+                if (active) m += pen0;
+            } else {
+                const double m0 = m + pen0, m1 = m + pen1;
+                const double k0 = active ? m0 : CUDART_INF, k1 = active ? m1 : CUDART_INF;
+                int r0c = 0, r1c = 0;
+#pragma unroll 4
+                for (int j = 0; j < 32; ++j) {
+                    const double k0j = __shfl_sync(full, k0, j);
+                    const double k1j = __shfl_sync(full, k1, j);
+                    const int oj = __shfl_sync(full, ord, j);
+                    const bool lt = oj < ord, le = oj <= ord;
+                    r0c += (int)((k0j < k0) || (lt && k0j == k0)) + (int)((k1j < k0) || (lt && k1j == k0));
+                    r1c += (int)((k0j < k1) || (le && k0j == k1)) + (int)((k1j < k1) || (lt && k1j == k1));
+                }
+                const bool s0 = active && (r0c < Lsz), s1 = active && (r1c < Lsz);
+                const uint32_t cm = __ballot_sync(full, s0 && s1);
+                const uint32_t fm = __ballot_sync(full, !(s0 || s1));
+                const int jfree = __popc(fm & ((1u << lane) - 1u));
+                const bool take = !(s0 || s1) && (jfree < __popc(cm));
+                const int src = take ? (int)__fns(cm, 0, jfree + 1) : lane;
+                const double cm1 = __shfl_sync(full, m1, src);
+                const int cr1 = __shfl_sync(full, r1c, src);
+                const unsigned long long ca = __shfl_sync(full, aptr, src), cb = __shfl_sync(full, bptr, src);
+                for (int j = 0; j < 32; ++j) {              // decision bits follow the clone
+                    const uint32_t uw = U[j * 32 + src];
+                    __syncwarp();
+                    if (take) U[j * 32 + lane] = uw;
+                }
+                if (s0) { m = m0; ord = r0c; bit = 0; }
+                else if (s1) { m = m1; ord = r1c; bit = 1; }
+                else if (take) { m = cm1; ord = cr1; aptr = ca; bptr = cb; bit = 1; active = true; }
+                else active = false;
+                if (bit) U[(i >> 5) * 32 + lane] |= 1u << (i & 31);
+            }
+            bptr = wide_extend(B, T, lane, bptr, i, bit);
+            __syncwarp();
+        }
+        // ---- output in ascending (metric, order): sorted(paths, key=metric) (rtwm/fastpolar.py:335)
+        int rank = 0;
+        for (int j = 0; j < 32; ++j) {
+            const int aj = __shfl_sync(full, (int)active, j);
+            const double mj = __shfl_sync(full, m, j);
+            const int oj = __shfl_sync(full, ord, j);
+            if (aj && (mj < m || (mj == m && oj < ord))) ++rank;
+        }
+        const uint32_t am = __ballot_sync(full, active);
+        const int np = __popc(am);
+        const bool wr = active && rank < Lsz;
+        const size_t orow = (size_t)w * Lsz + (size_t)(wr ? rank : 0);
+        uint8_t* out = P.path_payload + orow * nbytes;
+        uint32_t crcreg = 0, crcbits = 0;
+        {
+            unsigned long long acc = 0;
+            int fill = 0, nb = 0;
+            const uint32_t crc_tab = smem_base() + (uint32_t)LY::CRC_OFF;
+#pragma unroll 1
+            for (int j = 0; j < 32; ++j) {
+                uint32_t v = U[j * 32 + lane] & ~c_frozen[j];
+#pragma unroll
+                for (int s5 = 0; s5 < 5; ++s5) {
+                    const uint32_t tt = v & c_cmp[j][s5];
+                    v = (v ^ tt) | (tt >> (1 << s5));
+                }
+                acc |= (unsigned long long)v << fill;
+                fill += c_cnt[j];
+#pragma unroll 1
+                while (fill >= 8) {
+                    const uint32_t byte = __brev((uint32_t)acc) >> 24;
+                    acc >>= 8; fill -= 8;
+                    if (nb < nbytes) {
+                        uint32_t t8;
+                        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(t8) : "r"(crc_tab + (crcreg ^ byte)) : "memory");
+                        crcreg = t8;
+                        if (wr) out[nb] = (uint8_t)byte;
+                    } else {
+                        crcbits = byte;
+                    }
+                    ++nb;
+                }
+            }
+        }
+        if (wr) {
+            P.path_crc[orow] = (crcreg == crcbits) ? 1 : 0;
+            P.path_metric[orow] = m;
+        }
+        // unused list slots of this codeword: metric +inf, crc 0 (as the fast kernel leaves them)
+        if (lane >= np && lane < Lsz) {
+            P.path_crc[(size_t)w * Lsz + lane] = 0;
+            P.path_metric[(size_t)w * Lsz + lane] = CUDART_INF;
+        }
+        if (lane == 0) P.npaths[w] = np;
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // hard-decision fast path (rtwm/fastpolar.py:261-276): one warp per codeword
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t warp_transform(uint32_t x, int lane)
@@ -1710,6 +1972,38 @@ int es_scl_list(const float* llr, const int32_t* index, int ncw, int neg_mode, i
 {
     return es_scl_list_margin(llr, index, ncw, neg_mode, list_size, scratch, scratch_bytes, path_payload, path_crc,
                               path_metric, npaths, nullptr, stream);
+}
+
+size_t es_scl_wide_scratch_bytes(void)
+{
+    return (size_t)sm_count() * WIDE_W * WIDE_SCRATCH_BYTES;
+}
+
+int es_scl_list_wide(const float* llr, int ncw, int neg_mode, int list_size, void* scratch, size_t scratch_bytes,
+                     uint8_t* path_payload, uint8_t* path_crc, double* path_metric, int32_t* npaths, void* stream)
+{
+    if (!g_code_ready) { set_error("es_scl_list_wide: call es_polar_set_code first"); return ES_ENOTREADY; }
+    if (list_size < 1 || list_size > 32) { set_error("es_scl_list_wide: list_size %d not in 1..32", list_size); return ES_EINVAL; }
+    if (ncw <= 0) return ES_OK;
+    if (neg_mode && (ncw & 1)) { set_error("es_scl_list_wide: neg_mode takes 2 codewords per row, got ncw=%d", ncw); return ES_EINVAL; }
+    SclDev* D;
+    int rc = scl_configure(&D);
+    if (rc != ES_OK) return rc;
+    int ctas = sm_count();
+    const int need_ctas = (ncw + WIDE_W - 1) / WIDE_W;
+    if (ctas > need_ctas) ctas = need_ctas;
+    const size_t need = (size_t)ctas * WIDE_W * WIDE_SCRATCH_BYTES;
+    if (!scratch || scratch_bytes < need) { set_error("es_scl_list_wide: scratch %zu < %zu bytes", scratch_bytes, need); return ES_EINVAL; }
+    const size_t smem = (size_t)SclLY::TAB_BYTES + (size_t)WIDE_W * 32 * 32 * sizeof(uint32_t);
+    ES_CUDA_OK(cudaFuncSetAttribute(scl_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // every slot pointer starts at 0 and level 0 is the LLR row itself; the bl bytes of a level are written before they are read
+    WideParams P;
+    P.llr = llr; P.ncw = ncw; P.neg_mode = neg_mode; P.list_size = list_size;
+    P.scratch = (unsigned char*)scratch; P.phi_tab = D->phi_tab;
+    P.path_payload = path_payload; P.path_crc = path_crc; P.path_metric = path_metric; P.npaths = npaths;
+    scl_wide_kernel<<<ctas, WIDE_W * 32, smem, (cudaStream_t)stream>>>(P);
+    ES_CUDA_OK(cudaGetLastError());
+    return ES_OK;
 }
 
 int es_scl_collect_hits(const uint8_t* hard_crc, const uint8_t* path_crc, const uint8_t* hard_payload,

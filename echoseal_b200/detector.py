@@ -9,7 +9,8 @@ inputs / outputs (BASELINE.json north_star).  There is no CPU fallback.
 
 Deviations from the reference, on purpose:
   * `list_size` defaults to 8 (north_star fixes SCL-8; the reference class default of 256 costs 33 s per
-    failing decode); larger values are accepted and served with 8 paths (polar_gpu.effective_list_size).
+    failing decode); 9..32 run on the wide-list kernel (exact, ~10x slower), larger values are accepted and served
+    with 32 paths and a warning (polar_gpu.effective_list_size).
   * nothing is printed.
 """
 from __future__ import annotations
@@ -106,7 +107,7 @@ class _Decode:
                 cnt, cw, slot, pl = polar_gpu.collect_hits(pay_h, crc_h, out, self.L, n)
                 self.h_cw, self.h_slot, self.h_pl = cw.cpu(), slot.cpu(), pl.cpu()
             cw = self.h_cw.numpy()[:n]; sl = self.h_slot.numpy()[:n]
-            order = np.argsort(cw * 16 + sl, kind="stable")
+            order = np.argsort(cw * 64 + sl, kind="stable")          # slot 0 = hard decision, 1..32 = list rank + 1
             hit_cw = np.ascontiguousarray(cw[order]); hit_slot = np.ascontiguousarray(sl[order])
             hit_pay = np.ascontiguousarray(self.h_pl.numpy()[:n][order])
             self._dev_out = None
@@ -329,7 +330,7 @@ class WatermarkDetector:
         self.session_nonce: bytes | None = None
         self._band_key = getattr(self.sec, "band_key", key32)      # rtwm/detector.py:31 (quirk 9)
         self._mf_cache = {}
-        self._list_size = polar_gpu.effective_list_size(list_size)     # ValueError below 1; above 8: SCL-8 and a warning
+        self._list_size = polar_gpu.effective_list_size(list_size)     # ValueError below 1; above 32: SCL-32 and a warning
         self._aead = getattr(self.sec, "_aead", None)
         self._pre_sy = 2.0 * PRE_BITS.astype(np.float32) - 1.0
         self._hdr_pn_bits = self.sec.pn_bits(0, HDR_L)

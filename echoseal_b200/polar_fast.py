@@ -1,7 +1,8 @@
 """B200-native drop-in for rtwm/polar_fast.py and rtwm/fastpolar.PolarCode: same names, arguments,
 return types and error behaviour (rtwm/polar_fast.py:26-87, rtwm/fastpolar.py:193-359); the arithmetic
 runs in the sm_100a kernels (es_polar_encode / es_scl_hard / es_scl_list).  `decode_batch` is additive.
-list_size above 8 is served with SCL-8 (north_star) and a one-time warning (polar_gpu.effective_list_size)."""
+list_size 9..32 runs on the wide-list kernel; above 32 it is served with SCL-32 and a one-time warning
+(polar_gpu.effective_list_size)."""
 from __future__ import annotations
 from typing import Callable, Optional, Tuple
 import numpy as np

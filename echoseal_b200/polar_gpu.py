@@ -11,23 +11,25 @@ from .polar_tables import frozen_mask
 
 _code_key = None
 _scratch = {}
-MAX_LIST = 8
+MAX_LIST = 32          # 1..8: the SCL-8 kernel; 9..32: the wide-list kernel (es_scl_list_wide, same arithmetic, ~10x slower)
+FAST_LIST = 8
 _warned_list = set()
+_scratch_wide = {}
 
 
 def effective_list_size(list_size: int) -> int:
-    """The list the kernels run: min(list_size, 8).  The reference accepts any list_size >= 1 (its constructor default is
-    256, rtwm/detector.py:27; its own quick test uses 32); the B200 path implements SCL-8 (north_star), so a larger
-    request is served with 8 paths and a one-time warning instead of an error.  Verdict parity with the reference at
-    list_size > 8 therefore holds for every frame SCL-8 recovers; a frame only a longer list would recover comes
-    back False / None here (INTEGRATION.md)."""
+    """The list the kernels run: min(list_size, 32).  The reference accepts any list_size >= 1 (its constructor default is
+    256, rtwm/detector.py:27; its own quick test uses 32).  Lists of 1..8 run on the SCL-8 kernel (north_star), 9..32 on
+    the wide-list kernel (exact, about a tenth of the rate); a larger request is served with 32 paths and a one-time
+    warning instead of an error: verdict parity with the reference then holds for every frame SCL-32 recovers
+    (INTEGRATION.md)."""
     L = int(list_size)
     if L < 1:
         raise ValueError("list_size must be >= 1")
     if L > MAX_LIST:
         if L not in _warned_list:
             import warnings
-            warnings.warn(f"list_size={L}: the B200 path decodes with SCL-{MAX_LIST}; larger lists are clamped", RuntimeWarning,
+            warnings.warn(f"list_size={L}: the B200 path decodes with at most SCL-{MAX_LIST}; larger lists are clamped", RuntimeWarning,
                           stacklevel=3)
             _warned_list.add(L)
         return MAX_LIST
@@ -85,8 +87,10 @@ def list_decode(llr: torch.Tensor, list_size: int = 8, neg_mode: int = 0, index:
     N.require_cuda(llr, index)
     if llr.dtype != torch.float32 or llr.dim() != 2 or llr.shape[1] != 1024:
         raise ValueError("llr must be float32 [rows,1024]")
-    if not (1 <= list_size <= 8):
-        raise ValueError("list_size must be in 1..8 on the B200 path")
+    if not (1 <= list_size <= MAX_LIST):
+        raise ValueError(f"list_size must be in 1..{MAX_LIST} on the B200 path")
+    if list_size > FAST_LIST and (want_margin or (index is not None and neg_mode)):
+        raise ValueError("want_margin / index with neg_mode are served by the SCL-8 kernel only (list_size <= 8)")
     set_code(1024, K)
     dev = llr.device
     ncw_total = llr.shape[0] * (2 if neg_mode else 1)
@@ -106,6 +110,25 @@ def list_decode(llr: torch.Tensor, list_size: int = 8, neg_mode: int = 0, index:
     else:
         n = ncw_total
     if n == 0:
+        return out
+    if list_size > FAST_LIST and index is not None:
+        # the wide kernel decodes whole batches: run it on the listed rows and scatter the results
+        sel = index.long()
+        sub = list_decode(llr[sel].contiguous(), list_size=list_size, K=K)
+        for k in ("payload", "crc", "metric", "npaths"):
+            out[k][sel] = sub[k]
+        return out
+    if list_size > FAST_LIST:
+        lib = N.lib()
+        lib.es_scl_wide_scratch_bytes.restype = C.c_size_t
+        key = (dev.index, torch.cuda.current_stream().cuda_stream)
+        sw = _scratch_wide.get(key)
+        if sw is None:
+            sw = _scratch_wide[key] = torch.empty(int(lib.es_scl_wide_scratch_bytes()), dtype=torch.uint8, device=dev)
+        with N.timed("scl_list_wide"):
+            N.check(lib.es_scl_list_wide(N.ptr(llr), C.c_int(n), C.c_int(neg_mode), C.c_int(list_size), N.ptr(sw),
+                                         C.c_size_t(sw.numel()), N.ptr(out["payload"]), N.ptr(out["crc"]),
+                                         N.ptr(out["metric"]), N.ptr(out["npaths"]), N.stream_ptr()), "es_scl_list_wide")
         return out
     scratch = _get_scratch(dev)
     with N.timed("scl_list"):

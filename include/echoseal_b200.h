@@ -51,6 +51,12 @@ int es_scl_list_margin(const float* llr, const int32_t* index, int ncw, int neg_
                        void* scratch, size_t scratch_bytes,
                        uint8_t* path_payload, uint8_t* path_crc, double* path_metric, int32_t* npaths,
                        double* min_margin /*[ncw_total]*/, void* stream);
+/* Wide-list decoder, list sizes 1..32 (rtwm/detector.py:27 accepts any list_size; the reference's quick test uses 32): the
+ * arithmetic and rules of es_scl_list in the plain bit-by-bit form, one warp per codeword, one lane per path; about a
+ * tenth of the SCL-8 rate.  Outputs as es_scl_list.  scratch: es_scl_wide_scratch_bytes() bytes of device memory. */
+size_t es_scl_wide_scratch_bytes(void);
+int es_scl_list_wide(const float* llr, int ncw, int neg_mode, int list_size, void* scratch, size_t scratch_bytes,
+                     uint8_t* path_payload, uint8_t* path_crc, double* path_metric, int32_t* npaths, void* stream);
 /* compaction of the CRC-passing candidates (hard decision = slot 0, list rank r = slot r+1): the inputs of the
  * validator callback of PolarCode.decode (rtwm/fastpolar.py:269-276, 335-349). Unordered; *counter may exceed cap. */
 int es_scl_collect_hits(const uint8_t* hard_crc, const uint8_t* path_crc, const uint8_t* hard_payload,

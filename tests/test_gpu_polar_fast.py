@@ -84,10 +84,13 @@ def test_error_behaviour(pf):
         pf.PolarCode(1024, 2000)                             # K > N
     with pytest.raises(ValueError):
         pf.PolarCode(1024, 448, list_size=0)
-    with pytest.warns(RuntimeWarning):                       # the reference accepts any list_size (its own quick test uses 32):
-        pc32 = pf.PolarCode(1024, 448, list_size=32)         # accepted here too, served with SCL-8
+    pc32 = pf.PolarCode(1024, 448, list_size=32)             # the reference's own quick test uses 32: the wide-list kernel
     llr = (2.0 * pf.encode(bytes(range(55))).astype(np.float32) - 1.0) * 4.0
     bits, ok = pc32.decode(llr)
+    assert ok and np.packbits(bits).tobytes() == bytes(range(55))
+    with pytest.warns(RuntimeWarning):                       # the reference default (256) is accepted and served with SCL-32
+        pc256 = pf.PolarCode(1024, 448, list_size=256)
+    bits, ok = pc256.decode(llr)
     assert ok and np.packbits(bits).tobytes() == bytes(range(55))
     with pytest.raises(ValueError):
         pf.PolarCode(1024, 448).encode(np.zeros(100, np.uint8))

@@ -141,3 +141,27 @@ def test_pn_sign_convention(api):
     frame = tx._make_frame_chips()
     pn = 2 * api.SecureChannel(KEY).pn_bits(0, frame.size)[191:].astype(np.float64) - 1
     assert abs(float(np.mean(frame[191:] * pn))) < 0.2
+
+
+def test_quick_roundtrip_list_size_32(api):
+    """The reference's own tests/test_roundtrip_quick.py builds WatermarkDetector(key, list_size=32): accepted here and
+    decoded with 32 paths (wide-list kernel), same verdict, attempt lists and number of SCL decodes as the oracle run with
+    the same list size (rtwm/detector.py:27,44-152)."""
+    import warnings
+    from oracle import detector_oracle as do
+    key = bytes(range(32))
+    tx = api.WatermarkEmbedder(key)
+    rng = np.random.default_rng(3)
+    t = np.arange(24000) / 48000.0
+    speech = (0.1 * np.sin(2 * np.pi * 220 * t) + 0.01 * rng.standard_normal(t.size)).astype(np.float32)
+    wm = np.concatenate([tx.process(speech[i:i + 1024]) for i in range(0, speech.size, 1024)])
+    with warnings.catch_warnings():
+        warnings.simplefilter("error")                      # no clamp warning at 32
+        rx = api.WatermarkDetector(key, list_size=32)
+    got = rx.verify(wm, 48000)
+    want, det = do.verify(wm.astype(np.float32), key, list_size=32, return_details=True)
+    assert got == want
+    r = rx.last_result
+    assert r.n_scl == det["n_scl"]
+    for bi in range(4):
+        assert r.attempts[bi] == [(int(a), int(b)) for a, b in det["attempts"][bi]]

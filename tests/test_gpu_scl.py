@@ -214,3 +214,34 @@ def test_encode_decode_roundtrip_large(gpu):
     llr = (bits.float() * 2 - 1) * 10.0
     ph, crc = polar_gpu.hard_decide(llr.contiguous())
     assert bool((crc == 1).all()) and bool((ph == pay).all())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("L", [16, 32, 12])
+def test_wide_list_matches_oracle_and_model(L):
+    """List sizes above 8 (es_scl_list_wide; rtwm/detector.py:27 accepts any list_size, the reference's quick test uses
+    32): every final path in order, CRC flags and metrics equal the device-arithmetic model bit for bit (ties included,
+    +row / -row pairing), and the glibc oracle's lists on the tie-free AWGN set (rtwm/fastpolar.py:280-349)."""
+    import torch
+    from echoseal_b200 import polar_gpu
+    from oracle import polar_oracle as po
+    from _inputs import awgn_llr_set, detector_like_llr_set
+    llr, _ = awgn_llr_set(48, seed=41)
+    d = torch.from_numpy(llr).cuda()
+    out = polar_gpu.list_decode(d, list_size=L)
+    model = po.scl_batch(llr, L=L, device_arith=True)
+    ref = po.scl_batch(llr, L=L)
+    pay = out["payload"].cpu().numpy(); crc = out["crc"].cpu().numpy(); met = out["metric"].cpu().numpy()
+    assert (out["npaths"].cpu().numpy() == model["npaths"]).all()
+    assert (pay == np.packbits(model["path_info"], axis=2)).all() and (crc == model["path_crc"]).all()
+    assert (met == model["path_metric"]).all()
+    tie_free = ref["stats"][:, 1] > 1e-11
+    assert tie_free.sum() >= 24
+    assert (pay[tie_free] == np.packbits(ref["path_info"], axis=2)[tie_free]).all() and (crc[tie_free] == ref["path_crc"][tie_free]).all()
+    np.testing.assert_allclose(met[tie_free], ref["path_metric"][tie_free], rtol=1e-12, atol=1e-15)   # phi is exactly 0 beyond d = 37
+    tl = detector_like_llr_set(12, seed=9)
+    out = polar_gpu.list_decode(torch.from_numpy(tl).cuda(), list_size=L, neg_mode=1)
+    model = po.scl_batch(tl, L=L, device_arith=True, neg_mode=True)
+    assert (out["payload"].cpu().numpy() == np.packbits(model["path_info"], axis=2)).all()
+    assert (out["crc"].cpu().numpy() == model["path_crc"]).all()
+    assert (out["metric"].cpu().numpy() == model["path_metric"]).all()
