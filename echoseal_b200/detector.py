@@ -67,16 +67,47 @@ class _Decode:
         self.I = int(enum["item_peak"].size)
         self.llr = None
         self.ev = None
+        self._items = None
+        self._buf = None
 
-    def enqueue_llr(self):
-        if not self.I:
+    def stage_items(self, stream, buf):
+        """host -> device copy of the item list and PN bits on a side stream into a persistent staging buffer (no
+        allocator traffic off the main stream): it runs under the SCL kernel of the previous sub-batch instead of
+        between two kernels of the main stream.  buf: dict(ip, pn, ev) owned by the caller; too small -> not staged."""
+        if not self.I or self._items is not None or buf is None or buf["ip"].numel() < self.I:
             return
         ip_h = torch.from_numpy(self.enum["item_peak"]).pin_memory()
         pn_h = torch.from_numpy(self.enum["pn"]).pin_memory()
         self._keep = (ip_h, pn_h)
-        ip = ip_h.to(self.dev, non_blocking=True)
-        pn = pn_h.to(self.dev, non_blocking=True)
+        ip, pn = buf["ip"][:self.I], buf["pn"][:self.I]
+        with torch.cuda.stream(stream):
+            if buf["ev"] is not None:
+                stream.wait_event(buf["ev"])                       # the llr kernel that read this buffer last (or its allocation)
+            ip.copy_(ip_h, non_blocking=True)
+            pn.copy_(pn_h, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(stream)
+        self._items = (ip, pn, ev)
+        self._buf = buf
+
+    def enqueue_llr(self):
+        if not self.I:
+            return
+        if self._items is not None:
+            ip, pn, ev = self._items
+            torch.cuda.current_stream().wait_event(ev)
+        else:
+            ip_h = torch.from_numpy(self.enum["item_peak"]).pin_memory()
+            pn_h = torch.from_numpy(self.enum["pn"]).pin_memory()
+            self._keep = (ip_h, pn_h)
+            ip = ip_h.to(self.dev, non_blocking=True)
+            pn = pn_h.to(self.dev, non_blocking=True)
         self.llr = rx_gpu.llr(self.mf, ip, pn)                      # [2I,1024]: PN variant 0 / 1 per item
+        if self._buf is not None:
+            self._buf["ev"] = torch.cuda.Event()
+            self._buf["ev"].record()
+            self._buf = None
+        self._items = None
 
     def enqueue_scl(self):
         if not self.I:
@@ -205,6 +236,8 @@ def verify_batch(keys, audio, *, fs_target: int = 48_000, list_size: int = 8, mf
     bounds = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
     end_of = {int(bounds[i]): int(bounds[i + 1]) for i in range(len(sizes))}
     copy_stream = None if is_tensor else torch.cuda.Stream()
+    item_stream = torch.cuda.Stream()
+    item_ring, item_use = [], [0]
     staged = {}
     # device staging ring for host input: three buffers of the largest sub-batch, allocated once per call, so the
     # side-stream copies never go through the caching allocator (cross-stream frees made it cudaMalloc / stall
@@ -269,6 +302,17 @@ def verify_batch(keys, audio, *, fs_target: int = 48_000, list_size: int = 8, mf
         sb.ev.synchronize()
         sb.enum = sb.bank.rx_enumerate(sb.kidx, n, sb.pk_h.numpy(), sb.npk_h.numpy(), sb.hdr_h.numpy())
         sb.dec = _Decode(sb.bank, sb.kidx, sb.enum, sb.fr["mf_aligned"], list_size, dev)
+        if sb.dec.I:
+            if not item_ring:
+                # two persistent staging buffers, sized from the first sub-batch's items per clip with 50 % headroom
+                cap = int(1.5 * sb.dec.I / max(1, sb.s1 - sb.s0) * max(sizes)) + 4096
+                for _ in range(2):
+                    b = dict(ip=torch.empty(cap, dtype=torch.int32, device=dev),
+                             pn=torch.empty((cap, 152), dtype=torch.uint8, device=dev), ev=torch.cuda.Event())
+                    b["ev"].record()                                # memory handed out in main-stream order
+                    item_ring.append(b)
+            sb.dec.stage_items(item_stream, item_ring[item_use[0] % 2])
+            item_use[0] += 1
 
     def finish(sb):
         ns = np.ascontiguousarray(nonce_state[sb.s0:sb.s1])
