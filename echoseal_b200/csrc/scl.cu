@@ -179,22 +179,6 @@ __device__ __forceinline__ void fcomb2(double a0, double b0, double a1, double b
     r1 = Q.b;
 #endif
 }
-// the same with the four chains inlined into the caller's loop (the passes over the DRAM-resident levels: no call, so
-// the loads, stores and g arithmetic of the loop schedule into the latency gaps of the chains)
-#ifndef ES_SCL_PHI_INL
-#define ES_SCL_PHI_INL 0
-#endif
-__device__ __forceinline__ void fcomb2_inl(double a0, double b0, double a1, double b1, uint32_t tab, double& r0, double& r1)
-{
-#if !ES_SCL_PHI_INL
-    fcomb2(a0, b0, a1, b1, tab, r0, r1);
-    return;
-#endif
-    const double p0 = psi_fast(a0 - b0, tab), p1 = psi_fast(a0 + b0, tab), p2 = psi_fast(a1 - b1, tab), p3 = psi_fast(a1 + b1, tab);
-    r0 = p0 - p1;
-    r1 = p2 - p3;
-}
-
 // same value as f(a, b), also handing out the two phi terms: fm = phi(|a-b|), fp = phi(|a+b|).
 // They are exactly the phi values the reference's penalty needs for the NEXT (odd) leaf, whose LLR is
 // b-a or b+a (rtwm/fastpolar.py:26-40) — so that penalty costs nothing.
@@ -265,23 +249,9 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 // generic-proxy writes (st.global / st.shared) before, async-proxy accesses (bulk copies) after
-#ifndef ES_SCL_DBG_DELAY
-#define ES_SCL_DBG_DELAY 0
-#endif
-#ifndef ES_SCL_DBG_FENCE
-#define ES_SCL_DBG_FENCE 0
-#endif
 __device__ __forceinline__ void fence_proxy_async()
 {
-#if ES_SCL_DBG_FENCE
-    __threadfence_system();
-    asm volatile("fence.proxy.async.global;" ::: "memory");
-#endif
     asm volatile("fence.proxy.async;" ::: "memory");
-#if ES_SCL_DBG_DELAY
-    __threadfence();
-    __nanosleep(ES_SCL_DBG_DELAY);
-#endif
 }
 __device__ __forceinline__ double lds_f64(uint32_t addr)
 {
@@ -312,15 +282,6 @@ struct SclParams {
 };
 
 constexpr int SCL_S = 6;   // first LLR-tree level kept in shared memory
-#ifndef ES_SCL_TMA
-#define ES_SCL_TMA 1         // 1: the passes read their source rows from the TMA-fed ring; 0: straight from global memory
-#endif
-#ifndef ES_SCL_TMA_GF
-#define ES_SCL_TMA_GF ES_SCL_TMA
-#endif
-#ifndef ES_SCL_TMA_F
-#define ES_SCL_TMA_F ES_SCL_TMA
-#endif
 constexpr int RING_STAGES = 2;      // the passes toggle between two stages (st ^= 1)
 #ifndef ES_SCL_RING_ALIAS
 #define ES_SCL_RING_ALIAS 1  // stage 1 lives in the rows of level 7 (dead while any DRAM-level pass runs: those rewrite levels <= 6,
@@ -512,9 +473,6 @@ __device__ __noinline__ void negate_level0(double* l0)
 // parameter (256 bytes; 32 for level 0, [position][codeword]) so that the eight loads of a chunk are one address
 // plus immediates; the four phi chains of a chunk are inlined (fcomb2_inl), so nothing is called inside the loops.
 // ---------------------------------------------------------------------------------------------
-#ifndef ES_SCL_DBG_VERIFY
-#define ES_SCL_DBG_VERIFY 0
-#endif
 #ifndef ES_SCL_PASS_INLINE
 #define ES_SCL_PASS_INLINE 1     // the two ring passes inlined into the kernel body (single call site each)
 #endif
@@ -666,7 +624,7 @@ __device__ __forceinline__ uint32_t pass_gf_body(const Lane& L, int l0, bool do_
         gd += 8 * 32;
         if (do_f) {
             double r0, r1;
-            fcomb2_inl(g0, gh0, g1, gh1, tab, r0, r1);
+            fcomb2(g0, gh0, g1, gh1, tab, r0, r1);
 #if ES_SCL_L2HINT
             if (!nat) { stg_hint(fd, r0, fpol); stg_hint(fd + f1, r1, fpol); }
             else
@@ -724,11 +682,11 @@ __device__ ES_PASS_INLINE uint32_t pass_f_fn(uint32_t wsm, double* gw, int lane,
         const uint32_t at = R.wait();
         if (c == half) fd = fbase + 32;
         ring_ld4<256>(at, 0, v0, v1, v2, v3);
-        fcomb2_inl(v0, v2, v1, v3, tab, r0, r1);               // f[r], f[r+q]
+        fcomb2(v0, v2, v1, v3, tab, r0, r1);               // f[r], f[r+q]
         fd[0] = r0; fd[dq] = r1;
         ring_ld4<256>(at, 4, v0, v1, v2, v3);
         R.refill(L, hi4(v0, v1, v2, v3));
-        fcomb2_inl(v0, v2, v1, v3, tab, r0, r1);               // f[r+1], f[r+1+q]
+        fcomb2(v0, v2, v1, v3, tab, r0, r1);               // f[r+1], f[r+1+q]
         fd[d1] = r0; fd[d1 + dq] = r1;
         fd += fstep;
     }
@@ -818,15 +776,7 @@ __device__ __forceinline__ void llr_update8(Lane& L, int i, int last)   // l0 <=
 // "tie contract").  Four interleaved partial sums over the elements in natural order, combined as
 // (s0 + s1) + (s2 + s3).  a = position 0 of the node in the lane's slot; lq >= 0: quarter-interleaved node
 // with quarters of 2^lq elements (>= 8), lq < 0: natural order.
-#ifndef ES_SCL_R0_INLINE
-#define ES_SCL_R0_INLINE 0
-#endif
-#if ES_SCL_R0_INLINE
-__device__ __forceinline__
-#else
-__device__ __noinline__
-#endif
-double r0_sum(const double* a, int lq, int count, uint32_t tab)
+__device__ __noinline__ double r0_sum(const double* a, int lq, int count, uint32_t tab)
 {
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
     const int step = (lq < 0) ? 32 : 128;
@@ -870,32 +820,8 @@ struct Carry { double c0, c1, c2, c3; uint32_t qb; };
 // pen0/pen1 = penalties of deciding 0 / 1 (rtwm/fastpolar.py:32-40).  Metrics are non-negative finite
 // doubles, so their bit patterns order like unsigned integers; the reference's stable tie-break
 // (candidate index 2*ord+bit) folds into the comparison as  (kj < k) + (kj == k && c) == (kj < k + c).
-#ifndef ES_SCL_NTH_LUT
-#define ES_SCL_NTH_LUT 1     // clone-source lookup (n-th set bit of the clone mask) from a 2 KB shared table
-#endif
-#ifndef ES_SCL_LOCKSTEP
-#define ES_SCL_LOCKSTEP 0    // n > 0 (power of two): CTA barrier every n quads
-#endif
-#ifndef ES_SCL_RANK_KEY
-#define ES_SCL_RANK_KEY 1    // 1: unique 64-bit integer keys exchanged through shared memory; 0: FP64 compares over shuffles
-#endif
-// general ranking of the 16 candidates of a codeword by (metric, path order, bit): the reference's stable tie-break
-// (candidate index 2*ord+bit) makes "<" a "<=" against later candidates
-__device__ __forceinline__ void rank_ties_body(double k0, double k1, int ord, int& r0, int& r1)
-{
-    const unsigned full = 0xffffffffu;
-    r0 = 0; r1 = 0;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const double k0j = __shfl_sync(full, k0, j, 8);
-        const double k1j = __shfl_sync(full, k1, j, 8);
-        const int oj = __shfl_sync(full, ord, j, 8);
-        const bool lt = oj < ord, le = oj <= ord;
-        r0 += (int)((k0j < k0) || (lt && k0j == k0)) + (int)((k1j < k0) || (lt && k1j == k0));
-        r1 += (int)((k0j < k1) || (le && k0j == k1)) + (int)((k1j < k1) || (lt && k1j == k1));
-    }
-}
-// The same order as ONE unsigned 64-bit key per candidate.  A path metric is a sum of penalties that are each 0 or
+// Ranking of the 16 candidates of a codeword by (metric, path order, bit) = the reference's stable sort over candidates
+// appended in (path, 0, 1) order (rtwm/fastpolar.py:288-299), as ONE unsigned 64-bit key per candidate.  A path metric is a sum of penalties that are each 0 or
 // >= 2^-54 (phi_fast is exactly 0 or >= 2^-53; |leaf| is only added on top of phi), so it is 0 or >= 2^-54 and < 2^64: its
 // exponent field spans fewer than 128 values above 960 and the bit pattern, rebased there, leaves four low bits for the
 // candidate index.  Keys are unique, so the rank is a plain count of smaller keys.
@@ -914,7 +840,6 @@ __device__ __forceinline__ int info_step(Lane& L, int list_size, double pen0, do
     const unsigned full = 0xffffffffu;
     const double m0 = L.m + pen0, m1 = L.m + pen1;
     int r0 = 0, r1 = 0;
-#if ES_SCL_RANK_KEY
     {
         const unsigned long long k0 = L.active ? rank_key(m0, 2u * (uint32_t)L.ord) : ~0ull;
         const unsigned long long k1 = L.active ? rank_key(m1, 2u * (uint32_t)L.ord + 1u) : ~0ull;
@@ -931,13 +856,6 @@ __device__ __forceinline__ int info_step(Lane& L, int list_size, double pen0, do
             r1 += (int)(k0j < k1) + (int)(k1j < k1);
         }
     }
-#else
-    {
-        // metrics are non-negative finite doubles; candidates of inactive lanes are +inf: never "before" anything.
-        const double k0 = L.active ? m0 : CUDART_INF, k1 = L.active ? m1 : CUDART_INF;
-        rank_ties_body(k0, k1, L.ord, r0, r1);
-    }
-#endif
     if (MG) {
         // prune margin (rtwm/fastpolar.py:288-299 sorts the 2|P| candidates and keeps L): relative gap between rank L-1
         // and rank L, minimum over the decode.  gap/den is compared by cross-multiplication; one division at the end.
@@ -959,16 +877,13 @@ __device__ __forceinline__ int info_step(Lane& L, int list_size, double pen0, do
     // clone source for free lanes (j-th free lane takes the j-th clone)
     const int jfree = __popc(fm & ((1u << L.p()) - 1u));
     const bool take = !(s0 || s1) && (jfree < __popc(cm));
-#if ES_SCL_NTH_LUT
-    int src = L.p();
+    int src = L.p();                 // clone source: the jfree-th set bit of the clone mask, from a 2 KB shared table
     if (take) {
         uint32_t v;
         asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(smem_base() + (uint32_t)SclLY::NTH_OFF + cm * 8u + (uint32_t)jfree) : "memory");
         src = (int)v;
     }
-#else
-    const int src = take ? nth_set8(cm, jfree) : L.p();
-#endif
+
     const double cm1 = __shfl_sync(full, m1, src, 8);
     const int cr1 = __shfl_sync(full, r1, src, 8);
     const uint32_t cptr = __shfl_sync(full, L.ptr, src, 8);
@@ -1098,12 +1013,7 @@ __global__ void __maxnreg__(ES_SCL_MAXNREG) scl_list_kernel(SclParams P)
 #define gscr (L.gw)
 
 #pragma unroll 1
-#if ES_SCL_LOCKSTEP
-    for (int grp0 = blockIdx.x * W; grp0 < ((P.nunits + 3) >> 2); grp0 += gridDim.x * W) {
-        const int grp = grp0 + warp;                   // every warp of the CTA runs every trip (surplus warps redo the last unit, unwritten)
-#else
     for (int grp = blockIdx.x * W + warp; grp < ((P.nunits + 3) >> 2); grp += gridDim.x * W) {
-#endif
         const int j = grp * 4 + (L.lane >> 3);
         bool valid = j < P.nunits;
         const int jj = valid ? j : (P.nunits - 1);
@@ -1139,9 +1049,6 @@ __global__ void __maxnreg__(ES_SCL_MAXNREG) scl_list_kernel(SclParams P)
 #pragma unroll 1
         for (int q = qfirst; q < 256; ++q) {
             const int i = q << 2;
-#if ES_SCL_LOCKSTEP
-            if ((q & (ES_SCL_LOCKSTEP - 1)) == 0) __syncthreads();   // all warps of the CTA in the same loops: one hot code region per SM
-#endif
             if (q == 128 && P.pair && pass == 0) {
                 // bit 512: everything the second half reads from the first half is the level-1 partial sums
                 // (global rows, never rewritten) plus these per-lane words
@@ -1892,14 +1799,6 @@ int es_polar_set_code(const uint8_t* frozen_host, int K)
     return ES_OK;
 }
 
-#if ES_SCL_DBG_VERIFY
-int es_scl_debug_read(unsigned long long* out, int n)
-{
-    ES_CUDA_OK(cudaDeviceSynchronize());
-    ES_CUDA_OK(cudaMemcpyFromSymbol(out, es::g_dbg, sizeof(unsigned long long) * (size_t)(n < 256 ? n : 256)));
-    return ES_OK;
-}
-#endif
 
 int es_scl_grid_ctas(void)
 {

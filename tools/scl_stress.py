@@ -31,24 +31,5 @@ def main():
         else:
             print("  identical to rep 0:", bool((pay == first[0]).all() and (met == first[1]).all()))
 
-def dump_debug():
-    import ctypes as C
-    from echoseal_b200 import _native as N
-    if not hasattr(N.lib(), "es_scl_debug_read"):
-        return
-    buf = (C.c_ulonglong * 256)()
-    N.lib().es_scl_debug_read(buf, 256)
-    import struct
-    print("debug mismatches:", buf[0])
-    for n in range(min(int(buf[0]), 60)):
-        tag = buf[4 + 4 * n]
-        f = lambda u: struct.unpack("d", struct.pack("Q", u))[0]
-        print(f"  kind={tag >> 56} lvl={(tag >> 48) & 255} chunk={(tag >> 32) & 0xffff} cta={(tag >> 16) & 0xffff} which={(tag >> 8) & 255} lane={tag & 255} "
-              f"staged={f(buf[5 + 4 * n]):.6g} direct={f(buf[6 + 4 * n]):.6g} clk={buf[7 + 4 * n]}")
-
 if __name__ == "__main__":
     main()
-    try:
-        dump_debug()
-    except AttributeError:
-        pass
