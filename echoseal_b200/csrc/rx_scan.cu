@@ -16,6 +16,7 @@
 // peaks i32 [clips][4][25] ; mf_aligned f32 [clips][4][25][1024].
 #include "common.cuh"
 #include <math_constants.h>
+#include <cuda.h>          // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
 
 namespace es {
 
@@ -141,6 +142,120 @@ __global__ void __launch_bounds__(BP_WARPS * 32, BP_MIN_CTAS) bandpass_kernel(co
             __syncwarp();
         }
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1, TMA form.  Same lane-per-chunk recurrence, chunk grid and input double buffer as bandpass_kernel; the RESULTS leave
+// through the tensor-memory accelerator: every 8 samples the warp's tile [32 chunks][8 samples] of a band is one
+// cp.async.bulk.tensor.4d store (SASS UTMASTG) from a 64-byte-swizzled shared tile, coordinates (sample, chunk, band, clip)
+// in the tensor map of y.  Only the very last chunk of a clip is ragged (it ends at the clip end, n, not at the chunk
+// length): tiles of that chunk beyond n go out through a second tensor map whose box has 31 rows, and lane 31 writes the
+// one partially valid tile itself.  The transposing store loop of bandpass_kernel (4 bands x 8 row groups x
+// ~12 instructions per 8 samples and lane, two thirds of that kernel's non-FP64 instructions) becomes 4 instructions of
+// one lane.  Two tile sets alternate: a set is refilled only after cp.async.bulk.wait_group.read has seen its stores read it.
+// ---------------------------------------------------------------------------------------------
+struct BpTmaShared {
+    double yout[2][NBANDS][32][8];          // 64-byte rows, 16-byte units XOR-swizzled with (row >> 1) & 3 (SWIZZLE_64B)
+    float xin[2][32][BP_STEP + 1];
+};
+
+template <bool ODDZ>
+__global__ void __launch_bounds__(32, 10) bandpass_tma_kernel(const float* __restrict__ x, int nclips, int n, long long x_stride,
+                                                              double* __restrict__ y, const __grid_constant__ CUtensorMap tmy,
+                                                              const __grid_constant__ CUtensorMap tmy31, int ch, int groups)
+{
+    extern __shared__ __align__(1024) unsigned char bp_raw[];
+    BpTmaShared& S = *reinterpret_cast<BpTmaShared*>(bp_raw);
+    const int lane = threadIdx.x;
+    const long long wid = blockIdx.x;
+    if (wid >= (long long)nclips * groups) return;
+    const int grp = (int)(wid % groups);
+    const int clip = (int)(wid / groups);
+    const float* xs = x + (long long)clip * x_stride;
+    double z[NBANDS][8];
+#pragma unroll
+    for (int bd = 0; bd < NBANDS; ++bd)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) z[bd][i] = 0.0;
+    const int chunk0 = grp * 32;
+    // samples of the clip inside the last chunk of this warp (rows 0..30 are always whole)
+    const long long lim_ll = (long long)n - (long long)(chunk0 + 31) * ch;
+    const int last_lim = lim_ll >= ch ? ch : (lim_ll < 0 ? 0 : (int)lim_ll);
+    const int nsteps = (BP_WARM + ch + BP_STEP - 1) / BP_STEP;
+    auto fetch = [&](int st) {          // as bandpass_kernel: row r = chunk chunk0 + r, two rows per instruction
+        const int rel = -BP_WARM + st * BP_STEP + (lane & 15);
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&S.xin[st & 1][lane >> 4][lane & 15]);
+#pragma unroll 8
+        for (int i = 0; i < 16; ++i) {
+            const long long j = (long long)(chunk0 + 2 * i + (lane >> 4)) * ch + rel;
+            const bool in = (j >= 0 && j < n);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + i * 2 * (BP_STEP + 1) * 4),
+                         "l"(xs + (in ? j : 0)), "r"(in ? 4 : 0));
+        }
+        asm volatile("cp.async.commit_group;");
+    };
+    fetch(0);
+    // this lane's row in a tile: unit u (two doubles) of row `lane` sits at unit u ^ ((lane >> 1) & 3)
+    const int sw = (lane >> 1) & 3;
+    int tile = 0;                       // tiles stored so far: set = tile & 1
+#pragma unroll 1
+    for (int st = 0; st < nsteps; ++st) {
+        const int rel = -BP_WARM + st * BP_STEP;
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncwarp();
+        if (st + 1 < nsteps) fetch(st + 1);
+        const float(*xin)[BP_STEP + 1] = S.xin[st & 1];
+#pragma unroll 1
+        for (int q8 = 0; q8 < BP_STEP / 8; ++q8) {
+            const int o0 = rel + q8 * 8;
+            const bool emit = (o0 >= 0 && o0 < ch);
+            const int set = tile & 1;
+            if (emit) {
+                // the stores issued from this set two tiles ago must have read it
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                __syncwarp();
+            }
+#pragma unroll 2
+            for (int t = 0; t < 8; ++t) {
+                const double xn = (double)xin[lane][q8 * 8 + t];
+#pragma unroll
+                for (int bd = 0; bd < NBANDS; ++bd) {
+                    const double yn = fma(c_bp_b[bd][0], xn, z[bd][0]);
+#pragma unroll
+                    for (int i = 0; i < 7; ++i) {
+                        const double zi = (ODDZ && !(i & 1)) ? z[bd][i + 1] : fma(c_bp_b[bd][i + 1], xn, z[bd][i + 1]);
+                        z[bd][i] = fma(-c_bp_a[bd][i + 1], yn, zi);
+                    }
+                    z[bd][7] = fma(-c_bp_a[bd][8], yn, c_bp_b[bd][8] * xn);
+                    if (emit) S.yout[set][bd][lane][(((t >> 1) ^ sw) << 1) | (t & 1)] = yn;
+                }
+            }
+            if (emit) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the tile was written with ordinary stores
+                __syncwarp();
+                const bool whole = (o0 + 8 <= last_lim);          // row 31 of the tile lies inside the clip
+                if (lane == 0) {
+                    const CUtensorMap* tm = whole ? &tmy : &tmy31;
+#pragma unroll
+                    for (int bd = 0; bd < NBANDS; ++bd) {
+                        const uint32_t src = (uint32_t)__cvta_generic_to_shared(&S.yout[set][bd][0][0]);
+                        asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3, %4}], [%5];"
+                                     ::"l"(tm), "r"(o0), "r"(chunk0), "r"(bd), "r"(clip), "r"(src) : "memory");
+                    }
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                if (!whole && lane == 31 && o0 < last_lim) {      // the one partially valid tile of the clip's last chunk
+                    double* yr = y + (long long)clip * NBANDS * n + (long long)(chunk0 + 31) * ch + o0;
+#pragma unroll
+                    for (int bd = 0; bd < NBANDS; ++bd)
+                        for (int t = 0; t < 8 && o0 + t < last_lim; ++t)
+                            yr[(long long)bd * n + t] = S.yout[set][bd][31][(((t >> 1) ^ sw) << 1) | (t & 1)];
+                }
+                ++tile;
+            }
+        }
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // all stores complete before the CTA exits
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1662,19 +1777,81 @@ int es_rx_set_filters(const double* bp_b /*[4][9]*/, const double* bp_a /*[4][9]
     return ES_OK;
 }
 
+// chunk grid of K1 (and of the fused scan): a function of n ONLY -- the chunk boundaries decide where the (4e-13)
+// warm-up truncation falls, so a clip's filtered samples, and everything downstream, are bit-identical whatever batch
+// it is verified in.  About BP_CHUNK samples per chunk, a clip = a whole number of 32-chunk warps, the chunk length a
+// multiple of 16 samples so that the rows of y start on 128-byte lines.
+static void bp_chunk_grid(int n, int* groups_out, int* ch_out)
+{
+    int groups = (int)(((long long)n + 16LL * BP_CHUNK) / (32LL * BP_CHUNK));
+    if (groups < 1) groups = 1;
+    int ch = (int)(((long long)n + 32LL * groups - 1) / (32LL * groups));
+    ch = (ch + 15) & ~15;
+    *groups_out = groups; *ch_out = ch;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tensor_map_encoder()
+{
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+static int g_bp_force_plain = 0;
+void es_rx_bandpass_force_plain(int on) { g_bp_force_plain = on ? 1 : 0; }      // tests: the non-TMA form on the same chunk grid
+
 int es_rx_bandpass(const float* x, int nclips, int n, long long x_stride, double* y, void* stream)
 {
     if (!g_rx_ready) { set_error("es_rx_bandpass: call es_rx_set_filters first"); return ES_ENOTREADY; }
     if (nclips <= 0 || n <= 0) return ES_OK;
-    // chunk length: about BP_CHUNK, such that a clip is a whole number of 32-chunk warps.  A function of n ONLY:
-    // the chunk boundaries decide where the (4e-13) warm-up truncation falls, so a clip's filtered samples -- and
-    // everything downstream -- are bit-identical whatever batch it is verified in.
-    int groups = (int)(((long long)n + 16LL * BP_CHUNK) / (32LL * BP_CHUNK));
-    if (groups < 1) groups = 1;
-    int ch = (int)(((long long)n + 32LL * groups - 1) / (32LL * groups));
-    ch = (ch + 15) & ~15;                                  // rows of y start on 128-byte lines
+    int groups, ch;
+    bp_chunk_grid(n, &groups, &ch);
     const long long warps = (long long)nclips * groups;
     const unsigned grid = (unsigned)((warps + BP_WARPS - 1) / BP_WARPS);
+    // TMA form: rows of y 16-byte aligned (n even), and only the last chunk of a clip ragged
+    const bool tma_ok = !g_bp_force_plain && (n % 2) == 0 && ((reinterpret_cast<uintptr_t>(y) & 15u) == 0) &&
+                        (32LL * groups * ch - n) < ch && warps <= 0x7fffffffLL;
+    EncodeTiledFn enc = tma_ok ? tensor_map_encoder() : nullptr;
+    if (enc) {
+        // y as a 4-d tensor (sample in chunk, chunk, band, clip); box = 8 samples x 32 (31) chunks of one band of one clip.
+        // The chunk dimension counts only chunks that START inside the clip; a box row beyond it is dropped by the hardware.
+        CUtensorMap tm, tm31;
+        const cuuint64_t nchunks = (cuuint64_t)(((long long)n + ch - 1) / ch);
+        const cuuint64_t dims[4] = {(cuuint64_t)ch, nchunks, (cuuint64_t)NBANDS, (cuuint64_t)nclips};
+        const cuuint64_t strides[3] = {(cuuint64_t)ch * 8u, (cuuint64_t)n * 8u, (cuuint64_t)n * 8u * NBANDS};
+        const cuuint32_t box[4] = {8, 32, 1, 1}, box31[4] = {8, 31, 1, 1};
+        const cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, (void*)y, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r == CUDA_SUCCESS)
+            r = enc(&tm31, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, (void*)y, dims, strides, box31, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r == CUDA_SUCCESS) {
+            int& configured = g_rxdev[current_device()].cfg[5];
+            if (!configured) {
+                ES_CUDA_OK(cudaFuncSetAttribute(bandpass_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BpTmaShared) + 1024));
+                ES_CUDA_OK(cudaFuncSetAttribute(bandpass_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BpTmaShared) + 1024));
+                ES_CUDA_OK(cudaFuncSetAttribute(bandpass_tma_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+                ES_CUDA_OK(cudaFuncSetAttribute(bandpass_tma_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+                configured = 1;
+            }
+            const size_t smem = sizeof(BpTmaShared);
+            if (g_bp_oddz) bandpass_tma_kernel<true><<<(unsigned)warps, 32, smem, (cudaStream_t)stream>>>(x, nclips, n, x_stride, y, tm, tm31, ch, groups);
+            else bandpass_tma_kernel<false><<<(unsigned)warps, 32, smem, (cudaStream_t)stream>>>(x, nclips, n, x_stride, y, tm, tm31, ch, groups);
+            ES_CUDA_OK(cudaGetLastError());
+            return ES_OK;
+        }
+    }
     if (g_bp_oddz) bandpass_kernel<true><<<grid, BP_WARPS * 32, 0, (cudaStream_t)stream>>>(x, nclips, n, x_stride, y, ch, groups);
     else bandpass_kernel<false><<<grid, BP_WARPS * 32, 0, (cudaStream_t)stream>>>(x, nclips, n, x_stride, y, ch, groups);
     ES_CUDA_OK(cudaGetLastError());
@@ -1686,11 +1863,8 @@ int es_rx_scan(const float* x, int nclips, int n, long long x_stride, double* co
     if (!g_rx_ready) { set_error("es_rx_scan: call es_rx_set_filters first"); return ES_ENOTREADY; }
     const int nc = n - (PRE_L - 1);
     if (nclips <= 0 || nc <= 0) return ES_OK;
-    // the chunk grid of es_rx_bandpass (a function of n only)
-    int groups = (int)(((long long)n + 16LL * BP_CHUNK) / (32LL * BP_CHUNK));
-    if (groups < 1) groups = 1;
-    int ch = (int)(((long long)n + 32LL * groups - 1) / (32LL * groups));
-    ch = (ch + 15) & ~15;
+    int groups, ch;
+    bp_chunk_grid(n, &groups, &ch);          // the chunk grid of es_rx_bandpass
     const long long blocks = (long long)nclips * groups * NBANDS;
     if (blocks > 0x7fffffffLL) { set_error("es_rx_scan: %lld warps exceed the grid", blocks); return ES_EINVAL; }
     const bool aligned = ((reinterpret_cast<uintptr_t>(x) & 15u) == 0) && ((x_stride & 3) == 0);

@@ -64,6 +64,11 @@ def set_filters(fs: int, mf_taps: list[np.ndarray]):
     _filter_sig = sig
 
 
+def bandpass_force_plain(on: bool):
+    """tests: run K1 without the TMA store path (same chunk grid, so the two forms are comparable bit for bit)"""
+    N.lib().es_rx_bandpass_force_plain(C.c_int(1 if on else 0))
+
+
 def bandpass(x: torch.Tensor) -> torch.Tensor:
     """x float32[B,n] -> y float64[B,4,n] (K1)."""
     N.require_cuda(x)

@@ -75,6 +75,8 @@ int es_rx_set_filters(const double* bp_b /*[4][9]*/, const double* bp_a /*[4][9]
 /* K1: y = lfilter(b, a, x) for the 4 bands (rtwm/detector.py:59-60) */
 int es_rx_bandpass(const float* x /*[clips][x_stride]*/, int nclips, int n, long long x_stride,
                    double* y /*[clips][4][n]*/, void* stream);
+/* test hook: 1 = K1 without its TMA tensor-store form (same chunk grid: both forms give the same bits) */
+void es_rx_bandpass_force_plain(int on);
 /* K2: cosine-normalised preamble correlation (rtwm/detector.py:76-79) */
 int es_rx_ncc(const double* y, int nclips, int n, double* corr /*[clips][4][n-62]*/, void* stream);
 /* K1+K2 fused (rtwm/detector.py:59-60,75-79): band-pass and normalised correlation in one pass, the filtered signal

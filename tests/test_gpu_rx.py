@@ -595,3 +595,22 @@ def test_fused_scan_ragged_and_unaligned(env):
         ref = rx_gpu.ncc(rx_gpu.bandpass(x.contiguous()))
         assert corr.shape == ref.shape
         assert float((corr - ref).abs().max()) < 1e-11, (B, n, pitch)
+
+
+@pytest.mark.gpu
+def test_bandpass_tma_store_equals_plain_form(env):
+    """K1 writes y through cp.async.bulk.tensor stores when the clip divides into even-length chunks exactly (144 000 =
+    64 x 2250): bit-identical to the transposing-store form on the same chunk grid, at several batch sizes; lengths that
+    do not divide take the plain form."""
+    torch, rx_gpu, detector, clips, taps = env
+    g = torch.Generator(device="cuda").manual_seed(11)
+    for B, n in [(1, 144000), (5, 144000), (3, 288000), (2, 48000), (2, 143999), (2, 147456), (1, 100002), (3, 2000), (1, 1000000)]:
+        x = (torch.randn((B, n), device="cuda", generator=g) * 0.1).contiguous()
+        y = rx_gpu.bandpass(x)
+        rx_gpu.bandpass_force_plain(True)
+        try:
+            y0 = rx_gpu.bandpass(x)
+        finally:
+            rx_gpu.bandpass_force_plain(False)
+        assert bool((y == y0).all()), (B, n)
+        assert bool(torch.isfinite(y).all())
