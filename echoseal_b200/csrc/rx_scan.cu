@@ -273,11 +273,28 @@ __host__ __device__ __forceinline__ constexpr int ncc_pad(int j) { return j + (j
 
 constexpr int NCC_SPAN = 12;                    // consecutive tiles per CTA (input tiles double-buffered with cp.async)
 
+// K3's first pass done by its producer (es_rx_ncc_hist): the 2048-bin monotone histogram of the row and the values of the
+// six central bins (where the median of a correlation row sits), so that K3 reads corr only once.  Bins as K3's sel_bin<0>.
+constexpr int NCC_HBINS = 2048;
+constexpr int NCC_SPEC_LO = 1021, NCC_SPEC_HI = 1027, NCC_SPEC_CAP = 6144;
+__device__ __forceinline__ int ncc_bin(double v)
+{
+    const double s = (v + 1.0) * 1024.0;
+    return (s >= 2047.0) ? 2047 : ((s <= 0.0) ? 0 : (int)s);
+}
+struct NccAux { unsigned int* hist; double* spec; unsigned int* nspec; };   // [rows][2048], [rows][NCC_SPEC_CAP], [rows]
+
+template <bool AUX>
 __global__ void __launch_bounds__(256, 4) ncc_kernel(const double* __restrict__ y, int n, int nc,
-                                                     double* __restrict__ corr)
+                                                     double* __restrict__ corr, NccAux aux)
 {
     extern __shared__ __align__(16) double ncc_sm[];
     constexpr int BUF = ncc_pad(NCC_IN) + 1;
+    unsigned int* sh = reinterpret_cast<unsigned int*>(ncc_sm + 2 * BUF);     // AUX: this CTA's share of the row histogram
+    if (AUX) {
+        for (int b = threadIdx.x; b < NCC_HBINS; b += 256) sh[b] = 0;
+        __syncthreads();
+    }
     const int cb = blockIdx.y;                  // clip*4 + band
     const int band = cb & 3;
     const double* ys = y + (long long)cb * n;
@@ -342,9 +359,24 @@ __global__ void __launch_bounds__(256, 4) ncc_kernel(const double* __restrict__ 
         __syncthreads();
         for (int t = threadIdx.x; t < NCC_TILE; t += 256) {
             const int i = i0 + t;
-            if (i < nc) cs[i] = sy[ncc_pad(t)];
+            if (i < nc) {
+                const double v = sy[ncc_pad(t)];
+                cs[i] = v;
+                if (AUX) {
+                    const int b = ncc_bin(v);
+                    atomicAdd(&sh[b], 1u);
+                    if (b >= NCC_SPEC_LO && b < NCC_SPEC_HI) {
+                        const unsigned int p = atomicAdd(&aux.nspec[cb], 1u);
+                        if (p < (unsigned)NCC_SPEC_CAP) aux.spec[(long long)cb * NCC_SPEC_CAP + p] = v;
+                    }
+                }
+            }
         }
         __syncthreads();                            // the buffer is refilled two tiles later
+    }
+    if (AUX) {
+        unsigned int* gh = aux.hist + (long long)cb * NCC_HBINS;
+        for (int b = threadIdx.x; b < NCC_HBINS; b += 256) { const unsigned int c = sh[b]; if (c) atomicAdd(&gh[b], c); }
     }
 }
 
@@ -843,6 +875,7 @@ constexpr int PK2_CAP = 6144;          // gathered values per stage (about 2700 
 constexpr int PK2_SUB = 2048;          // values of the (sub-)bins holding the two middle ranks
 constexpr int PK2_NCAND = 2048;        // threshold candidates / top-bin candidates
 constexpr int PK2_SPEC_LO = 1021, PK2_SPEC_HI = 1027;   // speculative median bins
+static_assert(PK2_CAP == NCC_SPEC_CAP && PK2_SPEC_LO == NCC_SPEC_LO && PK2_SPEC_HI == NCC_SPEC_HI && SEL_BINS == NCC_HBINS, "K2 forms K3's first pass");
 constexpr int PK2_UNROLL = 8;          // loads in flight per thread in the streaming passes
 constexpr int PK2_MIN_NC = 8192;       // shorter rows go to the general form directly
 
@@ -877,9 +910,11 @@ __device__ __forceinline__ void pk2_select2(Pk2Shared& S, int ms, int ra, int rb
     __syncthreads();
 }
 
+// aux (optional): the histogram and central-bin values the producer of corr already formed (es_rx_ncc_hist): pass A is
+// then a copy of 8 + <= 48 KB instead of a streaming pass over the 1.15 MB row
 __global__ void __launch_bounds__(PK_THREADS) peaks2_kernel(const double* __restrict__ corr, int nc,
                                                             int32_t* __restrict__ peaks, int32_t* __restrict__ npeaks,
-                                                            double* __restrict__ stats)
+                                                            double* __restrict__ stats, NccAux aux)
 {
     extern __shared__ __align__(16) unsigned char pk_raw[];
     PkUnion& U = *reinterpret_cast<PkUnion*>(pk_raw);
@@ -896,6 +931,15 @@ __global__ void __launch_bounds__(PK_THREADS) peaks2_kernel(const double* __rest
     for (int b = tid; b < SEL_BINS; b += PK_THREADS) S.hist[b] = 0;
     if (tid == 0) { S.nbuf = 0; S.nsub = 0; S.ncand = 0; S.ntop = 0; S.nkeep = 0; S.below_cnt = 0; S.npeaks = 0; }
     __syncthreads();
+    if (aux.hist) {
+        const unsigned int* gh = aux.hist + (long long)cb * NCC_HBINS;
+        for (int b = tid; b < SEL_BINS; b += PK_THREADS) S.hist[b] = gh[b];
+        const unsigned int ns = aux.nspec[cb];
+        const double* gs = aux.spec + (long long)cb * NCC_SPEC_CAP;
+        const unsigned int take = ns < (unsigned)PK2_CAP ? ns : (unsigned)PK2_CAP;
+        for (unsigned int i = tid; i < take; i += PK_THREADS) S.buf[i] = gs[i];
+        if (tid == 0) S.nbuf = ns;
+    } else {
     // PK2_UNROLL loads in flight per thread: with 1024 threads per SM the streaming passes need that to reach HBM speed
     for (int i0 = tid; i0 < nc; i0 += PK_THREADS * PK2_UNROLL) {
         double vv[PK2_UNROLL];
@@ -913,6 +957,7 @@ __global__ void __launch_bounds__(PK_THREADS) peaks2_kernel(const double* __rest
                 if (p < (unsigned)PK2_CAP) S.buf[p] = v;
             }
         }
+    }
     }
     __syncthreads();
     if (warp == 0) {            // exclusive prefix over the 2048 bins: 64 bins per lane
@@ -1892,28 +1937,47 @@ int es_rx_scan(const float* x, int nclips, int n, long long x_stride, double* co
     return ES_OK;
 }
 
-int es_rx_ncc(const double* y, int nclips, int n, double* corr, void* stream)
+// hist u32[rows][2048], spec f64[rows][6144], nspec u32[rows] (rows = clips * 4): K3's first pass formed by K2 while the
+// correlation values are at hand; all three may be null (plain es_rx_ncc).  hist and nspec are zeroed here.
+int es_rx_ncc_hist(const double* y, int nclips, int n, double* corr, uint32_t* hist, double* spec, uint32_t* nspec, void* stream)
 {
     if (!g_rx_ready) { set_error("es_rx_ncc: call es_rx_set_filters first"); return ES_ENOTREADY; }
     const int nc = n - (PRE_L - 1);
     if (nclips <= 0 || nc <= 0) return ES_OK;
+    const bool aux_on = hist && spec && nspec;
     const int ntiles = (nc + NCC_TILE - 1) / NCC_TILE;
-    const size_t smem = 2 * (size_t)(ncc_pad(NCC_IN) + 1) * sizeof(double);
+    const size_t smem = 2 * (size_t)(ncc_pad(NCC_IN) + 1) * sizeof(double) + (aux_on ? NCC_HBINS * sizeof(unsigned int) : 0);
     int& configured = g_rxdev[current_device()].cfg[0];
     if (!configured) {
-        ES_CUDA_OK(cudaFuncSetAttribute(ncc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int big = (int)(2 * (size_t)(ncc_pad(NCC_IN) + 1) * sizeof(double) + NCC_HBINS * sizeof(unsigned int));
+        ES_CUDA_OK(cudaFuncSetAttribute(ncc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+        ES_CUDA_OK(cudaFuncSetAttribute(ncc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
         configured = 1;
     }
     dim3 grid((ntiles + NCC_SPAN - 1) / NCC_SPAN, nclips * NBANDS);
-    ncc_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(y, n, nc, corr);
+    NccAux aux{hist, spec, nspec};
+    if (aux_on) {
+        ES_CUDA_OK(cudaMemsetAsync(hist, 0, (size_t)nclips * NBANDS * NCC_HBINS * sizeof(uint32_t), (cudaStream_t)stream));
+        ES_CUDA_OK(cudaMemsetAsync(nspec, 0, (size_t)nclips * NBANDS * sizeof(uint32_t), (cudaStream_t)stream));
+        ncc_kernel<true><<<grid, 256, smem, (cudaStream_t)stream>>>(y, n, nc, corr, aux);
+    } else {
+        ncc_kernel<false><<<grid, 256, smem, (cudaStream_t)stream>>>(y, n, nc, corr, aux);
+    }
     ES_CUDA_OK(cudaGetLastError());
     return ES_OK;
+}
+
+int es_rx_ncc(const double* y, int nclips, int n, double* corr, void* stream)
+{
+    return es_rx_ncc_hist(y, nclips, n, corr, nullptr, nullptr, nullptr, stream);
 }
 
 static int g_peaks_general = 0;
 void es_rx_peaks_force_general(int on) { g_peaks_general = on ? 1 : 0; }
 
-int es_rx_peaks(const double* corr, int nclips, int nc, int32_t* peaks, int32_t* npeaks, double* stats, void* stream)
+// hist / spec / nspec: the outputs of es_rx_ncc_hist for the same corr (all null: K3 makes its own first pass)
+int es_rx_peaks_hist(const double* corr, int nclips, int nc, const uint32_t* hist, const double* spec, const uint32_t* nspec,
+                     int32_t* peaks, int32_t* npeaks, double* stats, void* stream)
 {
     if (nclips <= 0) return ES_OK;
     int& configured = g_rxdev[current_device()].cfg[1];
@@ -1922,12 +1986,19 @@ int es_rx_peaks(const double* corr, int nclips, int nc, int32_t* peaks, int32_t*
         ES_CUDA_OK(cudaFuncSetAttribute(peaks2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PkUnion)));
         configured = 1;
     }
+    NccAux aux{const_cast<uint32_t*>(hist), const_cast<double*>(spec), const_cast<uint32_t*>(nspec)};
+    if (!(hist && spec && nspec)) aux = NccAux{nullptr, nullptr, nullptr};
     if (g_peaks_general)
         peaks_kernel<<<nclips * NBANDS, PK_THREADS, sizeof(PeakShared), (cudaStream_t)stream>>>(corr, nc, peaks, npeaks, stats);
     else
-        peaks2_kernel<<<nclips * NBANDS, PK_THREADS, sizeof(PkUnion), (cudaStream_t)stream>>>(corr, nc, peaks, npeaks, stats);
+        peaks2_kernel<<<nclips * NBANDS, PK_THREADS, sizeof(PkUnion), (cudaStream_t)stream>>>(corr, nc, peaks, npeaks, stats, aux);
     ES_CUDA_OK(cudaGetLastError());
     return ES_OK;
+}
+
+int es_rx_peaks(const double* corr, int nclips, int nc, int32_t* peaks, int32_t* npeaks, double* stats, void* stream)
+{
+    return es_rx_peaks_hist(corr, nclips, nc, nullptr, nullptr, nullptr, peaks, npeaks, stats, stream);
 }
 
 size_t es_rx_peaks_long_scratch_bytes(int nclips, int nc)

@@ -285,9 +285,9 @@ def verify_batch(keys, audio, *, fs_target: int = 48_000, list_size: int = 8, mf
         if not is_tensor:
             ring_free[slot_of[s0]] = torch.cuda.Event()
             ring_free[slot_of[s0]].record()                # x is only read by the band-pass
-        corr = rx_gpu.ncc(y)
-        sb.pk, sb.npk, sb.st = rx_gpu.peaks(corr)
-        del corr
+        corr, aux = rx_gpu.ncc(y, with_hist=True)              # K2 also forms K3's first pass (histogram + central bins)
+        sb.pk, sb.npk, sb.st = rx_gpu.peaks(corr, aux)
+        del corr, aux
         sb.fr = rx_gpu.frames(y, sb.pk, sb.npk, hdr_pn)
         del y
         sb.pk_h, sb.npk_h, sb.hdr_h = _pinned_like(sb.pk), _pinned_like(sb.npk), _pinned_like(sb.fr["hdr"])

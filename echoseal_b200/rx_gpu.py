@@ -80,19 +80,33 @@ def bandpass(x: torch.Tensor) -> torch.Tensor:
     return y
 
 
-def ncc(y: torch.Tensor) -> torch.Tensor:
-    """y float64[B,4,n] -> corr float64[B,4,n-62] (K2)."""
+K3_LONG_MIN = 1 << 21      # correlation length from which the multi-CTA form of K3 is used
+K3_TWO_PASS_MIN = 8192     # shorter rows take K3's general form, which does not use the producer's histogram
+NCC_SPEC_CAP = 6144
+
+
+def ncc(y: torch.Tensor, with_hist: bool = False):
+    """y float64[B,4,n] -> corr float64[B,4,n-62] (K2).  with_hist: also returns K3's first pass, formed while the
+    correlation values are at hand (es_rx_ncc_hist): (corr, aux) with aux = (hist u32[B*4,2048], central-bin values
+    f64[B*4,6144], their count u32[B*4]) for peaks(corr, aux) — or aux = None when the row length does not use it."""
     N.require_cuda(y)
     B, _, n = y.shape
     nc = max(0, n - (PRE_L - 1))
     corr = torch.empty((B, 4, nc), dtype=torch.float64, device=y.device)
+    aux = None
+    if with_hist and K3_TWO_PASS_MIN <= nc < K3_LONG_MIN:
+        aux = (torch.empty((B * 4, 2048), dtype=torch.int32, device=y.device),
+               torch.empty((B * 4, NCC_SPEC_CAP), dtype=torch.float64, device=y.device),
+               torch.empty((B * 4,), dtype=torch.int32, device=y.device))
     if nc > 0:
         with N.timed("ncc"):
-            N.check(N.lib().es_rx_ncc(N.ptr(y), C.c_int(B), C.c_int(n), N.ptr(corr), N.stream_ptr()), "es_rx_ncc")
-    return corr
+            if aux is None:
+                N.check(N.lib().es_rx_ncc(N.ptr(y), C.c_int(B), C.c_int(n), N.ptr(corr), N.stream_ptr()), "es_rx_ncc")
+            else:
+                N.check(N.lib().es_rx_ncc_hist(N.ptr(y), C.c_int(B), C.c_int(n), N.ptr(corr), N.ptr(aux[0]), N.ptr(aux[1]),
+                                               N.ptr(aux[2]), N.stream_ptr()), "es_rx_ncc_hist")
+    return (corr, aux) if with_hist else corr
 
-
-K3_LONG_MIN = 1 << 21      # correlation length from which the multi-CTA form of K3 is used
 
 
 def scan(x: torch.Tensor) -> torch.Tensor:
@@ -138,9 +152,10 @@ def peaks_force_general(on: bool):
     N.lib().es_rx_peaks_force_general(C.c_int(1 if on else 0))
 
 
-def peaks(corr: torch.Tensor):
+def peaks(corr: torch.Tensor, aux=None):
     """corr float64[B,4,nc] -> (peaks i32[B,4,25] (-1 padded), npeaks i32[B,4], stats f64[B,4,4] =
-    med, mad, thr, used_fallback) (K3).  Long recordings (nc >= 2^21) take the multi-CTA form."""
+    med, mad, thr, used_fallback) (K3).  Long recordings (nc >= 2^21) take the multi-CTA form.  aux: the second result of
+    ncc(y, with_hist=True) for this corr — K3 then reads corr once instead of twice."""
     N.require_cuda(corr)
     B, _, nc = corr.shape
     pk = torch.full((B, 4, PEAK_LIMIT), -1, dtype=torch.int32, device=corr.device)
@@ -160,8 +175,12 @@ def peaks(corr: torch.Tensor):
         if int(ovf.item()) == 0:
             return pk, npk, st
     with N.timed("peaks"):
-        N.check(N.lib().es_rx_peaks(N.ptr(corr), C.c_int(B), C.c_int(nc), N.ptr(pk), N.ptr(npk), N.ptr(st),
-                                    N.stream_ptr()), "es_rx_peaks")
+        if aux is not None and nc < K3_LONG_MIN:
+            N.check(N.lib().es_rx_peaks_hist(N.ptr(corr), C.c_int(B), C.c_int(nc), N.ptr(aux[0]), N.ptr(aux[1]), N.ptr(aux[2]),
+                                             N.ptr(pk), N.ptr(npk), N.ptr(st), N.stream_ptr()), "es_rx_peaks_hist")
+        else:
+            N.check(N.lib().es_rx_peaks(N.ptr(corr), C.c_int(B), C.c_int(nc), N.ptr(pk), N.ptr(npk), N.ptr(st),
+                                        N.stream_ptr()), "es_rx_peaks")
     return pk, npk, st
 
 

@@ -79,6 +79,10 @@ int es_rx_bandpass(const float* x /*[clips][x_stride]*/, int nclips, int n, long
 void es_rx_bandpass_force_plain(int on);
 /* K2: cosine-normalised preamble correlation (rtwm/detector.py:76-79) */
 int es_rx_ncc(const double* y, int nclips, int n, double* corr /*[clips][4][n-62]*/, void* stream);
+/* es_rx_ncc that also forms K3's first pass while the correlation values are at hand: per (clip, band) row the 2048-bin
+ * monotone histogram of corr (hist u32[rows][2048]) and the values of its six central bins (spec f64[rows][6144], count in
+ * nspec u32[rows]); es_rx_peaks_hist then reads corr once instead of twice.  rows = clips * 4. */
+int es_rx_ncc_hist(const double* y, int nclips, int n, double* corr, uint32_t* hist, double* spec, uint32_t* nspec, void* stream);
 /* K1+K2 fused (rtwm/detector.py:59-60,75-79): band-pass and normalised correlation in one pass, the filtered signal
  * stays on the SM.  Same chunk grid and arithmetic as es_rx_bandpass + es_rx_ncc; windows that cross a chunk boundary see
  * the filter's 4e-13 warm-up truncation on the far side.  corr f64 [clips][4][n-62]. */
@@ -87,6 +91,8 @@ int es_rx_scan(const float* x /*[clips][x_stride]*/, int nclips, int n, long lon
  * stats = med, mad, thr, used_fallback */
 int es_rx_peaks(const double* corr, int nclips, int nc, int32_t* peaks /*[clips][4][25]*/,
                 int32_t* npeaks /*[clips][4]*/, double* stats /*[clips][4][4]*/, void* stream);
+int es_rx_peaks_hist(const double* corr, int nclips, int nc, const uint32_t* hist, const double* spec, const uint32_t* nspec,
+                     int32_t* peaks, int32_t* npeaks, double* stats, void* stream);
 /* test hook: on != 0 makes es_rx_peaks run every row through the general multi-pass form instead of the two-pass
  * form (the two give identical results; tests compare them) */
 void es_rx_peaks_force_general(int on);

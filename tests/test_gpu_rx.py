@@ -614,3 +614,31 @@ def test_bandpass_tma_store_equals_plain_form(env):
             rx_gpu.bandpass_force_plain(False)
         assert bool((y == y0).all()), (B, n)
         assert bool(torch.isfinite(y).all())
+
+
+@pytest.mark.gpu
+def test_peaks_from_producer_histogram_equal_two_pass(env):
+    """K2 can form K3's first pass (2048-bin histogram + central-bin values) while it has the correlation values at hand
+    (es_rx_ncc_hist / es_rx_peaks_hist): peaks, counts and med / MAD / threshold bits equal K3's own two-pass form on the
+    detector clips, on adversarial rows (silence, plateaus, off-centre medians: rows whose speculation misses take the
+    general form either way) and on ragged lengths."""
+    torch, rx_gpu, detector, clips, taps = env
+    g = torch.Generator(device="cuda").manual_seed(3)
+    xs = [torch.from_numpy(clips[n_][0][None]).cuda() for n_ in NAMES]
+    xs.append((torch.randn((6, 144000), device="cuda", generator=g) * 0.05).contiguous())
+    adv = torch.zeros((4, 100000), device="cuda")
+    adv[1] = 0.2; adv[2, ::7] = 1.0; adv[3] = torch.randn(100000, device="cuda", generator=g) * 1e-4 + 0.5
+    xs.append(adv)
+    xs.append((torch.randn((3, 20011), device="cuda", generator=g) * 0.1).contiguous())
+    for x in xs:
+        y = rx_gpu.bandpass(x)
+        corr, aux = rx_gpu.ncc(y, with_hist=True)
+        if aux is None:                      # rows shorter than K3's two-pass form: nothing to hand over
+            assert corr.shape[2] < rx_gpu.K3_TWO_PASS_MIN
+            continue
+        corr0 = rx_gpu.ncc(y)
+        assert bool((corr == corr0).all())
+        a = rx_gpu.peaks(corr, aux)
+        b = rx_gpu.peaks(corr0)
+        for u, v in zip(a, b):
+            assert bool((u == v).all() if u.dtype != torch.float64 else ((u == v) | (torch.isnan(u) & torch.isnan(v))).all())
