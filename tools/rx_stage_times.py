@@ -24,8 +24,8 @@ def main():
         bank = T("KeyBank(keys)", lambda: KeyBank(keys))
         hdr_pn = T("hdr_pn->dev", lambda: torch.from_numpy(bank.hdr_pn(kidx)).to(dev))
         y = T("bandpass", lambda: rx_gpu.bandpass(clips))
-        corr = T("ncc", lambda: rx_gpu.ncc(y))
-        pk, npk, st = T("peaks", lambda: rx_gpu.peaks(corr))
+        corr, aux = T("ncc (+K3 first pass)", lambda: rx_gpu.ncc(y, with_hist=True))
+        pk, npk, st = T("peaks", lambda: rx_gpu.peaks(corr, aux))
         fr = T("frames", lambda: rx_gpu.frames(y, pk, npk, hdr_pn))
         del y
         corr_f = T("scan (K1+K2 fused)", lambda: rx_gpu.scan(clips))
