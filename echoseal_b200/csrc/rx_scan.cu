@@ -156,13 +156,22 @@ __global__ void __launch_bounds__(BP_WARPS * 32, BP_MIN_CTAS) bandpass_kernel(co
 // ---------------------------------------------------------------------------------------------
 struct BpTmaShared {
     double yout[2][NBANDS][32][8];          // 64-byte rows, 16-byte units XOR-swizzled with (row >> 1) & 3 (SWIZZLE_64B)
-    float xin[2][32][BP_STEP + 1];
+    union {
+        float xtile[2][32][BP_STEP];        // XTMA: input tiles as the tensor load delivers them (64-byte rows, same swizzle)
+        float xin[2][32][BP_STEP + 1];      // !XTMA: cp.async tiles, padded rows
+    };
+    unsigned long long bar[2];              // XTMA: one mbarrier per input stage
 };
 
-template <bool ODDZ>
+// XTMA: the INPUT tiles arrive through a tensor map of x as well (cp.async.bulk.tensor.3d, box [32 chunks][16 samples],
+// completion on an mbarrier): during the warm-up the box is taken from the tail of the previous chunk row (row -1 of a
+// clip is out of bounds: the hardware fills zeros, exactly the zero state the first chunk needs).
+template <bool ODDZ, bool XTMA>
 __global__ void __launch_bounds__(32, 10) bandpass_tma_kernel(const float* __restrict__ x, int nclips, int n, long long x_stride,
                                                               double* __restrict__ y, const __grid_constant__ CUtensorMap tmy,
-                                                              const __grid_constant__ CUtensorMap tmy31, int ch, int groups)
+                                                              const __grid_constant__ CUtensorMap tmy31,
+                                                              const __grid_constant__ CUtensorMap tmx,
+                                                              const __grid_constant__ CUtensorMap tmx31, int ch, int groups)
 {
     extern __shared__ __align__(1024) unsigned char bp_raw[];
     BpTmaShared& S = *reinterpret_cast<BpTmaShared*>(bp_raw);
@@ -182,7 +191,41 @@ __global__ void __launch_bounds__(32, 10) bandpass_tma_kernel(const float* __res
     const long long lim_ll = (long long)n - (long long)(chunk0 + 31) * ch;
     const int last_lim = lim_ll >= ch ? ch : (lim_ll < 0 ? 0 : (int)lim_ll);
     const int nsteps = (BP_WARM + ch + BP_STEP - 1) / BP_STEP;
-    auto fetch = [&](int st) {          // as bandpass_kernel: row r = chunk chunk0 + r, two rows per instruction
+    if (XTMA) {
+        if (lane == 0) {
+            const uint32_t b0 = (uint32_t)__cvta_generic_to_shared(&S.bar[0]);
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b0) : "memory");
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(b0 + 8u) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+    }
+    auto fetch = [&](int st) {
+        if (XTMA) {
+            // stage st = samples [rel0, rel0 + 16) of every chunk; before the chunk start they are the tail of the previous chunk row
+            const int rel0 = -BP_WARM + st * BP_STEP;
+            const int col = rel0 < 0 ? ch + rel0 : rel0;
+            const int row = rel0 < 0 ? chunk0 - 1 : chunk0;
+            const bool whole = rel0 < 0 || rel0 + BP_STEP <= last_lim;        // row 31 of the box lies inside the clip
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&S.xtile[st & 1][0][0]);
+            const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&S.bar[st & 1]);
+            if (lane == 0) {
+                const CUtensorMap* tm = whole ? &tmx : &tmx31;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(whole ? 2048u : 1984u) : "memory");
+                asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                             ::"r"(dst), "l"(tm), "r"(col), "r"(row), "r"(clip), "r"(bar) : "memory");
+            }
+            if (!whole && lane == 31) {         // the ragged last chunk: its valid samples by hand, zeros beyond the clip
+                const long long j0 = (long long)(chunk0 + 31) * ch + rel0;
+                for (int k = 0; k < BP_STEP; ++k) {
+                    const long long j = j0 + k;
+                    S.xtile[st & 1][31][((((k >> 2) ^ ((31 >> 1) & 3)) << 2) | (k & 3))] = (j < n) ? __ldg(xs + j) : 0.0f;
+                }
+            }
+            return;
+        }
+        // as bandpass_kernel: row r = chunk chunk0 + r, two rows per instruction
         const int rel = -BP_WARM + st * BP_STEP + (lane & 15);
         const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&S.xin[st & 1][lane >> 4][lane & 15]);
 #pragma unroll 8
@@ -201,7 +244,17 @@ __global__ void __launch_bounds__(32, 10) bandpass_tma_kernel(const float* __res
 #pragma unroll 1
     for (int st = 0; st < nsteps; ++st) {
         const int rel = -BP_WARM + st * BP_STEP;
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (XTMA) {
+            const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&S.bar[st & 1]);
+            const uint32_t parity = (uint32_t)(st >> 1) & 1u;
+            uint32_t ok;
+            do {
+                asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                             : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+            } while (!ok);
+        } else {
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
         __syncwarp();
         if (st + 1 < nsteps) fetch(st + 1);
         const float(*xin)[BP_STEP + 1] = S.xin[st & 1];
@@ -210,14 +263,24 @@ __global__ void __launch_bounds__(32, 10) bandpass_tma_kernel(const float* __res
             const int o0 = rel + q8 * 8;
             const bool emit = (o0 >= 0 && o0 < ch);
             const int set = tile & 1;
+            float xv[8];
+            if (XTMA) {
+                // floats 8 q8 .. 8 q8 + 7 of this lane's row: units 2 q8 and 2 q8 + 1, each at unit ^ ((lane >> 1) & 3)
+                const float4 a = *reinterpret_cast<const float4*>(&S.xtile[st & 1][lane][((2 * q8) ^ sw) << 2]);
+                const float4 b = *reinterpret_cast<const float4*>(&S.xtile[st & 1][lane][((2 * q8 + 1) ^ sw) << 2]);
+                xv[0] = a.x; xv[1] = a.y; xv[2] = a.z; xv[3] = a.w; xv[4] = b.x; xv[5] = b.y; xv[6] = b.z; xv[7] = b.w;
+            } else {
+#pragma unroll
+                for (int t = 0; t < 8; ++t) xv[t] = xin[lane][q8 * 8 + t];
+            }
             if (emit) {
                 // the stores issued from this set two tiles ago must have read it
                 if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                 __syncwarp();
             }
-#pragma unroll 2
+#pragma unroll
             for (int t = 0; t < 8; ++t) {
-                const double xn = (double)xin[lane][q8 * 8 + t];
+                const double xn = (double)xv[t];
 #pragma unroll
                 for (int bd = 0; bd < NBANDS; ++bd) {
                     const double yn = fma(c_bp_b[bd][0], xn, z[bd][0]);
@@ -1852,8 +1915,9 @@ static EncodeTiledFn tensor_map_encoder()
     return fn;
 }
 
-static int g_bp_force_plain = 0;
-void es_rx_bandpass_force_plain(int on) { g_bp_force_plain = on ? 1 : 0; }      // tests: the non-TMA form on the same chunk grid
+static int g_bp_force_plain = 0, g_bp_force_cpasync = 0;
+// tests: 1 = the non-TMA form on the same chunk grid; 2 = TMA stores but cp.async input tiles; 0 = default
+void es_rx_bandpass_force_plain(int on) { g_bp_force_plain = (on == 1) ? 1 : 0; g_bp_force_cpasync = (on == 2) ? 1 : 0; }
 
 int es_rx_bandpass(const float* x, int nclips, int n, long long x_stride, double* y, void* stream)
 {
@@ -1881,18 +1945,44 @@ int es_rx_bandpass(const float* x, int nclips, int n, long long x_stride, double
         if (r == CUDA_SUCCESS)
             r = enc(&tm31, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, (void*)y, dims, strides, box31, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                     CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        // x as a 3-d tensor (sample in chunk, chunk, clip) when its rows are 16-byte aligned: the input tiles come by TMA too
+        CUtensorMap tmx, tmx31;
+        // (the warm-up box is the tail of ONE previous chunk row: chunks at least as long as the warm-up)
+        bool xtma = r == CUDA_SUCCESS && ((reinterpret_cast<uintptr_t>(x) & 15u) == 0) && ((x_stride & 3) == 0) && ch >= BP_WARM;
+        if (xtma) {
+            const cuuint64_t xdims[3] = {(cuuint64_t)ch, nchunks, (cuuint64_t)nclips};
+            const cuuint64_t xstrides[2] = {(cuuint64_t)ch * 4u, (cuuint64_t)x_stride * 4u};
+            const cuuint32_t xbox[3] = {BP_STEP, 32, 1}, xbox31[3] = {BP_STEP, 31, 1};
+            const cuuint32_t xe[3] = {1, 1, 1};
+            CUresult rx = enc(&tmx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)x, xdims, xstrides, xbox, xe, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (rx == CUDA_SUCCESS)
+                rx = enc(&tmx31, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)x, xdims, xstrides, xbox31, xe, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            xtma = (rx == CUDA_SUCCESS) && !g_bp_force_cpasync;
+        }
+        if (!xtma) { tmx = tm; tmx31 = tm31; }
         if (r == CUDA_SUCCESS) {
             int& configured = g_rxdev[current_device()].cfg[5];
             if (!configured) {
-                ES_CUDA_OK(cudaFuncSetAttribute(bandpass_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BpTmaShared) + 1024));
-                ES_CUDA_OK(cudaFuncSetAttribute(bandpass_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BpTmaShared) + 1024));
-                ES_CUDA_OK(cudaFuncSetAttribute(bandpass_tma_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-                ES_CUDA_OK(cudaFuncSetAttribute(bandpass_tma_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+                const void* fns[4] = {(const void*)bandpass_tma_kernel<false, false>, (const void*)bandpass_tma_kernel<false, true>,
+                                      (const void*)bandpass_tma_kernel<true, false>, (const void*)bandpass_tma_kernel<true, true>};
+                for (int i = 0; i < 4; ++i) {
+                    ES_CUDA_OK(cudaFuncSetAttribute(fns[i], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(BpTmaShared) + 1024));
+                    ES_CUDA_OK(cudaFuncSetAttribute(fns[i], cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+                }
                 configured = 1;
             }
             const size_t smem = sizeof(BpTmaShared);
-            if (g_bp_oddz) bandpass_tma_kernel<true><<<(unsigned)warps, 32, smem, (cudaStream_t)stream>>>(x, nclips, n, x_stride, y, tm, tm31, ch, groups);
-            else bandpass_tma_kernel<false><<<(unsigned)warps, 32, smem, (cudaStream_t)stream>>>(x, nclips, n, x_stride, y, tm, tm31, ch, groups);
+            const unsigned gw = (unsigned)warps;
+            cudaStream_t st = (cudaStream_t)stream;
+            if (g_bp_oddz) {
+                if (xtma) bandpass_tma_kernel<true, true><<<gw, 32, smem, st>>>(x, nclips, n, x_stride, y, tm, tm31, tmx, tmx31, ch, groups);
+                else bandpass_tma_kernel<true, false><<<gw, 32, smem, st>>>(x, nclips, n, x_stride, y, tm, tm31, tmx, tmx31, ch, groups);
+            } else {
+                if (xtma) bandpass_tma_kernel<false, true><<<gw, 32, smem, st>>>(x, nclips, n, x_stride, y, tm, tm31, tmx, tmx31, ch, groups);
+                else bandpass_tma_kernel<false, false><<<gw, 32, smem, st>>>(x, nclips, n, x_stride, y, tm, tm31, tmx, tmx31, ch, groups);
+            }
             ES_CUDA_OK(cudaGetLastError());
             return ES_OK;
         }

@@ -606,13 +606,17 @@ def test_bandpass_tma_store_equals_plain_form(env):
     g = torch.Generator(device="cuda").manual_seed(11)
     for B, n in [(1, 144000), (5, 144000), (3, 288000), (2, 48000), (2, 143999), (2, 147456), (1, 100002), (3, 2000), (1, 1000000)]:
         x = (torch.randn((B, n), device="cuda", generator=g) * 0.1).contiguous()
-        y = rx_gpu.bandpass(x)
-        rx_gpu.bandpass_force_plain(True)
+        import ctypes as C
+        from echoseal_b200 import _native as N
+        y = rx_gpu.bandpass(x)                         # TMA tensor loads and stores where the shapes allow
         try:
-            y0 = rx_gpu.bandpass(x)
+            N.lib().es_rx_bandpass_force_plain(C.c_int(1))
+            y0 = rx_gpu.bandpass(x)                    # plain form
+            N.lib().es_rx_bandpass_force_plain(C.c_int(2))
+            y2 = rx_gpu.bandpass(x)                    # TMA stores, cp.async input tiles
         finally:
-            rx_gpu.bandpass_force_plain(False)
-        assert bool((y == y0).all()), (B, n)
+            N.lib().es_rx_bandpass_force_plain(C.c_int(0))
+        assert bool((y == y0).all()) and bool((y2 == y0).all()), (B, n)
         assert bool(torch.isfinite(y).all())
 
 
