@@ -1,25 +1,29 @@
-// echoseal_b200/csrc/scl.cu — batched CRC-aided SCL decoder for Polar(1024,K)+CRC-8, list size <= 8,
-// and the matching encoder, hand-written for sm_100a.
+// echoseal_b200/csrc/scl.cu — batched CRC-aided SCL decoder for Polar(1024,K)+CRC-8 (list size <= 8 at full speed,
+// 9..32 on the wide-list kernel), the hard-decision fast path and the matching encoder, hand-written for sm_100a.
 //
 // Replaces rtwm/fastpolar.py:254-359 (PolarCode.decode), :237-252 (encode), :362-389 (CRC-8, transform)
-// behind rtwm/polar_fast.py:26-87.  Arithmetic is IEEE double with the reference's exact formulas:
-//   f = logaddexp(a,b) - logaddexp(0,a+b)          (rtwm/fastpolar.py:18-23; LLR = log P1/P0)
+// behind rtwm/polar_fast.py:26-87.  Arithmetic is IEEE double with the reference's formulas:
+//   f = logaddexp(a,b) - logaddexp(0,a+b)          (rtwm/fastpolar.py:18-23; LLR = log P1/P0), evaluated as
+//       psi(a-b) - psi(a+b), psi(x) = |x|/2 + log1p(exp(-|x|))   (the same quantity)
 //   g = b + (1-2u) a                                (rtwm/fastpolar.py:26-29)
 //   penalty(l,bit) = log1p(exp(-|l|)) (+|l| if bit != [l>=0])   (rtwm/fastpolar.py:32-40)
 //   frozen bits are penalised too; candidates are ranked by (metric, path order, bit) = the reference's
 //   stable sort over candidates appended in (path idx, bit 0, bit 1) order (rtwm/fastpolar.py:288-299).
 //
-// Mapping (B200-first):
-//   * one THREAD per list path, 8 lanes per codeword, 4 codewords per warp, 4 warps per CTA,
-//     persistent grid sized to the SM count x resident CTAs;  warps never wait on each other.
-//   * LLR tree: level l (1..10) keeps only its CURRENT node (2^(10-l) doubles) per path slot.
-//     levels >= S live in shared memory, levels < S in an L2-resident global scratch, both laid out
-//     [element][codeword(4)][slot(8)] so a warp access is one 256-byte row (conflict-free / coalesced).
+// Mapping of scl_list_kernel (B200-first):
+//   * one THREAD per list path, 8 lanes per codeword, 4 codewords per warp, 16 warps per CTA, one persistent CTA per SM;
+//     warps never wait on each other.
+//   * LLR tree: level l (1..10) keeps only its CURRENT node (2^(10-l) doubles) per path slot.  Levels 9..10 live in
+//     registers, levels S..8 in shared memory, levels < S in a global scratch [element][codeword(4)][slot(8)] (one
+//     256-byte row per element, quarter-interleaved) that is streamed through a TMA bulk-copy ring (cp.async.bulk +
+//     mbarrier); levels 1..2 carry an L2 evict_first policy.
 //   * lazy copy without reference counts: every path rewrites a level at the same bit index, so a path
 //     always writes its OWN slot and a clone only copies a 30-bit word of per-level slot pointers.
 //   * partial sums are bit-packed: levels 6..10 in one register, levels 1..5 as pointer-indirected
-//     32-bit words; the root (codeword estimate) is transformed back to u-hat at the end.
-//   * list pruning: 16 candidates ranked with 8-wide warp shuffles; survivors/clones matched by ballots.
+//     32-bit words; the root (codeword estimate) is transformed back to u-hat at the end and its un-frozen bits are
+//     bit-compressed into the payload.
+//   * list pruning: 16 candidates ranked through unique 64-bit integer keys exchanged in shared memory;
+//     survivors/clones matched by ballots.
 #include "common.cuh"
 #include <math_constants.h>
 #include <string.h>
