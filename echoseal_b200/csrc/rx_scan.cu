@@ -1,8 +1,9 @@
 // echoseal_b200/csrc/rx_scan.cu — RX scan stages of the detector, hand-written for sm_100a:
-//   K1  es_rx_bandpass : 4 x order-8 Butterworth band-pass, fp64, chunked with zero-state warm-up
+//   K1  es_rx_bandpass : 4 x order-8 Butterworth band-pass, fp64, chunked with zero-state warm-up; tiles move through
+//                        TMA tensor maps (cp.async.bulk.tensor loads + stores) where the shapes allow
 //                        (rtwm/detector.py:59-60  scipy.signal.lfilter(b, a, x.astype(float32)))
-//   K2  es_rx_ncc      : cosine-normalised 63-tap preamble correlation, fp64
-//                        (rtwm/detector.py:76-79)
+//   K2  es_rx_ncc      : cosine-normalised 63-tap preamble correlation, fp64 (rtwm/detector.py:76-79);
+//                        es_rx_ncc_hist also forms K3's first pass; es_rx_scan = K1+K2 fused (measured alternative)
 //   K3  es_rx_peaks    : exact median / MAD threshold, +-607 non-max suppression, first 25 peaks,
 //                        top-5 fallback (rtwm/detector.py:83-99, 107-110)
 //   K4  es_rx_frames   : per peak: header decode (rtwm/detector.py:452-515) and the PN-independent
